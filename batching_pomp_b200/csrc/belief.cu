@@ -1,0 +1,489 @@
+// belief.cu — the C-space belief model: cspacebelief::KNNModel
+// (/root/reference/include/batching_pomp/cspacebelief/KNNModel.hpp:56-134, BeliefPoint.hpp:43-71,
+// beliefDistanceFunction src/BatchingPOMP.cpp:213-219) and computeAndSetEdgeFreeProbability
+// (src/BatchingPOMP.cpp:464-493) as batched device operators.
+//
+// kNN is exact brute force over the append-only point set, tiled through shared memory:
+// one thread per query, a (distance, insertion index)-ordered top-k list per thread in shared
+// memory, the point set split into chunks across blocks and merged afterwards.  Ordering and
+// summation are sequential in ascending (distance, insertion index), as the CPU oracle defines
+// them, so results are bit-equal to the oracle and within 1e-12 relative of
+// the reference's Eigen-packetised sums.
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+#define BK_QB 128    // queries (threads) per block
+#define BK_TILE 256  // belief points staged per tile
+#define BK_KMAX 32   // largest supported k
+
+extern "C" int bpomp_belief_config(bpomp_ctx* ctx, int k, double prior, double prior_weight) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (k < 1 || k > BK_KMAX) return bp_fail(ctx, BPOMP_ERR_INVALID, "k must be in 1..%d", BK_KMAX);
+  ctx->knn = k;
+  ctx->prior = prior;
+  ctx->prior_weight = prior_weight;
+  return BPOMP_OK;
+}
+
+extern "C" int bpomp_belief_size(bpomp_ctx* ctx, uint64_t* count) {
+  if (!ctx || !count) return BPOMP_ERR_INVALID;
+  *count = ctx->bel_count;
+  return BPOMP_OK;
+}
+
+extern "C" int bpomp_belief_clear(bpomp_ctx* ctx) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  ctx->bel_count = 0;
+  return BPOMP_OK;
+}
+
+static int belief_grow(bpomp_ctx* ctx, uint64_t extra) {
+  uint64_t need = ctx->bel_count + extra;
+  BP_TRY(bp_reserve(ctx, ctx->d_bel_pts, (size_t)need * ctx->dim * sizeof(double), true));
+  BP_TRY(bp_reserve(ctx, ctx->d_bel_vals, (size_t)need * sizeof(double), true));
+  return BPOMP_OK;
+}
+
+extern "C" int bpomp_belief_append(bpomp_ctx* ctx, const double* states, const double* values, int64_t count) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (count < 0 || (count > 0 && (!states || !values))) return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
+  if (count == 0) return BPOMP_OK;
+  BP_TRY(belief_grow(ctx, (uint64_t)count));
+  size_t row = (size_t)ctx->dim * sizeof(double);
+  BP_CUDA(ctx, cudaMemcpyAsync((char*)ctx->d_bel_pts.p + ctx->bel_count * row, states, (size_t)count * row,
+                               cudaMemcpyHostToDevice, ctx->stream));
+  BP_CUDA(ctx, cudaMemcpyAsync(ctx->d_bel_vals.as<double>() + ctx->bel_count, values, (size_t)count * sizeof(double),
+                               cudaMemcpyHostToDevice, ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->bel_count += (uint64_t)count;
+  return BPOMP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Edge geometry helpers shared by append_checked and edge_pfree
+// ---------------------------------------------------------------------------
+struct EdgeSrc {
+  const double* from;        // explicit [count][D] or null
+  const double* to;
+  const uint32_t* from_ids;  // indexed or null
+  const uint32_t* to_ids;
+  const double* verts;
+};
+
+template <int D>
+__device__ __forceinline__ void bk_load(const EdgeSrc& s, int64_t e, double* f, double* t) {
+  const double* pf = s.from_ids ? s.verts + (size_t)s.from_ids[e] * D : s.from + (size_t)e * D;
+  const double* pt = s.to_ids ? s.verts + (size_t)s.to_ids[e] * D : s.to + (size_t)e * D;
+#pragma unroll
+  for (int j = 0; j < D; ++j) { f[j] = pf[j]; t[j] = pt[j]; }
+}
+
+// mode 0: number of belief queries of computeAndSetEdgeFreeProbability (BP.cpp:475)
+// mode 1: number of states checkAndSetEdgeBlocked appends to the model (BP.cpp:510-537)
+template <int D>
+__global__ void __launch_bounds__(256) bk_count_kernel(EdgeSrc src, int64_t count, double L, PermView pv, int mode,
+                                                       const int32_t* __restrict__ first_invalid,
+                                                       uint32_t* __restrict__ nst, uint32_t* __restrict__ cnt) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) {
+    double f[D], t[D];
+    bk_load<D>(src, e, f, t);
+    uint32_t n = bp_nstates(__dsqrt_rn(bp_dist2<D>(f, t)), L);
+    uint32_t c = 0;
+    if (n == 0u) {
+      atomicAdd(pv.flags + 1, 1);
+      n = 2u;
+    }
+    if (n > 2u) {
+      if (__ldg(pv.off + n) == BP_ABSENT) {
+        pv.need[n] = 1;
+        atomicAdd(pv.flags, 1);
+      }
+      if (mode == 0) {
+        uint32_t step = __ldg(pv.step + n);  // (unsigned)(n / log(n)), BP.cpp:472
+        c = (n - 2u + step - 1u) / step;      // i = 1, 1+step, ... < n-1
+      } else {
+        int32_t fi = first_invalid[e];
+        c = fi >= 1 ? (uint32_t)fi : n - 2u;
+      }
+    }
+    nst[e] = n;
+    cnt[e] = c;
+  }
+}
+
+// Writes the states of the selected slots of every edge: mode 0 -> query states (slots 1, 1+step, ..),
+// mode 1 -> checked states (slots 1..cnt) plus their belief values.
+template <int D>
+__global__ void __launch_bounds__(256) bk_expand_kernel(EdgeSrc src, int64_t count, PermView pv, int mode,
+                                                        const int32_t* __restrict__ first_invalid,
+                                                        const uint32_t* __restrict__ nst,
+                                                        const uint64_t* __restrict__ offs, double* __restrict__ out,
+                                                        double* __restrict__ out_vals) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t o = offs[e];
+    uint32_t c = (uint32_t)(offs[e + 1] - o);
+    if (c == 0) continue;
+    double f[D], t[D], dtf[D];
+    bk_load<D>(src, e, f, t);
+#pragma unroll
+    for (int j = 0; j < D; ++j) dtf[j] = __dsub_rn(t[j], f[j]);
+    uint32_t n = nst[e];
+    const double* tf = pv.tfrac + __ldg(pv.off + n);
+    uint32_t step = mode == 0 ? __ldg(pv.step + n) : 1u;
+    bool blocked = mode == 1 && first_invalid[e] >= 1;
+    for (uint32_t k = 0; k < c; ++k) {
+      double tt = __ldg(tf + 1u + k * step);
+#pragma unroll
+      for (int j = 0; j < D; ++j) out[(o + k) * D + j] = __dadd_rn(f[j], __dmul_rn(dtf[j], tt));
+      if (mode == 1) out_vals[o + k] = (blocked && k + 1 == c) ? 1.0 : 0.0;  // BP.cpp:525 / :535
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// kNN: partial top-k per (query, point chunk)
+// ---------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(BK_QB) bk_knn_partial(const double* __restrict__ queries, int64_t nq,
+                                                        const double* __restrict__ pts, uint64_t M, uint64_t chunk,
+                                                        int K, double* __restrict__ part_d,
+                                                        uint32_t* __restrict__ part_i) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double* s_pts = reinterpret_cast<double*>(smem);                                  // [BK_TILE][D]
+  double* s_kd = s_pts + BK_TILE * D;                                               // [K][BK_QB]
+  uint32_t* s_ki = reinterpret_cast<uint32_t*>(s_kd + (size_t)K * BK_QB);           // [K][BK_QB]
+  const int tid = threadIdx.x;
+  const int64_t qi = (int64_t)blockIdx.x * BK_QB + tid;
+  const uint64_t p_begin = (uint64_t)blockIdx.y * chunk;
+  const uint64_t p_end = p_begin + chunk < M ? p_begin + chunk : M;
+  double q[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) q[j] = qi < nq ? queries[qi * D + j] : 0.0;
+  int cnt = 0;
+  double worst = DBL_MAX, thr = DBL_MAX;  // worst distance in a full list; d2 prefilter threshold
+  for (uint64_t base = p_begin; base < p_end; base += BK_TILE) {
+    uint32_t tn = (uint32_t)((p_end - base) < BK_TILE ? (p_end - base) : BK_TILE);
+    __syncthreads();
+    for (uint32_t i = tid; i < tn * D; i += BK_QB) s_pts[i] = pts[base * D + i];
+    __syncthreads();
+    if (qi >= nq) continue;
+    for (uint32_t p = 0; p < tn; ++p) {
+      double d2 = 0.0;
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        double diff = __dsub_rn(q[j], s_pts[p * D + j]);
+        d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
+      }
+      if (cnt == K && d2 > thr) continue;
+      double dist = __dsqrt_rn(d2);
+      if (cnt == K && !(dist < worst)) continue;  // an equidistant later point never displaces (GNAT)
+      // insert after every entry with distance <= dist (indices ascend within the scan)
+      int pos = cnt < K ? cnt : K - 1;
+      while (pos > 0 && s_kd[(pos - 1) * BK_QB + tid] > dist) {
+        s_kd[pos * BK_QB + tid] = s_kd[(pos - 1) * BK_QB + tid];
+        s_ki[pos * BK_QB + tid] = s_ki[(pos - 1) * BK_QB + tid];
+        --pos;
+      }
+      s_kd[pos * BK_QB + tid] = dist;
+      s_ki[pos * BK_QB + tid] = (uint32_t)(base + p);
+      if (cnt < K) ++cnt;
+      if (cnt == K) {
+        worst = s_kd[(K - 1) * BK_QB + tid];
+        thr = __dmul_rn(__dmul_rn(worst, worst), 1.0 + 8.881784197001252e-16);  // conservative
+      }
+    }
+  }
+  if (qi < nq) {
+    double* od = part_d + ((size_t)blockIdx.y * nq + qi) * K;
+    uint32_t* oi = part_i + ((size_t)blockIdx.y * nq + qi) * K;
+    for (int k = 0; k < K; ++k) {
+      od[k] = k < cnt ? s_kd[k * BK_QB + tid] : DBL_MAX;
+      oi[k] = k < cnt ? s_ki[k * BK_QB + tid] : 0xFFFFFFFFu;
+    }
+  }
+}
+
+// Merge the P partial lists of each query and evaluate KNNModel::estimate (KNNModel.hpp:101-134).
+__global__ void __launch_bounds__(128) bk_merge_estimate(int64_t nq, int P, int K, uint64_t M,
+                                                         const double* __restrict__ part_d,
+                                                         const uint32_t* __restrict__ part_i,
+                                                         const double* __restrict__ vals, double prior,
+                                                         double prior_weight, double* __restrict__ out) {
+  for (int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; qi < nq; qi += (int64_t)gridDim.x * blockDim.x) {
+    if (M == 0) {  // KNNModel.hpp:104-106
+      out[qi] = prior;
+      continue;
+    }
+    int knn = (uint64_t)K < M ? K : (int)M;  // :108
+    unsigned char head[64];
+    for (int p = 0; p < P; ++p) head[p] = 0;
+    double dot = 0.0, wsum = 0.0;
+    for (int k = 0; k < knn; ++k) {
+      int best = -1;
+      double bd = 0.0;
+      uint32_t bi = 0;
+      for (int p = 0; p < P; ++p) {
+        if (head[p] >= K) continue;
+        size_t o = ((size_t)p * nq + qi) * K + head[p];
+        uint32_t ci = part_i[o];
+        if (ci == 0xFFFFFFFFu) continue;
+        double cd = part_d[o];
+        if (best < 0 || cd < bd || (cd == bd && ci < bi)) { best = p; bd = cd; bi = ci; }
+      }
+      if (best < 0) break;
+      head[best]++;
+      double distance = fmax(0.0001, bd);       // :121
+      double w = __ddiv_rn(1.0, distance);      // :122
+      double v = vals[bi];                      // :123
+      dot = __dadd_rn(dot, __dmul_rn(w, v));    // weights.dot(values), sequential
+      wsum = __dadd_rn(wsum, w);                // weights.sum()
+    }
+    double result = __ddiv_rn(dot, wsum);                                                   // :127
+    result = __ddiv_rn(__dadd_rn(result, __dmul_rn(prior_weight, prior)), __dadd_rn(1.0, prior_weight));  // :130
+    out[qi] = result;
+  }
+}
+
+// pfree[e] = prod (1 - est) over the edge's queries, in slot order (BP.cpp:473-488)
+__global__ void __launch_bounds__(256) bk_product_kernel(int64_t count, const uint64_t* __restrict__ offs,
+                                                         const double* __restrict__ est, double* __restrict__ pfree,
+                                                         uint32_t* __restrict__ nlook) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t o = offs[e], c = offs[e + 1] - o;
+    double r = 1.0;
+    for (uint64_t k = 0; k < c; ++k) r = __dmul_rn(r, __dsub_rn(1.0, est[o + k]));
+    pfree[e] = r;
+    if (nlook) nlook[e] = (uint32_t)c;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Host drivers
+// ---------------------------------------------------------------------------
+template <int D>
+static int knn_estimate_dev(bpomp_ctx* ctx, const double* d_queries, int64_t nq, double* d_out, DevBuf& bd, DevBuf& bi) {
+  if (nq <= 0) return BPOMP_OK;
+  const uint64_t M = ctx->bel_count;
+  const int K = ctx->knn;
+  int P = 1;
+  uint64_t chunk = M ? M : 1;
+  if (M > 0) {
+    int64_t qblocks = (nq + BK_QB - 1) / BK_QB;
+    int64_t want = 2 * (int64_t)ctx->num_sms;
+    while (qblocks * P < want && P < 64 && (M + (2 * P) - 1) / (2 * P) >= 1024) P *= 2;
+    chunk = (M + P - 1) / P;
+    chunk = (chunk + BK_TILE - 1) / BK_TILE * BK_TILE;
+    P = (int)((M + chunk - 1) / chunk);
+    BP_TRY(bp_reserve(ctx, bd, (size_t)P * nq * K * sizeof(double), false));
+    BP_TRY(bp_reserve(ctx, bi, (size_t)P * nq * K * sizeof(uint32_t), false));
+    size_t sm = (size_t)BK_TILE * D * sizeof(double) + (size_t)K * BK_QB * (sizeof(double) + sizeof(uint32_t));
+    auto kern = bk_knn_partial<D>;
+    BP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    dim3 grid((unsigned)((nq + BK_QB - 1) / BK_QB), (unsigned)P);
+    kern<<<grid, BK_QB, sm, ctx->stream>>>(d_queries, nq, ctx->d_bel_pts.as<double>(), M, chunk, K, bd.as<double>(),
+                                           bi.as<uint32_t>());
+    ctx->launches++;
+    BP_CUDA(ctx, cudaGetLastError());
+  }
+  int gm = (int)std::min<int64_t>((nq + 127) / 128, (int64_t)ctx->num_sms * 8);
+  bk_merge_estimate<<<gm, 128, 0, ctx->stream>>>(nq, P, K, M, bd.as<double>(), bi.as<uint32_t>(),
+                                                 ctx->d_bel_vals.as<double>(), ctx->prior, ctx->prior_weight, d_out);
+  ctx->launches++;
+  BP_CUDA(ctx, cudaGetLastError());
+  return BPOMP_OK;
+}
+
+static int knn_estimate_dispatch(bpomp_ctx* ctx, const double* d_q, int64_t nq, double* d_out, DevBuf& bd, DevBuf& bi) {
+  switch (ctx->dim) {
+    case 1: return knn_estimate_dev<1>(ctx, d_q, nq, d_out, bd, bi);
+    case 2: return knn_estimate_dev<2>(ctx, d_q, nq, d_out, bd, bi);
+    case 3: return knn_estimate_dev<3>(ctx, d_q, nq, d_out, bd, bi);
+    case 4: return knn_estimate_dev<4>(ctx, d_q, nq, d_out, bd, bi);
+    case 5: return knn_estimate_dev<5>(ctx, d_q, nq, d_out, bd, bi);
+    case 6: return knn_estimate_dev<6>(ctx, d_q, nq, d_out, bd, bi);
+    case 7: return knn_estimate_dev<7>(ctx, d_q, nq, d_out, bd, bi);
+    case 8: return knn_estimate_dev<8>(ctx, d_q, nq, d_out, bd, bi);
+  }
+  return bp_fail(ctx, BPOMP_ERR_INVALID, "unsupported dim %d", ctx->dim);
+}
+
+extern "C" int bpomp_belief_estimate(bpomp_ctx* ctx, const double* queries, int64_t nq, double* out) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (nq < 0 || (nq > 0 && (!queries || !out))) return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
+  if (nq == 0) return BPOMP_OK;
+  size_t bytes = (size_t)nq * ctx->dim * sizeof(double);
+  BP_TRY(bp_reserve(ctx, ctx->s_a, bytes, false));
+  BP_TRY(bp_reserve(ctx, ctx->s_b, (size_t)nq * sizeof(double), false));
+  BP_CUDA(ctx, cudaMemcpyAsync(ctx->s_a.p, queries, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  BP_TRY(knn_estimate_dispatch(ctx, ctx->s_a.as<double>(), nq, ctx->s_b.as<double>(), ctx->s_c, ctx->s_d));
+  BP_CUDA(ctx, cudaMemcpyAsync(out, ctx->s_b.p, (size_t)nq * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BPOMP_OK;
+}
+
+// count pass + scan + (resolve missing sample orders); leaves nst in s_e, offsets in s_g
+template <int D>
+static int edges_count_scan(bpomp_ctx* ctx, const EdgeSrc& src, int64_t count, int mode, const int32_t* d_first,
+                            uint64_t* total) {
+  BP_TRY(bp_reserve(ctx, ctx->s_e, (size_t)count * sizeof(uint32_t), false));
+  BP_TRY(bp_reserve(ctx, ctx->s_f, (size_t)count * sizeof(uint32_t), false));
+  BP_TRY(bp_reserve(ctx, ctx->s_g, ((size_t)count + 1) * sizeof(uint64_t), false));
+  int grid = (int)std::min<int64_t>((count + 255) / 256, (int64_t)ctx->num_sms * 8);
+  bk_count_kernel<D><<<grid, 256, 0, ctx->stream>>>(src, count, ctx->L, ctx->perm_view(), mode, d_first,
+                                                   ctx->s_e.as<uint32_t>(), ctx->s_f.as<uint32_t>());
+  ctx->launches++;
+  BP_CUDA(ctx, cudaGetLastError());
+  BP_TRY(bp_exclusive_scan_u32(ctx, ctx->s_f.as<uint32_t>(), (uint64_t)count, ctx->s_g.as<uint64_t>(), ctx->s_scan));
+  BP_CUDA(ctx, cudaMemcpyAsync(total, ctx->s_g.as<uint64_t>() + count, sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                               ctx->stream));
+  BP_TRY(bp_read_flags(ctx));
+  if (ctx->h_flags[1]) {
+    ctx->h_flags[1] = 0;
+    ctx->h_flags[0] = 0;
+    return bp_fail(ctx, BPOMP_ERR_RANGE, "an edge has more than %u states (segment_length too small)",
+                   BPOMP_NSTATES_MAX);
+  }
+  if (ctx->h_flags[0]) {
+    ctx->h_flags[0] = 0;
+    std::vector<uint8_t> need((size_t)BPOMP_NSTATES_MAX + 1);
+    BP_CUDA(ctx, cudaMemcpyAsync(need.data(), ctx->d_need.p, need.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    BP_CUDA(ctx, cudaMemsetAsync(ctx->d_need.p, 0, need.size(), ctx->stream));
+    std::vector<uint32_t> ns;
+    for (uint32_t n = 2; n <= BPOMP_NSTATES_MAX; ++n)
+      if (need[n]) ns.push_back(n);
+    BP_TRY(bp_perm_ensure_rows(ctx, ns));
+  }
+  return BPOMP_OK;
+}
+
+template <int D>
+static int edge_pfree_impl(bpomp_ctx* ctx, const EdgeSrc& src, int64_t count, double* pfree, uint32_t* nlookups) {
+  uint64_t nq = 0;
+  BP_TRY(edges_count_scan<D>(ctx, src, count, 0, nullptr, &nq));
+  int grid = (int)std::min<int64_t>((count + 255) / 256, (int64_t)ctx->num_sms * 8);
+  // query states -> s_c, estimates -> s_d, kNN partial lists -> s_i / s_j, results -> s_h
+  BP_TRY(bp_reserve(ctx, ctx->s_c, (size_t)(nq + 1) * D * sizeof(double), false));
+  BP_TRY(bp_reserve(ctx, ctx->s_d, (size_t)(nq + 1) * sizeof(double), false));
+  if (nq > 0) {
+    bk_expand_kernel<D><<<grid, 256, 0, ctx->stream>>>(src, count, ctx->perm_view(), 0, nullptr, ctx->s_e.as<uint32_t>(),
+                                                      ctx->s_g.as<uint64_t>(), ctx->s_c.as<double>(), nullptr);
+    ctx->launches++;
+    BP_CUDA(ctx, cudaGetLastError());
+    BP_TRY(knn_estimate_dispatch(ctx, ctx->s_c.as<double>(), (int64_t)nq, ctx->s_d.as<double>(), ctx->s_i, ctx->s_j));
+  }
+  BP_TRY(bp_reserve(ctx, ctx->s_h, (size_t)count * (sizeof(double) + sizeof(uint32_t)), false));
+  double* d_pf = ctx->s_h.as<double>();
+  uint32_t* d_nl = reinterpret_cast<uint32_t*>(d_pf + count);
+  bk_product_kernel<<<grid, 256, 0, ctx->stream>>>(count, ctx->s_g.as<uint64_t>(), ctx->s_d.as<double>(), d_pf, d_nl);
+  ctx->launches++;
+  BP_CUDA(ctx, cudaGetLastError());
+  BP_CUDA(ctx, cudaMemcpyAsync(pfree, d_pf, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (nlookups)
+    BP_CUDA(ctx, cudaMemcpyAsync(nlookups, d_nl, (size_t)count * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BPOMP_OK;
+}
+
+template <int D>
+static int append_checked_impl(bpomp_ctx* ctx, const EdgeSrc& src, int64_t count, const int32_t* d_first) {
+  uint64_t total = 0;
+  BP_TRY(edges_count_scan<D>(ctx, src, count, 1, d_first, &total));
+  if (total == 0) return BPOMP_OK;
+  BP_TRY(belief_grow(ctx, total));
+  int grid = (int)std::min<int64_t>((count + 255) / 256, (int64_t)ctx->num_sms * 8);
+  bk_expand_kernel<D><<<grid, 256, 0, ctx->stream>>>(src, count, ctx->perm_view(), 1, d_first, ctx->s_e.as<uint32_t>(),
+                                                    ctx->s_g.as<uint64_t>(),
+                                                    ctx->d_bel_pts.as<double>() + ctx->bel_count * D,
+                                                    ctx->d_bel_vals.as<double>() + ctx->bel_count);
+  ctx->launches++;
+  BP_CUDA(ctx, cudaGetLastError());
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->bel_count += total;
+  return BPOMP_OK;
+}
+
+#define BK_DISPATCH(fn, ...)                                           \
+  switch (ctx->dim) {                                                  \
+    case 1: return fn<1>(__VA_ARGS__);                                 \
+    case 2: return fn<2>(__VA_ARGS__);                                 \
+    case 3: return fn<3>(__VA_ARGS__);                                 \
+    case 4: return fn<4>(__VA_ARGS__);                                 \
+    case 5: return fn<5>(__VA_ARGS__);                                 \
+    case 6: return fn<6>(__VA_ARGS__);                                 \
+    case 7: return fn<7>(__VA_ARGS__);                                 \
+    case 8: return fn<8>(__VA_ARGS__);                                 \
+  }                                                                    \
+  return bp_fail(ctx, BPOMP_ERR_INVALID, "unsupported dim %d", ctx->dim)
+
+static int upload_edges(bpomp_ctx* ctx, const double* from, const double* to, const uint32_t* fi, const uint32_t* ti,
+                        int64_t count, EdgeSrc& src) {
+  memset(&src, 0, sizeof(src));
+  src.verts = ctx->d_verts.as<double>();
+  if (fi) {
+    for (int64_t e = 0; e < count; ++e)
+      if (fi[e] >= ctx->nverts || ti[e] >= ctx->nverts)
+        return bp_fail(ctx, BPOMP_ERR_RANGE, "edge %lld references a vertex id out of range", (long long)e);
+    size_t b = (size_t)count * sizeof(uint32_t);
+    BP_TRY(bp_reserve(ctx, ctx->s_a, b, false));
+    BP_TRY(bp_reserve(ctx, ctx->s_b, b, false));
+    BP_CUDA(ctx, cudaMemcpyAsync(ctx->s_a.p, fi, b, cudaMemcpyHostToDevice, ctx->stream));
+    BP_CUDA(ctx, cudaMemcpyAsync(ctx->s_b.p, ti, b, cudaMemcpyHostToDevice, ctx->stream));
+    src.from_ids = ctx->s_a.as<uint32_t>();
+    src.to_ids = ctx->s_b.as<uint32_t>();
+  } else {
+    size_t b = (size_t)count * ctx->dim * sizeof(double);
+    BP_TRY(bp_reserve(ctx, ctx->s_a, b, false));
+    BP_TRY(bp_reserve(ctx, ctx->s_b, b, false));
+    BP_CUDA(ctx, cudaMemcpyAsync(ctx->s_a.p, from, b, cudaMemcpyHostToDevice, ctx->stream));
+    BP_CUDA(ctx, cudaMemcpyAsync(ctx->s_b.p, to, b, cudaMemcpyHostToDevice, ctx->stream));
+    src.from = ctx->s_a.as<double>();
+    src.to = ctx->s_b.as<double>();
+  }
+  return BPOMP_OK;
+}
+
+static int edge_pfree_dispatch(bpomp_ctx* ctx, const EdgeSrc& src, int64_t count, double* pfree, uint32_t* nl) {
+  BK_DISPATCH(edge_pfree_impl, ctx, src, count, pfree, nl);
+}
+static int append_checked_dispatch(bpomp_ctx* ctx, const EdgeSrc& src, int64_t count, const int32_t* d_first) {
+  BK_DISPATCH(append_checked_impl, ctx, src, count, d_first);
+}
+
+extern "C" int bpomp_belief_edge_pfree(bpomp_ctx* ctx, const double* from, const double* to, int64_t count,
+                                       double* pfree, uint32_t* nlookups) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (count < 0 || (count > 0 && (!from || !to || !pfree))) return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
+  if (count == 0) return BPOMP_OK;
+  EdgeSrc src;
+  BP_TRY(upload_edges(ctx, from, to, nullptr, nullptr, count, src));
+  return edge_pfree_dispatch(ctx, src, count, pfree, nlookups);
+}
+
+extern "C" int bpomp_belief_edge_pfree_indexed(bpomp_ctx* ctx, const uint32_t* from_ids, const uint32_t* to_ids,
+                                               int64_t count, double* pfree, uint32_t* nlookups) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (count < 0 || (count > 0 && (!from_ids || !to_ids || !pfree)))
+    return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
+  if (count == 0) return BPOMP_OK;
+  EdgeSrc src;
+  BP_TRY(upload_edges(ctx, nullptr, nullptr, from_ids, to_ids, count, src));
+  return edge_pfree_dispatch(ctx, src, count, pfree, nlookups);
+}
+
+extern "C" int bpomp_belief_append_checked(bpomp_ctx* ctx, const double* from, const double* to,
+                                           const int32_t* first_invalid_slot, int64_t count) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (count < 0 || (count > 0 && (!from || !to || !first_invalid_slot)))
+    return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
+  if (count == 0) return BPOMP_OK;
+  EdgeSrc src;
+  BP_TRY(upload_edges(ctx, from, to, nullptr, nullptr, count, src));
+  BP_TRY(bp_reserve(ctx, ctx->s_c, (size_t)count * sizeof(int32_t), false));
+  BP_CUDA(ctx, cudaMemcpyAsync(ctx->s_c.p, first_invalid_slot, (size_t)count * sizeof(int32_t), cudaMemcpyHostToDevice,
+                               ctx->stream));
+  return append_checked_dispatch(ctx, src, count, ctx->s_c.as<int32_t>());
+}

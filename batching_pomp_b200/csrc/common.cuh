@@ -1,0 +1,191 @@
+// common.cuh — internal definitions shared by the sm_100a kernels and the C-ABI glue.
+// Public interface: include/bpomp_cuda.h.  Reference citations are relative to /root/reference/.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "bpomp_cuda.h"
+
+#define BP_ABSENT 0xFFFFFFFFu
+#define BP_GRID_C 16                                  // broad-phase cells per dimension
+#define BP_GRID_TRI (BP_GRID_C * (BP_GRID_C + 1) / 2)  // (c0 <= c1) cell ranges per dimension
+
+// ---------------------------------------------------------------------------
+// Error handling: no exception crosses the ABI.
+// ---------------------------------------------------------------------------
+int bp_fail(bpomp_ctx* ctx, int code, const char* fmt, ...);
+
+#define BP_CUDA(ctx, call)                                                                        \
+  do {                                                                                            \
+    cudaError_t _e = (call);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return bp_fail((ctx), BPOMP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), \
+                     __FILE__, __LINE__);                                                         \
+  } while (0)
+
+#define BP_TRY(expr)            \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != BPOMP_OK) return _r; \
+  } while (0)
+
+// Growable device buffer (library-owned device memory).
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+int bp_reserve(bpomp_ctx* ctx, DevBuf& b, size_t bytes, bool keep);  // grows geometrically
+void bp_free(DevBuf& b);
+
+// ---------------------------------------------------------------------------
+// Device views passed to kernels by value.
+// ---------------------------------------------------------------------------
+struct PermView {               // per-nStates sample order (util/BisectPerm.hpp + BP.cpp:459)
+  const uint32_t* off;          // [BPOMP_NSTATES_MAX+1] offset of row n in tfrac, BP_ABSENT if not resident
+  const double* tfrac;          // tfrac[off[n]+i] = double(1+perm_n[i]) / double(n+1)
+  const uint32_t* step;         // [BPOMP_NSTATES_MAX+1] (unsigned)(n / log(n)), host libm (BP.cpp:472)
+  uint8_t* need;                // [BPOMP_NSTATES_MAX+1] set to 1 for a missing row
+  int* flags;                   // device: [0] deferred edges, [1] range errors
+};
+
+struct BoxWorldView {
+  int nboxes;                   // B
+  int w4;                       // candidate-mask width in uint4 units (power of two >= ceil(B/128))
+  int lohi_stride;              // row stride of lohi in double2 units (dim | 1)
+  const double2* lohi;          // [B][lohi_stride]  (.x = lo, .y = hi)
+  const uint4* rmask;           // [dim][BP_GRID_TRI][w4] swizzled, boxes overlapping cell range [c0,c1]
+  double g0[BPOMP_DIM_MAX];     // grid origin per dim
+  double gs[BPOMP_DIM_MAX];     // cells per unit length per dim
+  size_t rmask_bytes, lohi_bytes;
+};
+
+struct ImageWorldView {
+  int W, H;
+  int tiles_x;                  // number of 8x8 tiles per row
+  const unsigned long long* bits;  // [tiles_y][tiles_x] 8x8 tile, bit (r&7)*8+(c&7) = pixel >= threshold
+};
+
+enum WorldKind { WORLD_NONE = 0, WORLD_BOXES = 1, WORLD_IMAGE = 2 };
+
+// ---------------------------------------------------------------------------
+// The context.
+// ---------------------------------------------------------------------------
+struct bpomp_ctx {
+  int device = 0;
+  int dim = 0;
+  double L = 0.0;
+  int num_sms = 148;
+  int smem_optin = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+
+  // sample-order tables
+  std::vector<uint32_t> h_perm_off;  // host mirror of PermView::off
+  uint32_t perm_reserved = 0;        // all n <= perm_reserved are resident
+  size_t tfrac_used = 0;             // doubles used in d_tfrac
+  DevBuf d_perm_off, d_tfrac, d_step, d_need;
+  int* h_flags = nullptr;            // pinned host copy of d_flags
+  int* d_flags = nullptr;            // device status flags written by kernels
+
+  // world
+  int world = WORLD_NONE;
+  BoxWorldView boxes{};
+  ImageWorldView image{};
+  DevBuf d_lohi, d_rmask, d_bits;
+
+  // vertex table (elements of mVertexNN)
+  DevBuf d_verts, d_active;
+  uint32_t nverts = 0;
+  std::vector<uint8_t> h_active;
+
+  // neighbour results
+  DevBuf d_nb_rowptr, d_nb_col, d_nb_dist, d_nb_query, d_nb_tmp, d_nb_tmp2;
+  uint64_t nb_nnz = 0;
+  uint32_t nb_nq = 0;
+  // neighbour grid
+  DevBuf d_grid_cell_start, d_grid_ids, d_grid_pts, d_grid_keys;
+  bool grid_valid = false;
+
+  // belief model
+  int knn = 15;
+  double prior = 0.5, prior_weight = 0.25;
+  DevBuf d_bel_pts, d_bel_vals;
+  uint64_t bel_count = 0;
+
+  // staging / scratch
+  DevBuf s_a, s_b, s_c, s_d, s_e, s_f, s_g, s_h, s_i, s_j, s_scan;
+
+  PermView perm_view() const;
+};
+
+// internal cross-file helpers
+int bp_read_flags(bpomp_ctx* ctx);
+int bp_perm_ensure_rows(bpomp_ctx* ctx, const std::vector<uint32_t>& ns);
+void bp_bisect_perm_host(uint32_t n, std::vector<int32_t>& first);
+
+// exclusive scan of n u32 counts into n+1 u64 offsets (d_out[n] = total); neighbors.cu
+int bp_exclusive_scan_u32(bpomp_ctx* ctx, const uint32_t* d_in, uint64_t n, uint64_t* d_out, DevBuf& tmp);
+
+// kernels' launchers (each bumps ctx->launches)
+int bp_launch_edge_check(bpomp_ctx* ctx, const double* d_from, const double* d_to, const uint32_t* d_from_ids,
+                         const uint32_t* d_to_ids, int64_t count, uint8_t* d_valid, int32_t* d_first,
+                         uint32_t* d_nstates, bool deferred_only);
+int bp_launch_states_valid(bpomp_ctx* ctx, const double* d_states, int64_t count, uint8_t* d_out);
+
+// ---------------------------------------------------------------------------
+// Device arithmetic.  Everything that must be bit-equal to the reference's unfused x86-64
+// FP64 code uses explicit round-to-nearest intrinsics, so it stays exact even if a file
+// were compiled without --fmad=false.
+// ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// RealVectorStateSpace::distance (OMPL; called at BP.cpp:431): sequential sum of squares, sqrt.
+template <int D>
+__device__ __forceinline__ double bp_dist2(const double* a, const double* b) {
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    double diff = __dsub_rn(a[j], b[j]);
+    s = __dadd_rn(s, __dmul_rn(diff, diff));
+  }
+  return s;
+}
+
+// nStates of initializeEdgePoints, BP.cpp:440-445.  Returns 0 if the count is out of range.
+__device__ __forceinline__ uint32_t bp_nstates(double dist, double L) {
+  double q = floor(__ddiv_rn(dist, L));
+  if (!(q >= 2.0)) return 2u;  // also NaN -> 2 is never reached by the reference; keep defined
+  if (q > (double)BPOMP_NSTATES_MAX) return 0u;
+  return (uint32_t)q;
+}
+
+// Monotone cell index used by the broad phase; the host builds the masks with the same function.
+__host__ __device__ __forceinline__ int bp_cell(double x, double g0, double gs) {
+#ifdef __CUDA_ARCH__
+  double v = __dmul_rn(__dsub_rn(x, g0), gs);
+#else
+  volatile double t = x - g0;
+  double v = t * gs;
+#endif
+  if (!(v > 0.0)) return 0;
+  if (v >= (double)BP_GRID_C) return BP_GRID_C - 1;
+  return (int)v;
+}
+
+__host__ __device__ __forceinline__ int bp_tri(int c0, int c1) { return c1 * (c1 + 1) / 2 + c0; }
+
+// Position of uint4 group w4i of row r inside the row (bank-conflict swizzle, see world.cu).
+__host__ __device__ __forceinline__ int bp_swz(int r, int w4i, int w4) {
+  int rows128 = w4 >= 8 ? 1 : 8 / w4;
+  return w4i ^ ((r / rows128) & (w4 - 1));
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,330 @@
+// ctx.cu — context lifetime, device buffers, sample-order tables, vertex table.
+// Reference citations are relative to /root/reference/.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <queue>
+
+#include "common.cuh"
+
+static std::string g_create_error;
+
+int bp_fail(bpomp_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  else g_create_error = buf;
+  return code;
+}
+
+int bp_reserve(bpomp_ctx* ctx, DevBuf& b, size_t bytes, bool keep) {
+  if (bytes <= b.cap) return BPOMP_OK;
+  size_t ncap = b.cap ? b.cap : 256;
+  while (ncap < bytes) ncap += ncap / 2 + 256;
+  ncap = (ncap + 255) & ~(size_t)255;
+  void* np = nullptr;
+  cudaError_t e = cudaMalloc(&np, ncap);
+  if (e != cudaSuccess) {
+    // retry with the exact size before giving up
+    ncap = (bytes + 255) & ~(size_t)255;
+    e = cudaMalloc(&np, ncap);
+    if (e != cudaSuccess)
+      return bp_fail(ctx, BPOMP_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", ncap, cudaGetErrorString(e));
+  }
+  if (keep && b.p && b.cap) {
+    e = cudaMemcpyAsync(np, b.p, b.cap, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      cudaFree(np);
+      return bp_fail(ctx, BPOMP_ERR_CUDA, "device buffer grow copy failed: %s", cudaGetErrorString(e));
+    }
+  }
+  if (b.p) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(b.p);
+  }
+  b.p = np;
+  b.cap = ncap;
+  return BPOMP_OK;
+}
+
+void bp_free(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+PermView bpomp_ctx::perm_view() const {
+  PermView v;
+  v.off = d_perm_off.as<uint32_t>();
+  v.tfrac = d_tfrac.as<double>();
+  v.step = d_step.as<uint32_t>();
+  v.need = d_need.as<uint8_t>();
+  v.flags = d_flags;
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// util::BisectPerm::get — include/batching_pomp/util/BisectPerm.hpp:45-89.
+// The reference repeatedly picks the first index farthest from every already-picked index
+// (virtual picks at -1 and n), O(n^2).  Equivalent gap formulation, O(n log n): a gap (a,b) of
+// unpicked indices offers value floor((b-a)/2) first reached at a + floor((b-a)/2); always take
+// the largest value, leftmost index on ties.
+// ---------------------------------------------------------------------------
+void bp_bisect_perm_host(uint32_t n, std::vector<int32_t>& first) {
+  first.clear();
+  first.reserve(n);
+  struct Gap {
+    int64_t val, idx, a, b;
+    bool operator<(const Gap& o) const { return val != o.val ? val < o.val : idx > o.idx; }
+  };
+  std::priority_queue<Gap> pq;
+  auto push = [&](int64_t a, int64_t b) {
+    int64_t v = (b - a) / 2;
+    if (v >= 1) pq.push(Gap{v, a + v, a, b});
+  };
+  push(-1, (int64_t)n);
+  while (!pq.empty()) {
+    Gap g = pq.top();
+    pq.pop();
+    first.push_back((int32_t)g.idx);
+    push(g.a, g.idx);
+    push(g.idx, g.b);
+  }
+}
+
+extern "C" int bpomp_bisect_perm(uint32_t n, int32_t* out) {
+  if (!out && n) return BPOMP_ERR_INVALID;
+  std::vector<int32_t> f;
+  bp_bisect_perm_host(n, f);
+  for (uint32_t i = 0; i < n; ++i) out[i] = f[i];
+  return BPOMP_OK;
+}
+
+// Uploads the rows for the given nStates values (those not yet resident).
+int bp_perm_ensure_rows(bpomp_ctx* ctx, const std::vector<uint32_t>& ns) {
+  std::vector<double> add;
+  std::vector<std::pair<uint32_t, uint32_t>> newoff;
+  std::vector<int32_t> perm;
+  size_t base = ctx->tfrac_used;
+  for (uint32_t n : ns) {
+    if (n < 2 || n > BPOMP_NSTATES_MAX) continue;
+    if (ctx->h_perm_off[n] != BP_ABSENT) continue;
+    bp_bisect_perm_host(n, perm);
+    size_t off = base + add.size();
+    if (off + n >= (size_t)BP_ABSENT) return bp_fail(ctx, BPOMP_ERR_RANGE, "sample-order table overflow");
+    ctx->h_perm_off[n] = (uint32_t)off;
+    newoff.emplace_back(n, (uint32_t)off);
+    // BP.cpp:459: 1.0*(1+order[i].first)/(nStates+1)   (int -> double, unsigned -> double)
+    for (uint32_t i = 0; i < n; ++i) add.push_back(1.0 * (1 + perm[i]) / (n + 1));
+  }
+  if (add.empty()) return BPOMP_OK;
+  BP_TRY(bp_reserve(ctx, ctx->d_tfrac, (base + add.size()) * sizeof(double), true));
+  BP_CUDA(ctx, cudaMemcpyAsync(ctx->d_tfrac.as<double>() + base, add.data(), add.size() * sizeof(double),
+                               cudaMemcpyHostToDevice, ctx->stream));
+  ctx->tfrac_used = base + add.size();
+  // offsets: contiguous runs are uploaded as one copy
+  size_t i = 0;
+  while (i < newoff.size()) {
+    size_t j = i + 1;
+    while (j < newoff.size() && newoff[j].first == newoff[j - 1].first + 1) ++j;
+    uint32_t n0 = newoff[i].first;
+    BP_CUDA(ctx, cudaMemcpyAsync(ctx->d_perm_off.as<uint32_t>() + n0, &ctx->h_perm_off[n0],
+                                 (j - i) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    i = j;
+  }
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `add` and offsets are host temporaries
+  return BPOMP_OK;
+}
+
+extern "C" int bpomp_perm_reserve(bpomp_ctx* ctx, uint32_t nmax) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (nmax > BPOMP_NSTATES_MAX) nmax = BPOMP_NSTATES_MAX;
+  if (nmax <= ctx->perm_reserved) return BPOMP_OK;
+  std::vector<uint32_t> ns;
+  for (uint32_t n = 2; n <= nmax; ++n)
+    if (ctx->h_perm_off[n] == BP_ABSENT) ns.push_back(n);
+  BP_TRY(bp_perm_ensure_rows(ctx, ns));
+  ctx->perm_reserved = nmax;
+  return BPOMP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// create / destroy
+// ---------------------------------------------------------------------------
+extern "C" const char* bpomp_last_error(const bpomp_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+static int create_impl(bpomp_ctx* ctx) {
+  BP_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  BP_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+  if (prop.major < 10)
+    return bp_fail(ctx, BPOMP_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only",
+                   ctx->device, prop.major, prop.minor);
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  BP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  ctx->stream = ctx->own_stream;
+  BP_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_flags, 4 * sizeof(int), cudaHostAllocDefault));
+  memset(ctx->h_flags, 0, 4 * sizeof(int));
+  BP_CUDA(ctx, cudaMalloc((void**)&ctx->d_flags, 4 * sizeof(int)));
+  BP_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), ctx->stream));
+
+  const size_t nent = (size_t)BPOMP_NSTATES_MAX + 1;
+  ctx->h_perm_off.assign(nent, BP_ABSENT);
+  BP_TRY(bp_reserve(ctx, ctx->d_perm_off, nent * sizeof(uint32_t), false));
+  BP_CUDA(ctx, cudaMemsetAsync(ctx->d_perm_off.p, 0xFF, nent * sizeof(uint32_t), ctx->stream));
+  BP_TRY(bp_reserve(ctx, ctx->d_need, nent, false));
+  BP_CUDA(ctx, cudaMemsetAsync(ctx->d_need.p, 0, nent, ctx->stream));
+  // stepSize table of computeAndSetEdgeFreeProbability, BP.cpp:472, with the host's libm
+  std::vector<uint32_t> step(nent, 1u);
+  for (size_t n = 2; n < nent; ++n) step[n] = static_cast<unsigned int>(n / std::log(n));
+  BP_TRY(bp_reserve(ctx, ctx->d_step, nent * sizeof(uint32_t), false));
+  BP_CUDA(ctx, cudaMemcpyAsync(ctx->d_step.p, step.data(), nent * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                               ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  BP_TRY(bpomp_perm_reserve(ctx, 256));
+  return BPOMP_OK;
+}
+
+extern "C" int bpomp_create(int device, int dim, double segment_length, bpomp_ctx** out) {
+  if (!out) return bp_fail(nullptr, BPOMP_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (dim < 1 || dim > BPOMP_DIM_MAX)
+    return bp_fail(nullptr, BPOMP_ERR_INVALID, "dim must be in 1..%d (got %d)", BPOMP_DIM_MAX, dim);
+  if (!(segment_length > 0.0) || !std::isfinite(segment_length))
+    return bp_fail(nullptr, BPOMP_ERR_INVALID,
+                   "segment_length must be finite and > 0 (set up the state space before the planner, "
+                   "src/BatchingPOMP.cpp:241)");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    return bp_fail(nullptr, BPOMP_ERR_CUDA, "no CUDA device available (%s); there is no CPU fallback",
+                   e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= ndev)
+    return bp_fail(nullptr, BPOMP_ERR_INVALID, "device %d out of range (have %d)", device, ndev);
+  bpomp_ctx* ctx = new bpomp_ctx();
+  ctx->device = device;
+  ctx->dim = dim;
+  ctx->L = segment_length;
+  int r = create_impl(ctx);
+  if (r != BPOMP_OK) {
+    g_create_error = ctx->err;
+    bpomp_destroy(ctx);
+    return r;
+  }
+  *out = ctx;
+  return BPOMP_OK;
+}
+
+extern "C" void bpomp_destroy(bpomp_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = {&ctx->d_perm_off, &ctx->d_tfrac, &ctx->d_step, &ctx->d_need, &ctx->d_lohi, &ctx->d_rmask,
+                    &ctx->d_bits, &ctx->d_verts, &ctx->d_active, &ctx->d_nb_rowptr, &ctx->d_nb_col,
+                    &ctx->d_nb_dist, &ctx->d_nb_query, &ctx->d_nb_tmp, &ctx->d_nb_tmp2, &ctx->d_grid_cell_start,
+                    &ctx->d_grid_ids, &ctx->d_grid_pts, &ctx->d_grid_keys, &ctx->d_bel_pts, &ctx->d_bel_vals,
+                    &ctx->s_a, &ctx->s_b, &ctx->s_c, &ctx->s_d, &ctx->s_e, &ctx->s_f, &ctx->s_g, &ctx->s_h, &ctx->s_i,
+                    &ctx->s_j, &ctx->s_scan};
+  for (DevBuf* b : bufs) bp_free(*b);
+  if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+  if (ctx->d_flags) cudaFree(ctx->d_flags);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+// Waits for the stream and brings the kernels' status flags ([0] deferred edges, [1] range errors)
+// to the host; non-zero device flags are cleared.
+int bp_read_flags(bpomp_ctx* ctx) {
+  BP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->h_flags[0] || ctx->h_flags[1])
+    BP_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), ctx->stream));
+  return BPOMP_OK;
+}
+
+extern "C" int bpomp_sync(bpomp_ctx* ctx) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  BP_TRY(bp_read_flags(ctx));
+  if (ctx->h_flags[1]) {
+    ctx->h_flags[1] = 0;
+    return bp_fail(ctx, BPOMP_ERR_RANGE, "an edge has more than %u states (segment_length too small)",
+                   BPOMP_NSTATES_MAX);
+  }
+  if (ctx->h_flags[0]) {
+    int n = ctx->h_flags[0];
+    ctx->h_flags[0] = 0;
+    return bp_fail(ctx, BPOMP_ERR_DEFERRED,
+                   "%d edges of a _dev call need sample orders beyond bpomp_perm_reserve(); they were "
+                   "marked BPOMP_EDGE_DEFERRED", n);
+  }
+  return BPOMP_OK;
+}
+
+extern "C" int bpomp_set_stream(bpomp_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return BPOMP_OK;
+}
+
+extern "C" void* bpomp_get_stream(bpomp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" uint64_t bpomp_launch_count(const bpomp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------
+// vertex table
+// ---------------------------------------------------------------------------
+extern "C" int bpomp_vertices_append(bpomp_ctx* ctx, const double* states, uint32_t count, uint32_t* first_id) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (first_id) *first_id = ctx->nverts;
+  if (count == 0) return BPOMP_OK;
+  if (!states) return bp_fail(ctx, BPOMP_ERR_INVALID, "states is NULL");
+  if ((uint64_t)ctx->nverts + count >= 0xFFFFFFFFull) return bp_fail(ctx, BPOMP_ERR_RANGE, "too many vertices");
+  size_t row = (size_t)ctx->dim * sizeof(double);
+  size_t n0 = ctx->nverts, n1 = n0 + count;
+  BP_TRY(bp_reserve(ctx, ctx->d_verts, n1 * row, true));
+  BP_TRY(bp_reserve(ctx, ctx->d_active, n1, true));
+  BP_CUDA(ctx, cudaMemcpyAsync((char*)ctx->d_verts.p + n0 * row, states, (size_t)count * row,
+                               cudaMemcpyHostToDevice, ctx->stream));
+  BP_CUDA(ctx, cudaMemsetAsync((char*)ctx->d_active.p + n0, 1, count, ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->h_active.resize(n1, 1);
+  ctx->nverts = (uint32_t)n1;
+  ctx->grid_valid = false;
+  return BPOMP_OK;
+}
+
+extern "C" int bpomp_vertices_set_active(bpomp_ctx* ctx, const uint32_t* ids, uint32_t count, int flag) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (count == 0) return BPOMP_OK;
+  if (!ids) return bp_fail(ctx, BPOMP_ERR_INVALID, "ids is NULL");
+  for (uint32_t i = 0; i < count; ++i)
+    if (ids[i] >= ctx->nverts) return bp_fail(ctx, BPOMP_ERR_RANGE, "vertex id %u out of range", ids[i]);
+  for (uint32_t i = 0; i < count; ++i) ctx->h_active[ids[i]] = flag ? 1 : 0;
+  BP_CUDA(ctx, cudaMemcpyAsync(ctx->d_active.p, ctx->h_active.data(), ctx->nverts, cudaMemcpyHostToDevice,
+                               ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->grid_valid = false;
+  return BPOMP_OK;
+}
+
+extern "C" int bpomp_vertices_count(bpomp_ctx* ctx, uint32_t* count) {
+  if (!ctx || !count) return BPOMP_ERR_INVALID;
+  *count = ctx->nverts;
+  return BPOMP_OK;
+}
+
+extern "C" int bpomp_vertices_clear(bpomp_ctx* ctx) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  ctx->nverts = 0;
+  ctx->h_active.clear();
+  ctx->grid_valid = false;
+  return BPOMP_OK;
+}

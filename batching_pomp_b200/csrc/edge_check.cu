@@ -1,0 +1,471 @@
+// edge_check.cu — batched edge evaluation (the isValid loop of checkAndSetEdgeBlocked,
+// /root/reference/src/BatchingPOMP.cpp:496-544, over edges discretised as
+// initializeEdgePoints does, :435-461) against the device-resident collision world.
+//
+// One thread per edge (DESIGN.md explains why not warp-per-edge: an FP64 instruction costs the
+// same issue slots for 1 or 32 active lanes, and a 7-DoF edge at the default resolution has
+// only ~5 checked samples).  Per edge:
+//   A. load both endpoints, distance (sequential unfused FP64), nStates;
+//   B. broad phase: AND the per-dimension cell-range masks of the edge's AABB (shared memory,
+//      staged once per CTA with a bulk async copy), exact AABB filter -> short candidate list;
+//   C. walk the samples in the reference's bisection order and test each against the
+//      candidates only; stop at the first invalid one.
+// Edges with no candidate box are FREE without interpolating a single state.
+#include <cfloat>
+
+#include "world.cuh"
+
+#define EC_THREADS 512
+#define EC_MAXCAND 16
+
+struct EdgeArgs {
+  const double* from;        // [count][D] or null (indexed)
+  const double* to;
+  const uint32_t* from_ids;  // [count] or null
+  const uint32_t* to_ids;
+  const double* verts;       // vertex table for the indexed form
+  int64_t count;
+  uint8_t* valid;
+  int32_t* first;
+  uint32_t* nstates;         // may be null
+  int deferred_only;         // re-run: only edges currently marked BPOMP_EDGE_DEFERRED
+  double L;
+};
+
+// ---- bulk async copy global -> shared (TMA engine, 1-D), completion on an mbarrier ----------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+template <int D, bool INDEXED>
+__device__ __forceinline__ void load_endpoints(const EdgeArgs& a, int64_t e, double* f, double* t) {
+  const double* pf;
+  const double* pt;
+  if (INDEXED) {
+    pf = a.verts + (size_t)__ldg(a.from_ids + e) * D;
+    pt = a.verts + (size_t)__ldg(a.to_ids + e) * D;
+  } else {
+    pf = a.from + (size_t)e * D;
+    pt = a.to + (size_t)e * D;
+  }
+  if ((D & 1) == 0) {
+#pragma unroll
+    for (int j = 0; j < D; j += 2) {
+      double2 vf = __ldg(reinterpret_cast<const double2*>(pf + j));
+      double2 vt = __ldg(reinterpret_cast<const double2*>(pt + j));
+      f[j] = vf.x; f[j + 1] = vf.y;
+      t[j] = vt.x; t[j + 1] = vt.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      f[j] = __ldg(pf + j);
+      t[j] = __ldg(pt + j);
+    }
+  }
+}
+
+// Phase A shared by both worlds.  Returns false when the edge is already decided.
+template <int D, bool INDEXED>
+__device__ __forceinline__ bool edge_prologue(const EdgeArgs& a, const PermView& pv, int64_t e, double* f, double* t,
+                                              uint32_t& n, uint32_t& off) {
+  if (a.deferred_only && a.valid[e] != BPOMP_EDGE_DEFERRED) return false;
+  load_endpoints<D, INDEXED>(a, e, f, t);
+  double dist = __dsqrt_rn(bp_dist2<D>(f, t));  // BP.cpp:163 distance(source, target)
+  n = bp_nstates(dist, a.L);                     // BP.cpp:440-445
+  if (n == 0u) {                                 // more than BPOMP_NSTATES_MAX states
+    atomicAdd(pv.flags + 1, 1);
+    a.valid[e] = BPOMP_EDGE_BLOCKED;
+    a.first[e] = -1;
+    if (a.nstates) a.nstates[e] = 0u;
+    return false;
+  }
+  if (a.nstates) a.nstates[e] = n;
+  if (n <= 2u) {  // BP.cpp:510: no slot in 1..n-2 -> FREE unchecked
+    a.valid[e] = BPOMP_EDGE_FREE;
+    a.first[e] = -1;
+    return false;
+  }
+  off = __ldg(pv.off + n);
+  if (off == BP_ABSENT) {  // sample order for this n not resident: host uploads it and re-runs
+    pv.need[n] = 1;
+    atomicAdd(pv.flags, 1);
+    a.valid[e] = BPOMP_EDGE_DEFERRED;
+    a.first[e] = -2;
+    return false;
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------
+// Box world
+// ---------------------------------------------------------------------------
+template <int D, bool INDEXED, bool STAGE>
+__global__ void __launch_bounds__(EC_THREADS, 1)
+    edge_check_boxes_kernel(EdgeArgs a, BoxWorldView w, PermView pv) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  // layout: [cand list EC_MAXCAND x EC_THREADS u16][mbarrier 16 B][rmask][lohi]
+  unsigned short* s_list = reinterpret_cast<unsigned short*>(smem);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + EC_MAXCAND * EC_THREADS * 2);
+  const uint4* rmask = w.rmask;
+  const double2* lohi = w.lohi;
+  if (STAGE) {
+    uint4* s_rmask = reinterpret_cast<uint4*>(smem + EC_MAXCAND * EC_THREADS * 2 + 16);
+    double2* s_lohi = reinterpret_cast<double2*>(reinterpret_cast<unsigned char*>(s_rmask) + w.rmask_bytes);
+    if (threadIdx.x == 0) {
+      mbar_init(s_bar, 1);
+      mbar_expect_tx(s_bar, (uint32_t)(w.rmask_bytes + w.lohi_bytes));
+      // bulk copies are issued in <= 32 KB pieces
+      for (size_t o = 0; o < w.rmask_bytes; o += 32768)
+        bulk_g2s(reinterpret_cast<unsigned char*>(s_rmask) + o, reinterpret_cast<const unsigned char*>(w.rmask) + o,
+                 (uint32_t)min((size_t)32768, w.rmask_bytes - o), s_bar);
+      for (size_t o = 0; o < w.lohi_bytes; o += 32768)
+        bulk_g2s(reinterpret_cast<unsigned char*>(s_lohi) + o, reinterpret_cast<const unsigned char*>(w.lohi) + o,
+                 (uint32_t)min((size_t)32768, w.lohi_bytes - o), s_bar);
+    }
+    __syncthreads();
+    mbar_wait(s_bar, 0);
+    rmask = s_rmask;
+    lohi = s_lohi;
+  }
+
+  const int tid = threadIdx.x;
+  for (int64_t e = (int64_t)blockIdx.x * EC_THREADS + tid; e < a.count; e += (int64_t)gridDim.x * EC_THREADS) {
+    double f[D], t[D];
+    uint32_t n, off;
+    if (!edge_prologue<D, INDEXED>(a, pv, e, f, t, n, off)) continue;
+
+    // ---- B. broad phase --------------------------------------------------------------
+    int nc = 0;
+    bool overflow = false;
+    if (w.nboxes > 0) {
+      int row[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        int c0 = bp_cell(fmin(f[j], t[j]), w.g0[j], w.gs[j]);
+        int c1 = bp_cell(fmax(f[j], t[j]), w.g0[j], w.gs[j]);
+        row[j] = j * BP_GRID_TRI + bp_tri(c0, c1);
+      }
+      for (int g = 0; g < w.w4; ++g) {
+        uint4 m = make_uint4(~0u, ~0u, ~0u, ~0u);
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          uint4 v = rmask[(size_t)row[j] * w.w4 + bp_swz(row[j], g, w.w4)];
+          m.x &= v.x; m.y &= v.y; m.z &= v.z; m.w &= v.w;
+        }
+        unsigned words[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          unsigned word = words[k];
+          while (word) {
+            int b = (g * 4 + k) * 32 + (__ffs(word) - 1);
+            word &= word - 1;
+            // exact AABB filter: every sample lies inside the endpoints' box
+            const double2* lh = lohi + (size_t)b * w.lohi_stride;
+            bool hit = true;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+              double2 v = lh[j];
+              if (fmax(f[j], t[j]) < v.x || fmin(f[j], t[j]) > v.y) { hit = false; break; }
+            }
+            if (hit) {
+              if (nc < EC_MAXCAND) s_list[nc++ * EC_THREADS + tid] = (unsigned short)b;
+              else overflow = true;
+            }
+          }
+        }
+      }
+    }
+
+    // ---- C. samples in bisection order -------------------------------------------------
+    int32_t bad = -1;
+    if (nc > 0) {
+      double dtf[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) dtf[j] = __dsub_rn(t[j], f[j]);  // interpolate: (to - from)
+      const double* tf = pv.tfrac + off;
+      for (uint32_t i = 1; i + 1 < n; ++i) {  // BP.cpp:510
+        double tt = __ldg(tf + i);            // (1+perm[i])/(n+1), BP.cpp:459
+        double x[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) x[j] = __dadd_rn(f[j], __dmul_rn(dtf[j], tt));
+        bool inside = false;
+        if (!overflow) {
+          for (int c = 0; c < nc; ++c) {
+            int b = s_list[c * EC_THREADS + tid];
+            if (bp_inside_box<D>(x, lohi + (size_t)b * w.lohi_stride)) { inside = true; break; }
+          }
+        } else {  // more candidates than the list holds: test every box (rare)
+          for (int b = 0; b < w.nboxes; ++b)
+            if (bp_inside_box<D>(x, lohi + (size_t)b * w.lohi_stride)) { inside = true; break; }
+        }
+        if (inside) { bad = (int32_t)i; break; }
+      }
+    }
+    a.valid[e] = bad < 0 ? BPOMP_EDGE_FREE : BPOMP_EDGE_BLOCKED;
+    a.first[e] = bad;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Image world (2-D)
+// ---------------------------------------------------------------------------
+template <bool INDEXED>
+__global__ void __launch_bounds__(256) edge_check_image_kernel(EdgeArgs a, ImageWorldView im, PermView pv) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.count;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    double f[2], t[2];
+    uint32_t n, off;
+    if (!edge_prologue<2, INDEXED>(a, pv, e, f, t, n, off)) continue;
+    double d0 = __dsub_rn(t[0], f[0]), d1 = __dsub_rn(t[1], f[1]);
+    const double* tf = pv.tfrac + off;
+    int32_t bad = -1;
+    for (uint32_t i = 1; i + 1 < n; ++i) {
+      double tt = __ldg(tf + i);
+      double x0 = __dadd_rn(f[0], __dmul_rn(d0, tt));
+      double x1 = __dadd_rn(f[1], __dmul_rn(d1, tt));
+      if (!bp_valid_image(x0, x1, im)) { bad = (int32_t)i; break; }
+    }
+    a.valid[e] = bad < 0 ? BPOMP_EDGE_FREE : BPOMP_EDGE_BLOCKED;
+    a.first[e] = bad;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Launch
+// ---------------------------------------------------------------------------
+template <int D, bool INDEXED>
+static int launch_boxes(bpomp_ctx* ctx, const EdgeArgs& a) {
+  const BoxWorldView& w = ctx->boxes;
+  size_t base = (size_t)EC_MAXCAND * EC_THREADS * 2 + 16;
+  size_t staged = base + w.rmask_bytes + w.lohi_bytes;
+  bool stage = staged <= (size_t)ctx->smem_optin && w.rmask_bytes + w.lohi_bytes < (1u << 20) && w.nboxes > 0;
+  int64_t tiles = (a.count + EC_THREADS - 1) / EC_THREADS;
+  int grid = (int)std::min<int64_t>(tiles, ctx->num_sms);
+  if (stage) {
+    auto k = edge_check_boxes_kernel<D, INDEXED, true>;
+    BP_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged));
+    k<<<grid, EC_THREADS, staged, ctx->stream>>>(a, w, ctx->perm_view());
+  } else {
+    auto k = edge_check_boxes_kernel<D, INDEXED, false>;
+    BP_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base));
+    k<<<grid, EC_THREADS, base, ctx->stream>>>(a, w, ctx->perm_view());
+  }
+  return BPOMP_OK;
+}
+
+template <bool INDEXED>
+static int launch_boxes_dim(bpomp_ctx* ctx, const EdgeArgs& a) {
+  switch (ctx->dim) {
+    case 1: return launch_boxes<1, INDEXED>(ctx, a);
+    case 2: return launch_boxes<2, INDEXED>(ctx, a);
+    case 3: return launch_boxes<3, INDEXED>(ctx, a);
+    case 4: return launch_boxes<4, INDEXED>(ctx, a);
+    case 5: return launch_boxes<5, INDEXED>(ctx, a);
+    case 6: return launch_boxes<6, INDEXED>(ctx, a);
+    case 7: return launch_boxes<7, INDEXED>(ctx, a);
+    case 8: return launch_boxes<8, INDEXED>(ctx, a);
+  }
+  return bp_fail(ctx, BPOMP_ERR_INVALID, "unsupported dim %d", ctx->dim);
+}
+
+int bp_launch_edge_check(bpomp_ctx* ctx, const double* d_from, const double* d_to, const uint32_t* d_from_ids,
+                         const uint32_t* d_to_ids, int64_t count, uint8_t* d_valid, int32_t* d_first,
+                         uint32_t* d_nstates, bool deferred_only) {
+  if (ctx->world == WORLD_NONE) return bp_fail(ctx, BPOMP_ERR_NO_WORLD, "no collision world set");
+  if (count <= 0) return BPOMP_OK;
+  EdgeArgs a;
+  a.from = d_from; a.to = d_to; a.from_ids = d_from_ids; a.to_ids = d_to_ids;
+  a.verts = ctx->d_verts.as<double>();
+  a.count = count; a.valid = d_valid; a.first = d_first; a.nstates = d_nstates;
+  a.deferred_only = deferred_only ? 1 : 0;
+  a.L = ctx->L;
+  const bool indexed = d_from_ids != nullptr;
+  if (ctx->world == WORLD_IMAGE) {
+    int grid = (int)std::min<int64_t>((count + 255) / 256, (int64_t)ctx->num_sms * 8);
+    if (indexed) edge_check_image_kernel<true><<<grid, 256, 0, ctx->stream>>>(a, ctx->image, ctx->perm_view());
+    else edge_check_image_kernel<false><<<grid, 256, 0, ctx->stream>>>(a, ctx->image, ctx->perm_view());
+  } else {
+    BP_TRY(indexed ? launch_boxes_dim<true>(ctx, a) : launch_boxes_dim<false>(ctx, a));
+  }
+  ctx->launches++;
+  BP_CUDA(ctx, cudaGetLastError());
+  return BPOMP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" int bpomp_edges_check_dev(bpomp_ctx* ctx, const double* d_from, const double* d_to, int64_t count,
+                                     uint8_t* d_valid, int32_t* d_first, uint32_t* d_nstates) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (count < 0 || (count > 0 && (!d_from || !d_to || !d_valid || !d_first)))
+    return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
+  return bp_launch_edge_check(ctx, d_from, d_to, nullptr, nullptr, count, d_valid, d_first, d_nstates, false);
+}
+
+extern "C" int bpomp_edges_check_indexed_dev(bpomp_ctx* ctx, const uint32_t* d_from_ids, const uint32_t* d_to_ids,
+                                             int64_t count, uint8_t* d_valid, int32_t* d_first,
+                                             uint32_t* d_nstates) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (count < 0 || (count > 0 && (!d_from_ids || !d_to_ids || !d_valid || !d_first)))
+    return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
+  return bp_launch_edge_check(ctx, nullptr, nullptr, d_from_ids, d_to_ids, count, d_valid, d_first, d_nstates, false);
+}
+
+// After a pass: if some edges met a non-resident sample order, upload the missing rows and
+// re-run the kernel on exactly those edges.
+static int resolve_deferred(bpomp_ctx* ctx, const double* d_from, const double* d_to, const uint32_t* d_fi,
+                            const uint32_t* d_ti, int64_t count, uint8_t* d_valid, int32_t* d_first,
+                            uint32_t* d_nstates) {
+  BP_TRY(bp_read_flags(ctx));
+  if (ctx->h_flags[1]) {
+    ctx->h_flags[1] = 0;
+    return bp_fail(ctx, BPOMP_ERR_RANGE, "an edge has more than %u states (segment_length too small)",
+                   BPOMP_NSTATES_MAX);
+  }
+  if (!ctx->h_flags[0]) return BPOMP_OK;
+  ctx->h_flags[0] = 0;
+  std::vector<uint8_t> need((size_t)BPOMP_NSTATES_MAX + 1);
+  BP_CUDA(ctx, cudaMemcpyAsync(need.data(), ctx->d_need.p, need.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  BP_CUDA(ctx, cudaMemsetAsync(ctx->d_need.p, 0, need.size(), ctx->stream));
+  std::vector<uint32_t> ns;
+  for (uint32_t n = 2; n <= BPOMP_NSTATES_MAX; ++n)
+    if (need[n]) ns.push_back(n);
+  BP_TRY(bp_perm_ensure_rows(ctx, ns));
+  BP_TRY(bp_launch_edge_check(ctx, d_from, d_to, d_fi, d_ti, count, d_valid, d_first, d_nstates, true));
+  BP_TRY(bp_read_flags(ctx));
+  if (ctx->h_flags[0] || ctx->h_flags[1]) {
+    ctx->h_flags[0] = ctx->h_flags[1] = 0;
+    return bp_fail(ctx, BPOMP_ERR_RANGE, "internal: deferred edges remain after re-run");
+  }
+  return BPOMP_OK;
+}
+
+static int edges_check_host(bpomp_ctx* ctx, const double* from, const double* to, const uint32_t* fi,
+                            const uint32_t* ti, int64_t count, uint8_t* valid, int32_t* first, uint32_t* nstates) {
+  if (ctx->world == WORLD_NONE) return bp_fail(ctx, BPOMP_ERR_NO_WORLD, "no collision world set");
+  if (count == 0) return BPOMP_OK;
+  const bool indexed = fi != nullptr;
+  size_t in_bytes = indexed ? (size_t)count * sizeof(uint32_t) : (size_t)count * ctx->dim * sizeof(double);
+  BP_TRY(bp_reserve(ctx, ctx->s_a, in_bytes, false));
+  BP_TRY(bp_reserve(ctx, ctx->s_b, in_bytes, false));
+  BP_TRY(bp_reserve(ctx, ctx->s_c, (size_t)count, false));
+  BP_TRY(bp_reserve(ctx, ctx->s_d, (size_t)count * sizeof(int32_t), false));
+  BP_TRY(bp_reserve(ctx, ctx->s_e, (size_t)count * sizeof(uint32_t), false));
+  if (indexed) {
+    for (int64_t e = 0; e < count; ++e)
+      if (fi[e] >= ctx->nverts || ti[e] >= ctx->nverts)
+        return bp_fail(ctx, BPOMP_ERR_RANGE, "edge %lld references a vertex id out of range", (long long)e);
+  }
+  BP_CUDA(ctx, cudaMemcpyAsync(ctx->s_a.p, indexed ? (const void*)fi : (const void*)from, in_bytes,
+                               cudaMemcpyHostToDevice, ctx->stream));
+  BP_CUDA(ctx, cudaMemcpyAsync(ctx->s_b.p, indexed ? (const void*)ti : (const void*)to, in_bytes,
+                               cudaMemcpyHostToDevice, ctx->stream));
+  const double* df = indexed ? nullptr : ctx->s_a.as<double>();
+  const double* dt = indexed ? nullptr : ctx->s_b.as<double>();
+  const uint32_t* dfi = indexed ? ctx->s_a.as<uint32_t>() : nullptr;
+  const uint32_t* dti = indexed ? ctx->s_b.as<uint32_t>() : nullptr;
+  uint8_t* dv = ctx->s_c.as<uint8_t>();
+  int32_t* dfirst = ctx->s_d.as<int32_t>();
+  uint32_t* dn = ctx->s_e.as<uint32_t>();
+  BP_TRY(bp_launch_edge_check(ctx, df, dt, dfi, dti, count, dv, dfirst, dn, false));
+  BP_TRY(resolve_deferred(ctx, df, dt, dfi, dti, count, dv, dfirst, dn));
+  BP_CUDA(ctx, cudaMemcpyAsync(valid, dv, (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA(ctx, cudaMemcpyAsync(first, dfirst, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (nstates)
+    BP_CUDA(ctx, cudaMemcpyAsync(nstates, dn, (size_t)count * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BPOMP_OK;
+}
+
+extern "C" int bpomp_edges_check(bpomp_ctx* ctx, const double* from, const double* to, int64_t count,
+                                 uint8_t* valid, int32_t* first_invalid_slot, uint32_t* nstates) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (count < 0 || (count > 0 && (!from || !to || !valid || !first_invalid_slot)))
+    return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
+  return edges_check_host(ctx, from, to, nullptr, nullptr, count, valid, first_invalid_slot, nstates);
+}
+
+extern "C" int bpomp_edges_check_indexed(bpomp_ctx* ctx, const uint32_t* from_ids, const uint32_t* to_ids,
+                                         int64_t count, uint8_t* valid, int32_t* first_invalid_slot,
+                                         uint32_t* nstates) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (count < 0 || (count > 0 && (!from_ids || !to_ids || !valid || !first_invalid_slot)))
+    return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
+  return edges_check_host(ctx, nullptr, nullptr, from_ids, to_ids, count, valid, first_invalid_slot, nstates);
+}
+
+// The states of one edge in slot order (debug / belief replay helper).
+__global__ void edge_states_kernel(const double* f, const double* t, int D, const double* tf, uint32_t n,
+                                   double* out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double tt = tf[i];
+    for (int j = 0; j < D; ++j) out[(size_t)i * D + j] = __dadd_rn(f[j], __dmul_rn(__dsub_rn(t[j], f[j]), tt));
+  }
+}
+__global__ void edge_nstates_kernel(const double* f, const double* t, int D, double L, uint32_t* n) {
+  double s = 0.0;
+  for (int j = 0; j < D; ++j) {
+    double diff = __dsub_rn(f[j], t[j]);
+    s = __dadd_rn(s, __dmul_rn(diff, diff));
+  }
+  *n = bp_nstates(__dsqrt_rn(s), L);
+}
+
+extern "C" int bpomp_edge_states(bpomp_ctx* ctx, const double* from, const double* to, double* out, uint32_t cap,
+                                 uint32_t* nstates) {
+  if (!ctx || !from || !to || !nstates) return BPOMP_ERR_INVALID;
+  const int D = ctx->dim;
+  BP_TRY(bp_reserve(ctx, ctx->s_a, 2 * D * sizeof(double) + 16, false));
+  double* df = ctx->s_a.as<double>();
+  double* dt = df + D;
+  uint32_t* dn = reinterpret_cast<uint32_t*>(dt + D);
+  BP_CUDA(ctx, cudaMemcpyAsync(df, from, D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  BP_CUDA(ctx, cudaMemcpyAsync(dt, to, D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  edge_nstates_kernel<<<1, 1, 0, ctx->stream>>>(df, dt, D, ctx->L, dn);
+  ctx->launches++;
+  uint32_t n = 0;
+  BP_CUDA(ctx, cudaMemcpyAsync(&n, dn, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n == 0) return bp_fail(ctx, BPOMP_ERR_RANGE, "edge has more than %u states", BPOMP_NSTATES_MAX);
+  *nstates = n;
+  if (!out || cap == 0) return BPOMP_OK;
+  BP_TRY(bp_perm_ensure_rows(ctx, std::vector<uint32_t>{n}));
+  uint32_t m = n < cap ? n : cap;
+  BP_TRY(bp_reserve(ctx, ctx->s_b, (size_t)m * D * sizeof(double), false));
+  edge_states_kernel<<<(m + 127) / 128, 128, 0, ctx->stream>>>(df, dt, D, ctx->d_tfrac.as<double>() + ctx->h_perm_off[n],
+                                                               m, ctx->s_b.as<double>());
+  ctx->launches++;
+  BP_CUDA(ctx, cudaGetLastError());
+  BP_CUDA(ctx, cudaMemcpyAsync(out, ctx->s_b.p, (size_t)m * D * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BPOMP_OK;
+}

@@ -1,0 +1,639 @@
+// neighbors.cu — r-disk neighbour generation ("densification"): replaces
+// ompl::NearestNeighborsGNAT<Vertex>::nearestR at /root/reference/src/BatchingPOMP.cpp:150.
+//
+// Grid-binned radius search emitting a device CSR:
+//   1. bin the ACTIVE vertices on a uniform grid over the first <=3 dimensions (cell >= r where
+//      the cell budget allows; one cell == brute force when r is huge, e.g. vertex batching's
+//      r = DBL_MAX, VertexBatching.hpp:71), points stored SoA in cell order;
+//   2. count pass  (S warps per query, ballot/popc),   3. exclusive scan -> row offsets,
+//   4. fill pass   (same traversal, ballot-ordered compaction into the row),
+//   5. per-row sort by (distance, id): GNAT returns rows ascending by distance; ties by id is this
+//      project's canonical rule.
+// Distances are RealVectorStateSpace::distance bit-for-bit (sequential unfused FP64 + IEEE sqrt).
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+#define NB_MAXG 3
+
+struct GridView {
+  int gd;                      // gridded dimensions (<= NB_MAXG)
+  int G[NB_MAXG];              // cells per gridded dim
+  double lo[NB_MAXG], inv[NB_MAXG];
+  const uint32_t* cell_start;  // [ncells+1]
+  const uint32_t* ids;         // [nactive] vertex ids in cell order
+  const double* pts;           // SoA [D][nactive] in cell order
+  uint32_t nactive;
+  uint32_t ncells;
+};
+
+__host__ __device__ __forceinline__ int nb_cell(double x, double lo, double inv, int G) {
+#ifdef __CUDA_ARCH__
+  double v = __dmul_rn(__dsub_rn(x, lo), inv);
+#else
+  volatile double t = x - lo;
+  double v = t * inv;
+#endif
+  if (!(v > 0.0)) return 0;
+  if (v >= (double)G) return G - 1;
+  return (int)v;
+}
+
+// ---------------------------------------------------------------------------
+// Grid build
+// ---------------------------------------------------------------------------
+template <int D>
+__global__ void nb_bbox_kernel(const double* __restrict__ verts, const uint8_t* __restrict__ active, uint32_t n,
+                               double* __restrict__ partial /* [blocks][2*NB_MAXG] */) {
+  double mn[NB_MAXG], mx[NB_MAXG];
+  constexpr int GD = D < NB_MAXG ? D : NB_MAXG;
+#pragma unroll
+  for (int j = 0; j < GD; ++j) { mn[j] = DBL_MAX; mx[j] = -DBL_MAX; }
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (!active[i]) continue;
+#pragma unroll
+    for (int j = 0; j < GD; ++j) {
+      double x = verts[(size_t)i * D + j];
+      mn[j] = fmin(mn[j], x);
+      mx[j] = fmax(mx[j], x);
+    }
+  }
+  __shared__ double s[256][2 * NB_MAXG];
+#pragma unroll
+  for (int j = 0; j < GD; ++j) { s[threadIdx.x][2 * j] = mn[j]; s[threadIdx.x][2 * j + 1] = mx[j]; }
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st)
+      for (int j = 0; j < GD; ++j) {
+        s[threadIdx.x][2 * j] = fmin(s[threadIdx.x][2 * j], s[threadIdx.x + st][2 * j]);
+        s[threadIdx.x][2 * j + 1] = fmax(s[threadIdx.x][2 * j + 1], s[threadIdx.x + st][2 * j + 1]);
+      }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    for (int j = 0; j < 2 * GD; ++j) partial[(size_t)blockIdx.x * 2 * NB_MAXG + j] = s[0][j];
+}
+
+template <int D>
+__device__ __forceinline__ uint32_t nb_cell_of(const double* v, const GridView& g) {
+  uint32_t c = 0;
+#pragma unroll
+  for (int j = 0; j < NB_MAXG; ++j)
+    if (j < g.gd && j < D) c = c * g.G[j] + nb_cell(v[j], g.lo[j], g.inv[j], g.G[j]);
+  return c;
+}
+
+template <int D>
+__global__ void nb_hist_kernel(const double* __restrict__ verts, const uint8_t* __restrict__ active, uint32_t n,
+                               GridView g, uint32_t* __restrict__ counts, uint32_t* __restrict__ cell_of) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (!active[i]) { cell_of[i] = BP_ABSENT; continue; }
+    double v[NB_MAXG];
+#pragma unroll
+    for (int j = 0; j < NB_MAXG; ++j) v[j] = j < D ? verts[(size_t)i * D + j] : 0.0;
+    uint32_t c = nb_cell_of<D>(v, g);
+    cell_of[i] = c;
+    atomicAdd(counts + c, 1u);
+  }
+}
+
+template <int D>
+__global__ void nb_scatter_kernel(const double* __restrict__ verts, uint32_t n, const uint32_t* __restrict__ cell_of,
+                                  const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ fill,
+                                  uint32_t* __restrict__ ids, double* __restrict__ pts, uint32_t nactive) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint32_t c = cell_of[i];
+    if (c == BP_ABSENT) continue;
+    uint32_t p = cell_start[c] + atomicAdd(fill + c, 1u);
+    ids[p] = i;
+#pragma unroll
+    for (int j = 0; j < D; ++j) pts[(size_t)j * nactive + p] = verts[(size_t)i * D + j];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Exclusive scan of u32 counts -> u64 offsets (three small kernels)
+// ---------------------------------------------------------------------------
+#define SCAN_BLOCK 1024
+__global__ void scan_block_sums(const uint32_t* __restrict__ in, uint64_t n, uint64_t* __restrict__ bsum) {
+  __shared__ unsigned long long s[32];
+  uint64_t i = (uint64_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
+  unsigned long long v = i < n ? in[i] : 0;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = s[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = v;
+  }
+}
+__global__ void scan_of_sums(uint64_t* bsum, uint64_t nb, uint64_t* total) {
+  // single thread block; sequential over chunks of 1024 with a block scan each
+  __shared__ unsigned long long s[32];
+  __shared__ unsigned long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint64_t base = 0; base < nb; base += SCAN_BLOCK) {
+    uint64_t i = base + threadIdx.x;
+    unsigned long long v = i < nb ? bsum[i] : 0, x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) s[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      unsigned long long w = s[threadIdx.x], z = w;
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long y = __shfl_up_sync(0xffffffffu, z, o);
+        if (threadIdx.x >= o) z += y;
+      }
+      s[threadIdx.x] = z - w;  // exclusive warp offsets
+    }
+    __syncthreads();
+    unsigned long long excl = x - v + s[threadIdx.x >> 5] + carry;
+    if (i < nb) bsum[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == SCAN_BLOCK - 1) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+__global__ void scan_finish(const uint32_t* __restrict__ in, uint64_t n, const uint64_t* __restrict__ bsum,
+                            uint64_t* __restrict__ out) {
+  __shared__ unsigned long long s[32];
+  uint64_t i = (uint64_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
+  unsigned long long v = i < n ? in[i] : 0, x = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) >= o) x += y;
+  }
+  if ((threadIdx.x & 31) == 31) s[threadIdx.x >> 5] = x;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    unsigned long long w = s[threadIdx.x], z = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long y = __shfl_up_sync(0xffffffffu, z, o);
+      if (threadIdx.x >= o) z += y;
+    }
+    s[threadIdx.x] = z - w;
+  }
+  __syncthreads();
+  if (i < n) out[i] = x - v + s[threadIdx.x >> 5] + bsum[blockIdx.x];
+}
+
+// out[n] receives the total.
+int bp_exclusive_scan_u32(bpomp_ctx* ctx, const uint32_t* d_in, uint64_t n, uint64_t* d_out, DevBuf& tmp) {
+  uint64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  if (nb == 0) nb = 1;
+  BP_TRY(bp_reserve(ctx, tmp, nb * sizeof(uint64_t), false));
+  uint64_t* bsum = tmp.as<uint64_t>();
+  scan_block_sums<<<(unsigned)nb, SCAN_BLOCK, 0, ctx->stream>>>(d_in, n, bsum);
+  scan_of_sums<<<1, SCAN_BLOCK, 0, ctx->stream>>>(bsum, nb, d_out + n);
+  scan_finish<<<(unsigned)nb, SCAN_BLOCK, 0, ctx->stream>>>(d_in, n, bsum, d_out);
+  ctx->launches += 3;
+  BP_CUDA(ctx, cudaGetLastError());
+  return BPOMP_OK;
+}
+
+__global__ void scan_to_u32(const uint64_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = (uint32_t)in[i];
+}
+
+// ---------------------------------------------------------------------------
+// Count / fill traversal: S warps per query.
+// ---------------------------------------------------------------------------
+struct QueryArgs {
+  const double* verts;      // AoS vertex table
+  const uint8_t* active;
+  const uint32_t* query;    // query ids, or null = identity (neighbors_all)
+  uint32_t nq;
+  int S;                    // slices (warps) per query
+  double r, r2pad;
+  int skip_inactive_query;  // neighbors_all: inactive vertices get empty rows
+  uint32_t* counts;         // [nq*S]      (count pass)
+  const uint64_t* offs;     // [nq*S+1]    (fill pass)
+  double* out_dist;         // unsorted pairs
+  uint32_t* out_id;
+};
+
+template <int D, bool FILL>
+__global__ void __launch_bounds__(256) nb_query_kernel(QueryArgs a, GridView g) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint64_t total = (uint64_t)a.nq * a.S;
+  for (uint64_t w = warp; w < total; w += nwarps) {
+    uint32_t qi = (uint32_t)(w / a.S);
+    int s = (int)(w % a.S);
+    uint32_t qid = a.query ? __ldg(a.query + qi) : qi;
+    uint32_t cnt = 0;
+    uint64_t base = FILL ? a.offs[w] : 0;
+    bool skip = a.skip_inactive_query && !a.active[qid];
+    if (!skip) {
+      double q[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) q[j] = __ldg(a.verts + (size_t)qid * D + j);
+      // cell range per gridded dim, padded so that rounding can never exclude a true neighbour
+      int c0[NB_MAXG], c1[NB_MAXG];
+#pragma unroll
+      for (int j = 0; j < NB_MAXG; ++j) {
+        c0[j] = 0; c1[j] = 0;
+        if (j < g.gd && j < D) {
+          double pad = (fabs(q[j]) + a.r) * 9.094947017729282e-13;  // 2^-40 relative
+          c0[j] = nb_cell(q[j] - a.r - pad, g.lo[j], g.inv[j], g.G[j]);
+          c1[j] = nb_cell(q[j] + a.r + pad, g.lo[j], g.inv[j], g.G[j]);
+        }
+      }
+      // cell id = ((c[0])*G[1] + c[1])*G[2] + c[2] (gd = 3); the last gridded dim is contiguous in
+      // memory, so every combination of the outer dims contributes one run of cells.
+      const int last = g.gd - 1;
+      const int GL = g.G[last];
+      const int A0 = g.gd >= 2 ? c0[0] : 0, A1 = g.gd >= 2 ? c1[0] : 0;
+      const int B0 = g.gd >= 3 ? c0[1] : 0, B1 = g.gd >= 3 ? c1[1] : 0;
+      for (int a0 = A0; a0 <= A1; ++a0) {
+        for (int b0 = B0; b0 <= B1; ++b0) {
+          const int prefix = g.gd == 1 ? 0 : (g.gd == 2 ? a0 : a0 * g.G[1] + b0);
+          const uint32_t first_cell = (uint32_t)(prefix * GL + c0[last]);
+          const uint32_t last_cell = (uint32_t)(prefix * GL + c1[last]);
+          uint32_t p0 = __ldg(g.cell_start + first_cell), p1 = __ldg(g.cell_start + last_cell + 1);
+          for (uint32_t pb = p0 + (uint32_t)s * 32u; pb < p1; pb += (uint32_t)a.S * 32u) {
+            uint32_t p = pb + lane;
+            bool hit = false;
+            double dist = 0.0;
+            uint32_t id = 0;
+            if (p < p1) {
+              double d2 = 0.0;
+#pragma unroll
+              for (int j = 0; j < D; ++j) {
+                double diff = __dsub_rn(q[j], __ldg(g.pts + (size_t)j * g.nactive + p));
+                d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
+              }
+              if (d2 <= a.r2pad) {  // cheap conservative prefilter, exact test below
+                dist = __dsqrt_rn(d2);
+                hit = dist <= a.r;  // inclusive, as GNAT nearestR
+                if (FILL && hit) id = __ldg(g.ids + p);
+              }
+            }
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (FILL && hit) {
+              uint64_t o = base + cnt + __popc(m & ((1u << lane) - 1u));
+              a.out_dist[o] = dist;
+              a.out_id[o] = id;
+            }
+            cnt += __popc(m);
+          }
+        }
+      }
+    }
+    if (!FILL && lane == 0) a.counts[w] = cnt;
+  }
+}
+
+// row_ptr[q] = offs[q*S]
+__global__ void nb_rowptr_kernel(const uint64_t* __restrict__ offs, uint32_t nq, int S, uint64_t* __restrict__ row_ptr,
+                                 unsigned long long* __restrict__ maxrow) {
+  unsigned long long mx = 0;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q <= nq; q += gridDim.x * blockDim.x) {
+    uint64_t o = offs[(uint64_t)q * S];
+    row_ptr[q] = o;
+    if (q < nq) {
+      unsigned long long len = offs[(uint64_t)(q + 1) * S] - o;
+      mx = len > mx ? len : mx;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long y = __shfl_down_sync(0xffffffffu, mx, o);
+    mx = y > mx ? y : mx;
+  }
+  if ((threadIdx.x & 31) == 0 && mx) atomicMax(maxrow, mx);
+}
+
+// ---------------------------------------------------------------------------
+// Row sort by (dist, id).  Rank sort out of shared memory: small rows one warp each, medium rows
+// one block each; rows beyond NB_MEDIUM use a global bitonic network (rare: huge radius).
+// ---------------------------------------------------------------------------
+#define NB_SMALL 128
+#define NB_MEDIUM 4096
+
+__device__ __forceinline__ bool nb_less(double da, uint32_t ia, double db, uint32_t ib) {
+  return da < db || (da == db && ia < ib);
+}
+
+__global__ void __launch_bounds__(256) nb_sort_small(const uint64_t* __restrict__ row_ptr, uint32_t nq,
+                                                     const double* __restrict__ in_d, const uint32_t* __restrict__ in_i,
+                                                     double* __restrict__ out_d, uint32_t* __restrict__ out_i) {
+  __shared__ double sd[8][NB_SMALL];
+  __shared__ uint32_t si[8][NB_SMALL];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nq; q += nw) {
+    uint64_t o = row_ptr[q];
+    uint32_t len = (uint32_t)min((unsigned long long)(row_ptr[q + 1] - o), 0xFFFFFFFFull);
+    if (len == 0 || len > NB_SMALL) continue;
+    for (uint32_t i = lane; i < len; i += 32) { sd[wib][i] = in_d[o + i]; si[wib][i] = in_i[o + i]; }
+    __syncwarp();
+    for (uint32_t i = lane; i < len; i += 32) {
+      double d = sd[wib][i];
+      uint32_t id = si[wib][i];
+      uint32_t rank = 0;
+      for (uint32_t k = 0; k < len; ++k) rank += nb_less(sd[wib][k], si[wib][k], d, id) ? 1u : 0u;
+      out_d[o + rank] = d;
+      out_i[o + rank] = id;
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(256) nb_sort_medium(const uint64_t* __restrict__ row_ptr, uint32_t nq,
+                                                      const double* __restrict__ in_d, const uint32_t* __restrict__ in_i,
+                                                      double* __restrict__ out_d, uint32_t* __restrict__ out_i) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double* sd = reinterpret_cast<double*>(smem);
+  uint32_t* si = reinterpret_cast<uint32_t*>(smem + NB_MEDIUM * sizeof(double));
+  for (uint32_t q = blockIdx.x; q < nq; q += gridDim.x) {
+    uint64_t o = row_ptr[q];
+    unsigned long long len64 = row_ptr[q + 1] - o;
+    if (len64 <= NB_SMALL || len64 > NB_MEDIUM) continue;
+    uint32_t len = (uint32_t)len64;
+    for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) { sd[i] = in_d[o + i]; si[i] = in_i[o + i]; }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
+      double d = sd[i];
+      uint32_t id = si[i];
+      uint32_t rank = 0;
+      for (uint32_t k = 0; k < len; ++k) rank += nb_less(sd[k], si[k], d, id) ? 1u : 0u;
+      out_d[o + rank] = d;
+      out_i[o + rank] = id;
+    }
+    __syncthreads();
+  }
+}
+
+// One compare-exchange step of an ascending-only bitonic network over a virtual length npad
+// (power of two): partner = i ^ mask, smaller key goes to the lower index.  The first step of
+// each merge uses mask = k-1 (mirror), the others mask = j.  Indices >= len act as +infinity
+// and are never moved, so no padding storage is needed.
+__global__ void nb_bitonic_step(double* __restrict__ d, uint32_t* __restrict__ ids, uint64_t len, uint64_t mask,
+                                uint64_t npad) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npad; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t l = i ^ mask;
+    if (l <= i || l >= len) continue;
+    double di = d[i], dl = d[l];
+    uint32_t ii = ids[i], il = ids[l];
+    if (nb_less(dl, il, di, ii)) { d[i] = dl; d[l] = di; ids[i] = il; ids[l] = ii; }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Host driver
+// ---------------------------------------------------------------------------
+template <int D>
+static int build_grid(bpomp_ctx* ctx, double r, GridView& g) {
+  const uint32_t n = ctx->nverts;
+  memset(&g, 0, sizeof(g));
+  // bounding box of the active vertices over the gridded dims
+  const int blocks = 64;
+  BP_TRY(bp_reserve(ctx, ctx->d_nb_tmp, blocks * 2 * NB_MAXG * sizeof(double), false));
+  nb_bbox_kernel<D><<<blocks, 256, 0, ctx->stream>>>(ctx->d_verts.as<double>(), ctx->d_active.as<uint8_t>(), n,
+                                                    ctx->d_nb_tmp.as<double>());
+  ctx->launches++;
+  std::vector<double> part((size_t)blocks * 2 * NB_MAXG);
+  BP_CUDA(ctx, cudaMemcpyAsync(part.data(), ctx->d_nb_tmp.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost,
+                               ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  uint32_t nactive = 0;
+  for (uint32_t i = 0; i < n; ++i) nactive += ctx->h_active[i];
+  g.gd = D < NB_MAXG ? D : NB_MAXG;
+  // cell budget: ~2^21 cells in total, and never more cells than ~4x the points
+  double budget = std::min(2097152.0, std::max(1.0, 4.0 * (double)nactive));
+  int gcap = (int)std::floor(std::pow(budget, 1.0 / g.gd));
+  if (gcap < 1) gcap = 1;
+  uint32_t ncells = 1;
+  for (int j = 0; j < g.gd; ++j) {
+    double mn = DBL_MAX, mx = -DBL_MAX;
+    for (int b = 0; b < blocks; ++b) {
+      mn = std::min(mn, part[(size_t)b * 2 * NB_MAXG + 2 * j]);
+      mx = std::max(mx, part[(size_t)b * 2 * NB_MAXG + 2 * j + 1]);
+    }
+    double span = mx - mn;
+    int G = 1;
+    if (nactive > 0 && std::isfinite(span) && span > 0.0 && std::isfinite(r) && r > 0.0) {
+      double want = std::floor(span / r);
+      G = want >= (double)gcap ? gcap : (want < 1.0 ? 1 : (int)want);
+    }
+    g.G[j] = G;
+    g.lo[j] = (nactive > 0 && std::isfinite(mn)) ? mn : 0.0;
+    g.inv[j] = (G > 1) ? (double)G / span : 0.0;
+    ncells *= (uint32_t)G;
+  }
+  g.ncells = ncells;
+  g.nactive = nactive;
+  BP_TRY(bp_reserve(ctx, ctx->d_grid_cell_start, ((size_t)ncells + 2) * sizeof(uint32_t), false));
+  BP_TRY(bp_reserve(ctx, ctx->d_grid_keys, ((size_t)n + 1) * sizeof(uint32_t), false));
+  BP_TRY(bp_reserve(ctx, ctx->d_grid_ids, ((size_t)nactive + 1) * sizeof(uint32_t), false));
+  BP_TRY(bp_reserve(ctx, ctx->d_grid_pts, ((size_t)nactive + 1) * D * sizeof(double), false));
+  const size_t counts_bytes = (((size_t)ncells + 2) * sizeof(uint32_t) + 7) / 8 * 8;
+  BP_TRY(bp_reserve(ctx, ctx->d_nb_tmp, counts_bytes + ((size_t)ncells + 2) * sizeof(uint64_t), false));
+  uint32_t* counts = ctx->d_nb_tmp.as<uint32_t>();
+  uint64_t* offs64 = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(ctx->d_nb_tmp.p) + counts_bytes);
+  BP_CUDA(ctx, cudaMemsetAsync(counts, 0, ((size_t)ncells + 2) * sizeof(uint32_t), ctx->stream));
+  int grid = (int)std::min<uint64_t>(((uint64_t)n + 255) / 256, (uint64_t)ctx->num_sms * 8);
+  if (grid < 1) grid = 1;
+  nb_hist_kernel<D><<<grid, 256, 0, ctx->stream>>>(ctx->d_verts.as<double>(), ctx->d_active.as<uint8_t>(), n, g, counts,
+                                                  ctx->d_grid_keys.as<uint32_t>());
+  ctx->launches++;
+  BP_TRY(bp_exclusive_scan_u32(ctx, counts, ncells, offs64, ctx->d_nb_tmp2));
+  scan_to_u32<<<grid, 256, 0, ctx->stream>>>(offs64, ncells + 1, ctx->d_grid_cell_start.as<uint32_t>());
+  BP_CUDA(ctx, cudaMemsetAsync(counts, 0, ((size_t)ncells + 2) * sizeof(uint32_t), ctx->stream));
+  nb_scatter_kernel<D><<<grid, 256, 0, ctx->stream>>>(ctx->d_verts.as<double>(), n, ctx->d_grid_keys.as<uint32_t>(),
+                                                     ctx->d_grid_cell_start.as<uint32_t>(), counts,
+                                                     ctx->d_grid_ids.as<uint32_t>(), ctx->d_grid_pts.as<double>(),
+                                                     nactive);
+  ctx->launches += 2;
+  BP_CUDA(ctx, cudaGetLastError());
+  g.cell_start = ctx->d_grid_cell_start.as<uint32_t>();
+  g.ids = ctx->d_grid_ids.as<uint32_t>();
+  g.pts = ctx->d_grid_pts.as<double>();
+  return BPOMP_OK;
+}
+
+template <int D>
+static int neighbors_impl(bpomp_ctx* ctx, const uint32_t* d_query, uint32_t nq, double r, bool all, uint64_t* nnz_out) {
+  GridView g;
+  BP_TRY(build_grid<D>(ctx, r, g));
+  // slices per query: enough warps to fill the machine when there are few queries
+  int S = 1;
+  {
+    uint64_t want = (uint64_t)ctx->num_sms * 64;  // resident warps
+    while ((uint64_t)nq * S < want && S < 1024 && (uint64_t)S * 32 * 4 < (uint64_t)g.nactive + 1) S *= 2;
+  }
+  uint64_t nw = (uint64_t)nq * S;
+  QueryArgs a;
+  memset(&a, 0, sizeof(a));
+  a.verts = ctx->d_verts.as<double>();
+  a.active = ctx->d_active.as<uint8_t>();
+  a.query = d_query;
+  a.nq = nq;
+  a.S = S;
+  a.r = r;
+  a.r2pad = (r * r) * (1.0 + 8.881784197001252e-16);  // 2^-50
+  if (!(a.r2pad >= 0.0)) a.r2pad = DBL_MAX;           // NaN guard
+  if (std::isinf(a.r2pad)) a.r2pad = DBL_MAX;
+  a.skip_inactive_query = all ? 1 : 0;
+  BP_TRY(bp_reserve(ctx, ctx->s_f, (nw + 2) * sizeof(uint32_t), false));
+  BP_TRY(bp_reserve(ctx, ctx->s_g, (nw + 2) * sizeof(uint64_t), false));
+  a.counts = ctx->s_f.as<uint32_t>();
+  int grid = (int)std::min<uint64_t>((nw * 32 + 255) / 256, (uint64_t)ctx->num_sms * 8);
+  if (grid < 1) grid = 1;
+  nb_query_kernel<D, false><<<grid, 256, 0, ctx->stream>>>(a, g);
+  ctx->launches++;
+  BP_CUDA(ctx, cudaGetLastError());
+  uint64_t* offs = ctx->s_g.as<uint64_t>();
+  BP_TRY(bp_exclusive_scan_u32(ctx, a.counts, nw, offs, ctx->d_nb_tmp2));
+  BP_TRY(bp_reserve(ctx, ctx->d_nb_rowptr, ((size_t)nq + 2) * sizeof(uint64_t), false));
+  unsigned long long* d_max = reinterpret_cast<unsigned long long*>(ctx->d_nb_rowptr.as<uint64_t>() + nq + 1);
+  BP_CUDA(ctx, cudaMemsetAsync(d_max, 0, sizeof(unsigned long long), ctx->stream));
+  nb_rowptr_kernel<<<(int)std::min<uint32_t>((nq + 256) / 256, 1024u), 256, 0, ctx->stream>>>(
+      offs, nq, S, ctx->d_nb_rowptr.as<uint64_t>(), d_max);
+  ctx->launches++;
+  uint64_t hostv[2];
+  BP_CUDA(ctx, cudaMemcpyAsync(&hostv[0], offs + nw, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA(ctx, cudaMemcpyAsync(&hostv[1], d_max, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  uint64_t nnz = hostv[0], maxrow = hostv[1];
+  BP_TRY(bp_reserve(ctx, ctx->d_nb_tmp, (nnz + 1) * sizeof(double), false));
+  BP_TRY(bp_reserve(ctx, ctx->s_f, std::max((nw + 2) * sizeof(uint32_t), (nnz + 1) * sizeof(uint32_t)), false));
+  BP_TRY(bp_reserve(ctx, ctx->d_nb_dist, (nnz + 1) * sizeof(double), false));
+  BP_TRY(bp_reserve(ctx, ctx->d_nb_col, (nnz + 1) * sizeof(uint32_t), false));
+  // s_f is reused for the unsorted ids: the counts are no longer needed after the scan
+  a.counts = nullptr;
+  a.offs = offs;
+  a.out_dist = ctx->d_nb_tmp.as<double>();
+  a.out_id = ctx->s_f.as<uint32_t>();
+  if (nnz > 0) {
+    nb_query_kernel<D, true><<<grid, 256, 0, ctx->stream>>>(a, g);
+    ctx->launches++;
+    BP_CUDA(ctx, cudaGetLastError());
+    const uint64_t* rp = ctx->d_nb_rowptr.as<uint64_t>();
+    if (maxrow > NB_MEDIUM) {
+      // Huge rows: sort them in place in the unsorted buffers with a global bitonic network, then
+      // the copy below moves them (rows <= NB_MEDIUM are rank-sorted out of place).
+      std::vector<uint64_t> h_rp((size_t)nq + 1);
+      BP_CUDA(ctx, cudaMemcpyAsync(h_rp.data(), rp, h_rp.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+      BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      for (uint32_t q = 0; q < nq; ++q) {
+        uint64_t len = h_rp[q + 1] - h_rp[q];
+        if (len <= NB_MEDIUM) continue;
+        uint64_t npad = 1;
+        while (npad < len) npad <<= 1;
+        double* dd = a.out_dist + h_rp[q];
+        uint32_t* di = a.out_id + h_rp[q];
+        int gb = (int)std::min<uint64_t>((npad + 255) / 256, (uint64_t)ctx->num_sms * 8);
+        for (uint64_t k = 2; k <= npad; k <<= 1) {
+          nb_bitonic_step<<<gb, 256, 0, ctx->stream>>>(dd, di, len, k - 1, npad);
+          ctx->launches++;
+          for (uint64_t j = k >> 2; j > 0; j >>= 1) {
+            nb_bitonic_step<<<gb, 256, 0, ctx->stream>>>(dd, di, len, j, npad);
+            ctx->launches++;
+          }
+        }
+        BP_CUDA(ctx, cudaMemcpyAsync(ctx->d_nb_dist.as<double>() + h_rp[q], dd, len * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+        BP_CUDA(ctx, cudaMemcpyAsync(ctx->d_nb_col.as<uint32_t>() + h_rp[q], di, len * sizeof(uint32_t),
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+      }
+    }
+    int gs = (int)std::min<uint64_t>(((uint64_t)nq * 32 + 255) / 256, (uint64_t)ctx->num_sms * 16);
+    nb_sort_small<<<std::max(gs, 1), 256, 0, ctx->stream>>>(rp, nq, a.out_dist, a.out_id, ctx->d_nb_dist.as<double>(),
+                                                           ctx->d_nb_col.as<uint32_t>());
+    ctx->launches++;
+    if (maxrow > NB_SMALL) {
+      size_t sm = NB_MEDIUM * (sizeof(double) + sizeof(uint32_t));
+      BP_CUDA(ctx, cudaFuncSetAttribute(nb_sort_medium, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      nb_sort_medium<<<(int)std::min<uint32_t>(nq, (uint32_t)ctx->num_sms * 4), 256, sm, ctx->stream>>>(
+          rp, nq, a.out_dist, a.out_id, ctx->d_nb_dist.as<double>(), ctx->d_nb_col.as<uint32_t>());
+      ctx->launches++;
+    }
+    BP_CUDA(ctx, cudaGetLastError());
+  }
+  ctx->nb_nnz = nnz;
+  ctx->nb_nq = nq;
+  if (nnz_out) *nnz_out = nnz;
+  return BPOMP_OK;
+}
+
+static int neighbors_dispatch(bpomp_ctx* ctx, const uint32_t* d_query, uint32_t nq, double r, bool all, uint64_t* nnz) {
+  switch (ctx->dim) {
+    case 1: return neighbors_impl<1>(ctx, d_query, nq, r, all, nnz);
+    case 2: return neighbors_impl<2>(ctx, d_query, nq, r, all, nnz);
+    case 3: return neighbors_impl<3>(ctx, d_query, nq, r, all, nnz);
+    case 4: return neighbors_impl<4>(ctx, d_query, nq, r, all, nnz);
+    case 5: return neighbors_impl<5>(ctx, d_query, nq, r, all, nnz);
+    case 6: return neighbors_impl<6>(ctx, d_query, nq, r, all, nnz);
+    case 7: return neighbors_impl<7>(ctx, d_query, nq, r, all, nnz);
+    case 8: return neighbors_impl<8>(ctx, d_query, nq, r, all, nnz);
+  }
+  return bp_fail(ctx, BPOMP_ERR_INVALID, "unsupported dim %d", ctx->dim);
+}
+
+extern "C" int bpomp_neighbors_radius(bpomp_ctx* ctx, const uint32_t* query_ids, uint32_t nq, double r, uint64_t* nnz) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (nq > 0 && !query_ids) return bp_fail(ctx, BPOMP_ERR_INVALID, "query_ids is NULL");
+  if (!(r >= 0.0)) return bp_fail(ctx, BPOMP_ERR_INVALID, "radius must be >= 0");
+  for (uint32_t i = 0; i < nq; ++i)
+    if (query_ids[i] >= ctx->nverts) return bp_fail(ctx, BPOMP_ERR_RANGE, "query id %u out of range", query_ids[i]);
+  if (nq == 0) {
+    ctx->nb_nnz = 0;
+    ctx->nb_nq = 0;
+    BP_TRY(bp_reserve(ctx, ctx->d_nb_rowptr, 2 * sizeof(uint64_t), false));
+    BP_CUDA(ctx, cudaMemsetAsync(ctx->d_nb_rowptr.p, 0, 2 * sizeof(uint64_t), ctx->stream));
+    if (nnz) *nnz = 0;
+    return BPOMP_OK;
+  }
+  BP_TRY(bp_reserve(ctx, ctx->d_nb_query, (size_t)nq * sizeof(uint32_t), false));
+  BP_CUDA(ctx, cudaMemcpyAsync(ctx->d_nb_query.p, query_ids, (size_t)nq * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                               ctx->stream));
+  return neighbors_dispatch(ctx, ctx->d_nb_query.as<uint32_t>(), nq, r, false, nnz);
+}
+
+extern "C" int bpomp_neighbors_all(bpomp_ctx* ctx, double r, uint64_t* nnz) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (!(r >= 0.0)) return bp_fail(ctx, BPOMP_ERR_INVALID, "radius must be >= 0");
+  if (ctx->nverts == 0) {
+    ctx->nb_nnz = 0;
+    ctx->nb_nq = 0;
+    BP_TRY(bp_reserve(ctx, ctx->d_nb_rowptr, 2 * sizeof(uint64_t), false));
+    BP_CUDA(ctx, cudaMemsetAsync(ctx->d_nb_rowptr.p, 0, 2 * sizeof(uint64_t), ctx->stream));
+    if (nnz) *nnz = 0;
+    return BPOMP_OK;
+  }
+  return neighbors_dispatch(ctx, nullptr, ctx->nverts, r, true, nnz);
+}
+
+extern "C" int bpomp_neighbors_fetch(bpomp_ctx* ctx, uint64_t* row_ptr, uint32_t* col, double* dist) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (row_ptr)
+    BP_CUDA(ctx, cudaMemcpyAsync(row_ptr, ctx->d_nb_rowptr.p, ((size_t)ctx->nb_nq + 1) * sizeof(uint64_t),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+  if (col && ctx->nb_nnz)
+    BP_CUDA(ctx, cudaMemcpyAsync(col, ctx->d_nb_col.p, ctx->nb_nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+  if (dist && ctx->nb_nnz)
+    BP_CUDA(ctx, cudaMemcpyAsync(dist, ctx->d_nb_dist.p, ctx->nb_nnz * sizeof(double), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BPOMP_OK;
+}
+
+extern "C" int bpomp_neighbors_device(bpomp_ctx* ctx, const uint64_t** d_row_ptr, const uint32_t** d_col,
+                                      const double** d_dist) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (d_row_ptr) *d_row_ptr = ctx->d_nb_rowptr.as<uint64_t>();
+  if (d_col) *d_col = ctx->d_nb_col.as<uint32_t>();
+  if (d_dist) *d_dist = ctx->d_nb_dist.as<double>();
+  return BPOMP_OK;
+}

@@ -1,0 +1,247 @@
+// world.cu — device-resident collision worlds, batched isValid and the vertex prune predicate.
+// Reference citations are relative to /root/reference/.
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+#include "world.cuh"
+
+// ---------------------------------------------------------------------------
+// World upload
+// ---------------------------------------------------------------------------
+extern "C" int bpomp_world_set_image(bpomp_ctx* ctx, const uint8_t* pix, int width, int height, int threshold) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (ctx->dim != 2) return bp_fail(ctx, BPOMP_ERR_INVALID, "the image world needs dim == 2 (ctx has %d)", ctx->dim);
+  if (!pix || width <= 0 || height <= 0) return bp_fail(ctx, BPOMP_ERR_INVALID, "bad image");
+  // Pack to 8x8-pixel tiles of one bit per pixel ("free" = pix >= threshold): a 4096^2 map is
+  // 2 MB and stays L2-resident; one 8-byte load covers the pixels a short edge crosses.
+  int tx = (width + 7) / 8, ty = (height + 7) / 8;
+  std::vector<unsigned long long> bits((size_t)tx * ty, 0ull);
+  for (int r = 0; r < height; ++r)
+    for (int c = 0; c < width; ++c)
+      if ((int)pix[(size_t)r * width + c] >= threshold)
+        bits[(size_t)(r >> 3) * tx + (c >> 3)] |= 1ull << (((r & 7) << 3) | (c & 7));
+  BP_TRY(bp_reserve(ctx, ctx->d_bits, bits.size() * sizeof(unsigned long long), false));
+  BP_CUDA(ctx, cudaMemcpyAsync(ctx->d_bits.p, bits.data(), bits.size() * sizeof(unsigned long long),
+                               cudaMemcpyHostToDevice, ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->image.W = width;
+  ctx->image.H = height;
+  ctx->image.tiles_x = tx;
+  ctx->image.bits = ctx->d_bits.as<unsigned long long>();
+  ctx->world = WORLD_IMAGE;
+  return BPOMP_OK;
+}
+
+extern "C" int bpomp_world_set_boxes(bpomp_ctx* ctx, const double* lo, const double* hi, int nboxes) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (nboxes < 0 || (nboxes > 0 && (!lo || !hi))) return bp_fail(ctx, BPOMP_ERR_INVALID, "bad boxes");
+  const int D = ctx->dim;
+  BoxWorldView& w = ctx->boxes;
+  memset(&w, 0, sizeof(w));
+  w.nboxes = nboxes;
+  int words = (nboxes + 31) / 32;
+  int w4 = 1;
+  while (w4 * 4 < words) w4 *= 2;
+  w.w4 = w4;
+  w.lohi_stride = D | 1;
+  // Broad-phase grid: BP_GRID_C cells per dim over the bounding region of all boxes.
+  for (int j = 0; j < D; ++j) {
+    double mn = DBL_MAX, mx = -DBL_MAX;
+    for (int b = 0; b < nboxes; ++b) {
+      double l = lo[(size_t)b * D + j], h = hi[(size_t)b * D + j];
+      if (l < mn) mn = l;
+      if (h > mx) mx = h;
+    }
+    double span = mx - mn;
+    w.g0[j] = (nboxes > 0 && std::isfinite(mn)) ? mn : 0.0;
+    w.gs[j] = (nboxes > 0 && std::isfinite(span) && span > 0.0) ? (double)BP_GRID_C / span : 0.0;
+    if (!std::isfinite(w.gs[j])) w.gs[j] = 0.0;
+  }
+  // rmask[j][tri(c0,c1)] = boxes whose cell interval [cell(lo_j), cell(hi_j)] meets [c0,c1].
+  // bp_cell is monotone, so any x in [lo_j,hi_j] has cell(x) inside the box's interval: the mask
+  // of the cell range spanned by a segment's endpoints is a superset of the boxes it can touch.
+  size_t rows = (size_t)D * BP_GRID_TRI;
+  std::vector<uint32_t> rmask(rows * w4 * 4, 0u);
+  std::vector<double2> lohi((size_t)std::max(nboxes, 1) * w.lohi_stride, make_double2(1.0, 0.0));
+  for (int b = 0; b < nboxes; ++b) {
+    bool empty = false;
+    for (int j = 0; j < D; ++j) {
+      double l = lo[(size_t)b * D + j], h = hi[(size_t)b * D + j];
+      lohi[(size_t)b * w.lohi_stride + j] = make_double2(l, h);
+      if (!(l <= h)) empty = true;  // contains nothing (also NaN bounds)
+    }
+    if (empty) continue;
+    for (int j = 0; j < D; ++j) {
+      int cl = bp_cell(lo[(size_t)b * D + j], w.g0[j], w.gs[j]);
+      int ch = bp_cell(hi[(size_t)b * D + j], w.g0[j], w.gs[j]);
+      for (int c1 = 0; c1 < BP_GRID_C; ++c1)
+        for (int c0 = 0; c0 <= c1; ++c0) {
+          if (!(cl <= c1 && ch >= c0)) continue;
+          int row = j * BP_GRID_TRI + bp_tri(c0, c1);
+          int word = b >> 5, g = word >> 2;
+          size_t u4 = (size_t)row * w4 + bp_swz(row, g, w4);
+          rmask[u4 * 4 + (word & 3)] |= 1u << (b & 31);
+        }
+    }
+  }
+  w.rmask_bytes = rmask.size() * sizeof(uint32_t);
+  w.lohi_bytes = (size_t)nboxes * w.lohi_stride * sizeof(double2);
+  BP_TRY(bp_reserve(ctx, ctx->d_rmask, w.rmask_bytes, false));
+  BP_TRY(bp_reserve(ctx, ctx->d_lohi, lohi.size() * sizeof(double2), false));
+  BP_CUDA(ctx, cudaMemcpyAsync(ctx->d_rmask.p, rmask.data(), w.rmask_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  BP_CUDA(ctx, cudaMemcpyAsync(ctx->d_lohi.p, lohi.data(), lohi.size() * sizeof(double2), cudaMemcpyHostToDevice,
+                               ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  w.rmask = ctx->d_rmask.as<uint4>();
+  w.lohi = ctx->d_lohi.as<double2>();
+  ctx->world = WORLD_BOXES;
+  return BPOMP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Batched isValid
+// ---------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) states_valid_boxes_kernel(const double* __restrict__ states, int64_t count,
+                                                                 BoxWorldView w, uint8_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    double x[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) x[j] = __ldg(states + i * D + j);
+    out[i] = bp_valid_boxes<D>(x, w, w.rmask, w.lohi) ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) states_valid_image_kernel(const double* __restrict__ states, int64_t count,
+                                                                 ImageWorldView im, uint8_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    double2 x = __ldg(reinterpret_cast<const double2*>(states) + i);
+    out[i] = bp_valid_image(x.x, x.y, im) ? 1 : 0;
+  }
+}
+
+template <int D>
+static void launch_valid_boxes(bpomp_ctx* ctx, const double* s, int64_t count, uint8_t* out, int grid) {
+  states_valid_boxes_kernel<D><<<grid, 256, 0, ctx->stream>>>(s, count, ctx->boxes, out);
+}
+
+int bp_launch_states_valid(bpomp_ctx* ctx, const double* d_states, int64_t count, uint8_t* d_out) {
+  if (ctx->world == WORLD_NONE) return bp_fail(ctx, BPOMP_ERR_NO_WORLD, "no collision world set");
+  if (count <= 0) return BPOMP_OK;
+  int grid = (int)std::min<int64_t>((count + 255) / 256, (int64_t)ctx->num_sms * 8);
+  if (ctx->world == WORLD_IMAGE) {
+    states_valid_image_kernel<<<grid, 256, 0, ctx->stream>>>(d_states, count, ctx->image, d_out);
+  } else {
+    switch (ctx->dim) {
+      case 1: launch_valid_boxes<1>(ctx, d_states, count, d_out, grid); break;
+      case 2: launch_valid_boxes<2>(ctx, d_states, count, d_out, grid); break;
+      case 3: launch_valid_boxes<3>(ctx, d_states, count, d_out, grid); break;
+      case 4: launch_valid_boxes<4>(ctx, d_states, count, d_out, grid); break;
+      case 5: launch_valid_boxes<5>(ctx, d_states, count, d_out, grid); break;
+      case 6: launch_valid_boxes<6>(ctx, d_states, count, d_out, grid); break;
+      case 7: launch_valid_boxes<7>(ctx, d_states, count, d_out, grid); break;
+      case 8: launch_valid_boxes<8>(ctx, d_states, count, d_out, grid); break;
+      default: return bp_fail(ctx, BPOMP_ERR_INVALID, "unsupported dim %d", ctx->dim);
+    }
+  }
+  ctx->launches++;
+  BP_CUDA(ctx, cudaGetLastError());
+  return BPOMP_OK;
+}
+
+extern "C" int bpomp_states_valid_dev(bpomp_ctx* ctx, const double* d_states, int64_t count, uint8_t* d_out) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (count < 0 || (count > 0 && (!d_states || !d_out))) return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
+  return bp_launch_states_valid(ctx, d_states, count, d_out);
+}
+
+extern "C" int bpomp_states_valid(bpomp_ctx* ctx, const double* states, int64_t count, uint8_t* out) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (count < 0 || (count > 0 && (!states || !out))) return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
+  if (ctx->world == WORLD_NONE) return bp_fail(ctx, BPOMP_ERR_NO_WORLD, "no collision world set");
+  if (count == 0) return BPOMP_OK;
+  size_t bytes = (size_t)count * ctx->dim * sizeof(double);
+  BP_TRY(bp_reserve(ctx, ctx->s_a, bytes, false));
+  BP_TRY(bp_reserve(ctx, ctx->s_c, (size_t)count, false));
+  BP_CUDA(ctx, cudaMemcpyAsync(ctx->s_a.p, states, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  BP_TRY(bp_launch_states_valid(ctx, ctx->s_a.as<double>(), count, ctx->s_c.as<uint8_t>()));
+  BP_CUDA(ctx, cudaMemcpyAsync(out, ctx->s_c.p, (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BPOMP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// vertexPruneFunction / isVertexInadmissible — BP.cpp:636-656
+// ---------------------------------------------------------------------------
+struct PruneArgs {
+  double start[BPOMP_DIM_MAX], goal[BPOMP_DIM_MAX];
+  double best;
+  int use_cost;
+};
+
+template <int D>
+__global__ void __launch_bounds__(256) states_prune_kernel(const double* __restrict__ states, int64_t count,
+                                                           PruneArgs a, const uint8_t* __restrict__ valid,
+                                                           uint8_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    bool prune = false;
+    if (a.use_cost) {  // BP.cpp:638-646
+      double x[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) x[j] = __ldg(states + i * D + j);
+      double ds = __dsqrt_rn(bp_dist2<D>(a.start, x));
+      double dg = __dsqrt_rn(bp_dist2<D>(a.goal, x));
+      prune = __dadd_rn(ds, dg) > a.best;
+    }
+    if (valid && !valid[i]) prune = true;  // BP.cpp:654
+    out[i] = prune ? 1 : 0;
+  }
+}
+
+extern "C" int bpomp_states_prune(bpomp_ctx* ctx, const double* states, int64_t count, const double* start,
+                                  const double* goal, double best_cost, int check_validity, uint8_t* out) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (count < 0 || (count > 0 && (!states || !out)) || !start || !goal)
+    return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
+  if (check_validity && ctx->world == WORLD_NONE) return bp_fail(ctx, BPOMP_ERR_NO_WORLD, "no collision world set");
+  if (count == 0) return BPOMP_OK;
+  const int D = ctx->dim;
+  size_t bytes = (size_t)count * D * sizeof(double);
+  BP_TRY(bp_reserve(ctx, ctx->s_a, bytes, false));
+  BP_TRY(bp_reserve(ctx, ctx->s_c, (size_t)count, false));
+  BP_TRY(bp_reserve(ctx, ctx->s_d, (size_t)count, false));
+  BP_CUDA(ctx, cudaMemcpyAsync(ctx->s_a.p, states, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const uint8_t* d_valid = nullptr;
+  if (check_validity) {
+    BP_TRY(bp_launch_states_valid(ctx, ctx->s_a.as<double>(), count, ctx->s_c.as<uint8_t>()));
+    d_valid = ctx->s_c.as<uint8_t>();
+  }
+  PruneArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int j = 0; j < D; ++j) {
+    a.start[j] = start[j];
+    a.goal[j] = goal[j];
+  }
+  a.best = best_cost;
+  a.use_cost = best_cost < DBL_MAX ? 1 : 0;  // BP.cpp:638
+  int grid = (int)std::min<int64_t>((count + 255) / 256, (int64_t)ctx->num_sms * 8);
+  const double* s = ctx->s_a.as<double>();
+  uint8_t* o = ctx->s_d.as<uint8_t>();
+  switch (D) {
+    case 1: states_prune_kernel<1><<<grid, 256, 0, ctx->stream>>>(s, count, a, d_valid, o); break;
+    case 2: states_prune_kernel<2><<<grid, 256, 0, ctx->stream>>>(s, count, a, d_valid, o); break;
+    case 3: states_prune_kernel<3><<<grid, 256, 0, ctx->stream>>>(s, count, a, d_valid, o); break;
+    case 4: states_prune_kernel<4><<<grid, 256, 0, ctx->stream>>>(s, count, a, d_valid, o); break;
+    case 5: states_prune_kernel<5><<<grid, 256, 0, ctx->stream>>>(s, count, a, d_valid, o); break;
+    case 6: states_prune_kernel<6><<<grid, 256, 0, ctx->stream>>>(s, count, a, d_valid, o); break;
+    case 7: states_prune_kernel<7><<<grid, 256, 0, ctx->stream>>>(s, count, a, d_valid, o); break;
+    case 8: states_prune_kernel<8><<<grid, 256, 0, ctx->stream>>>(s, count, a, d_valid, o); break;
+    default: return bp_fail(ctx, BPOMP_ERR_INVALID, "unsupported dim %d", D);
+  }
+  ctx->launches++;
+  BP_CUDA(ctx, cudaGetLastError());
+  BP_CUDA(ctx, cudaMemcpyAsync(out, o, (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BPOMP_OK;
+}

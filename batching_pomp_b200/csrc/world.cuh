@@ -1,0 +1,63 @@
+// world.cuh — device-side point tests against the two collision worlds.
+// The worlds stand in for the user's ompl::base::StateValidityChecker::isValid
+// (called at /root/reference/src/BatchingPOMP.cpp:518, 654, 777, 784).
+#pragma once
+#include "common.cuh"
+
+#ifdef __CUDACC__
+
+// 2-D occupancy image (README.md:56 convention; SURVEY.md §8c definition).
+__device__ __forceinline__ bool bp_valid_image(double x0, double x1, const ImageWorldView& im) {
+  if (!(x0 >= 0.0 && x0 <= 1.0 && x1 >= 0.0 && x1 <= 1.0)) return false;
+  int col = __double2int_rd(__dmul_rn(x0, (double)im.W));
+  int row = __double2int_rd(__dmul_rn(x1, (double)im.H));
+  col = min(col, im.W - 1);
+  row = min(row, im.H - 1);
+  unsigned long long tile = __ldg(im.bits + (size_t)(row >> 3) * im.tiles_x + (col >> 3));
+  return (tile >> (((row & 7) << 3) | (col & 7))) & 1ull;
+}
+
+// Closed-box containment of x in box b; lohi row = [stride] double2 (lo, hi).
+template <int D>
+__device__ __forceinline__ bool bp_inside_box(const double* x, const double2* lohi_row) {
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    double2 lh = lohi_row[j];
+    if (!(lh.x <= x[j] && x[j] <= lh.y)) return false;
+  }
+  return true;
+}
+
+// Point query through the cell-range masks (range [c,c]).  rmask/lohi may point to shared or global.
+template <int D>
+__device__ __forceinline__ bool bp_valid_boxes(const double* x, const BoxWorldView& w, const uint4* rmask,
+                                               const double2* lohi) {
+  if (w.nboxes == 0) return true;
+  int row[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    int c = bp_cell(x[j], w.g0[j], w.gs[j]);
+    row[j] = j * BP_GRID_TRI + bp_tri(c, c);
+  }
+  for (int g = 0; g < w.w4; ++g) {
+    uint4 m = make_uint4(~0u, ~0u, ~0u, ~0u);
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      uint4 v = rmask[(size_t)row[j] * w.w4 + bp_swz(row[j], g, w.w4)];
+      m.x &= v.x; m.y &= v.y; m.z &= v.z; m.w &= v.w;
+    }
+    unsigned words[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      unsigned word = words[k];
+      while (word) {
+        int b = (g * 4 + k) * 32 + (__ffs(word) - 1);
+        word &= word - 1;
+        if (bp_inside_box<D>(x, lohi + (size_t)b * w.lohi_stride)) return false;
+      }
+    }
+  }
+  return true;
+}
+
+#endif

@@ -1,0 +1,380 @@
+"""GPU parity tests proper: the sm_100a kernels, called through the C ABI, against the CPU oracle on
+the same seeded inputs.  Bit-exact for validity flags, first-invalid slots, nStates, neighbour rows and
+distances, prune masks; belief values bit-equal to the oracle (1e-12 relative is the bar against the
+reference's Eigen summation order)."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from batching_pomp_b200 import capi as c
+    c.load()
+    return c
+
+
+@pytest.fixture(scope="module")
+def wl():
+    from batching_pomp_b200 import workloads
+    return workloads
+
+
+def _ctx_boxes(capi, wl, d, nboxes, seed, fraction=0.01):
+    L = wl.segment_length(d, fraction)
+    lo, hi = wl.box_world(d, nboxes, seed)
+    ctx = capi.Context(d, L)
+    ctx.set_world_boxes(lo, hi)
+    return ctx, L, lo, hi
+
+
+@pytest.mark.parametrize("d,nboxes,count", [(7, 500, 200000), (2, 40, 50000), (3, 100, 50000), (6, 300, 50000),
+                                            (8, 200, 30000), (1, 5, 5000), (7, 33, 20000), (7, 1, 20000)])
+def test_edge_check_boxes_parity(capi, orc, wl, d, nboxes, count):
+    ctx, L, lo, hi = _ctx_boxes(capi, wl, d, nboxes, seed=3)
+    frm, to = wl.random_edges(count, d, seed=4, max_len=wl.halton_radius(10 ** 6, 7))
+    v, f, n = ctx.edges_check(frm, to)
+    ov, of, on = orc.edges_check_boxes(frm, to, L, lo, hi, nthreads=orc.max_threads())
+    np.testing.assert_array_equal(n, on)
+    np.testing.assert_array_equal(v, ov)
+    np.testing.assert_array_equal(f, of)
+    assert 0 < int((v == 0).sum()) < count or nboxes <= 1
+    ctx.close()
+
+
+def test_edge_check_long_edges_and_deferred_orders(capi, orc, wl):
+    """Edges across the whole cube (n up to ~100 at the default resolution, and up to ~2600 at a
+    finer one) exercise sample orders beyond the 256 rows resident at create."""
+    d = 7
+    lo, hi = wl.box_world(d, 500, 3)
+    frm = wl.uniform(11, (20000, d))
+    to = wl.uniform(12, (20000, d))
+    for fraction in (0.01, 0.0005):
+        L = wl.segment_length(d, fraction)
+        ctx = capi.Context(d, L)
+        ctx.set_world_boxes(lo, hi)
+        m = 20000 if fraction == 0.01 else 3000
+        v, f, n = ctx.edges_check(frm[:m], to[:m])
+        ov, of, on = orc.edges_check_boxes(frm[:m], to[:m], L, lo, hi, nthreads=orc.max_threads())
+        np.testing.assert_array_equal(n, on)
+        np.testing.assert_array_equal(v, ov)
+        np.testing.assert_array_equal(f, of)
+        if fraction != 0.01:
+            assert n.max() > 256
+        ctx.close()
+
+
+def test_edge_check_dense_world_candidate_overflow(capi, orc, wl):
+    """Many overlapping boxes around every edge: more than EC_MAXCAND candidates -> brute path."""
+    d = 3
+    rng = np.random.default_rng(5)
+    c = rng.random((400, d)) * 0.2 + 0.4
+    h = rng.random((400, d)) * 0.02 + 0.001
+    lo, hi = c - h, c + h
+    L = wl.segment_length(d, 0.005)
+    ctx = capi.Context(d, L)
+    ctx.set_world_boxes(lo, hi)
+    frm = rng.random((20000, d)) * 0.3 + 0.35
+    to = rng.random((20000, d)) * 0.3 + 0.35
+    v, f, n = ctx.edges_check(frm, to)
+    ov, of, on = orc.edges_check_boxes(frm, to, L, lo, hi, nthreads=orc.max_threads())
+    np.testing.assert_array_equal(n, on)
+    np.testing.assert_array_equal(v, ov)
+    np.testing.assert_array_equal(f, of)
+    ctx.close()
+
+
+def test_edge_check_edge_cases(capi, orc, wl):
+    d = 7
+    ctx, L, lo, hi = _ctx_boxes(capi, wl, d, 500, seed=3)
+    # empty batch
+    v, f, n = ctx.edges_check(np.zeros((0, d)), np.zeros((0, d)))
+    assert v.size == 0
+    # zero-length and sub-resolution edges: n = 2, FREE unchecked even inside an obstacle
+    inside = (lo[0] + hi[0]) / 2
+    frm = np.stack([inside, inside, np.zeros(d)])
+    to = np.stack([inside, inside + L / 10, np.full(d, L)])
+    v, f, n = ctx.edges_check(frm, to)
+    ov, of, on = orc.edges_check_boxes(frm, to, L, lo, hi)
+    assert n.tolist() == on.tolist() and n[0] == 2 and n[1] == 2
+    np.testing.assert_array_equal(v, ov)
+    np.testing.assert_array_equal(f, of)
+    # orientation matters: reversed edges are evaluated independently and must match the oracle too
+    a, b = wl.random_edges(30000, d, seed=9, max_len=0.6)
+    v1, f1, n1 = ctx.edges_check(b, a)
+    ov1, of1, on1 = orc.edges_check_boxes(b, a, L, lo, hi, nthreads=orc.max_threads())
+    np.testing.assert_array_equal(v1, ov1)
+    np.testing.assert_array_equal(f1, of1)
+    # no world with zero boxes: everything FREE
+    ctx.set_world_boxes(np.zeros((0, d)), np.zeros((0, d)))
+    v, f, n = ctx.edges_check(a[:100], b[:100])
+    assert v.tolist() == [1] * 100 and f.tolist() == [-1] * 100
+    ctx.close()
+
+
+def test_edge_check_no_world_is_an_error(capi):
+    ctx = capi.Context(2, 0.01)
+    with pytest.raises(capi.BpompError) as ei:
+        ctx.edges_check(np.zeros((1, 2)), np.ones((1, 2)))
+    assert ei.value.code == -3
+    ctx.close()
+
+
+@pytest.mark.parametrize("size,fraction,count", [(1024, 1e-3, 200000), (4096, 1e-4, 200000), (37, 1e-3, 20000)])
+def test_edge_check_image_parity(capi, orc, wl, size, fraction, count):
+    d = 2
+    pix = wl.image_world(size, seed=1) if size >= 64 else (np.random.default_rng(1).random((size, size + 5)) * 255).astype(np.uint8)
+    L = wl.segment_length(d, fraction)
+    ctx = capi.Context(d, L)
+    ctx.set_world_image(pix)
+    r = wl.halton_radius(10 ** 4 if fraction == 1e-3 else 10 ** 6, 2)
+    frm, to = wl.random_edges(count, d, seed=4, max_len=2 * r)
+    v, f, n = ctx.edges_check(frm, to)
+    ov, of, on = orc.edges_check_image(frm, to, L, pix, nthreads=orc.max_threads())
+    np.testing.assert_array_equal(n, on)
+    np.testing.assert_array_equal(v, ov)
+    np.testing.assert_array_equal(f, of)
+    assert 0 < int((v == 0).sum()) < count
+    ctx.close()
+
+
+def test_states_valid_and_prune_parity(capi, orc, wl):
+    d = 7
+    ctx, L, lo, hi = _ctx_boxes(capi, wl, d, 500, seed=3)
+    st = wl.uniform(21, (100000, d)) * 1.2 - 0.1  # some states outside the unit cube
+    np.testing.assert_array_equal(ctx.states_valid(st), orc.states_valid_boxes(st, lo, hi))
+    # points exactly on box faces are inside (closed boxes)
+    on_face = np.concatenate([lo[:50], hi[:50]])
+    assert ctx.states_valid(on_face).tolist() == [0] * 100
+    start, goal = np.full(d, 0.1), np.full(d, 0.9)
+    for best in (np.finfo(np.float64).max, 2.2, 2.1166, 3.0):
+        got = ctx.states_prune(st, start, goal, best, True)
+        inad = orc.vertices_inadmissible(st, start, goal, best)
+        want = (inad | (orc.states_valid_boxes(st, lo, hi) == 0)).astype(np.uint8)
+        np.testing.assert_array_equal(got, want)
+        np.testing.assert_array_equal(ctx.states_prune(st, start, goal, best, False), inad)
+    ctx.close()
+    # image world
+    pix = wl.image_world(512, seed=1)
+    ctx = capi.Context(2, 0.001)
+    ctx.set_world_image(pix)
+    st = wl.uniform(22, (100000, 2)) * 1.02 - 0.01
+    st[:4] = [[0.0, 0.0], [1.0, 1.0], [1.0, 0.0], [0.0, 1.0]]
+    np.testing.assert_array_equal(ctx.states_valid(st), orc.states_valid_image(st, pix))
+    ctx.close()
+
+
+@pytest.mark.parametrize("d,N,nq,rfun", [(2, 20000, 20000, "halton"), (7, 20000, 300, "halton"), (3, 5000, 5000, "halton"),
+                                         (2, 3000, 50, "max"), (7, 2000, 20, "max"), (2, 1, 1, "halton")])
+def test_neighbors_parity(capi, orc, wl, d, N, nq, rfun):
+    verts = wl.halton(N, d)
+    r = wl.halton_radius(N, d) if rfun == "halton" else np.finfo(np.float64).max
+    ctx = capi.Context(d, wl.segment_length(d))
+    assert ctx.vertices_append(verts[: N // 2]) == 0
+    assert ctx.vertices_append(verts[N // 2:]) == N // 2
+    rng = np.random.default_rng(0)
+    q = rng.choice(N, size=nq, replace=False).astype(np.uint32) if nq < N else np.arange(N, dtype=np.uint32)
+    rp, col, dist = ctx.neighbors_radius(q, r)
+    orp, ocol, odist = orc.neighbors_radius(verts, q, r, nthreads=orc.max_threads())
+    np.testing.assert_array_equal(rp, orp)
+    np.testing.assert_array_equal(col, ocol)
+    np.testing.assert_array_equal(dist, odist)
+    # deactivate a third of the vertices (BatchingManager::pruneVertices -> NN.remove)
+    off = rng.choice(N, size=N // 3, replace=False).astype(np.uint32)
+    ctx.vertices_set_active(off, 0)
+    active = np.ones(N, dtype=np.uint8)
+    active[off] = 0
+    rp, col, dist = ctx.neighbors_radius(q, r)
+    orp, ocol, odist = orc.neighbors_radius(verts, q, r, active=active, nthreads=orc.max_threads())
+    np.testing.assert_array_equal(rp, orp)
+    np.testing.assert_array_equal(col, ocol)
+    np.testing.assert_array_equal(dist, odist)
+    ctx.close()
+
+
+def test_neighbors_all_matches_per_query(capi, orc, wl):
+    d, N = 2, 30000
+    verts = wl.halton(N, d)
+    r = wl.halton_radius(N, d)
+    ctx = capi.Context(d, wl.segment_length(d))
+    ctx.vertices_append(verts)
+    off = np.arange(0, N, 7, dtype=np.uint32)
+    ctx.vertices_set_active(off, 0)
+    rp, col, dist = ctx.neighbors_all(r)
+    active = np.ones(N, dtype=np.uint8)
+    active[off] = 0
+    orp, ocol, odist = orc.neighbors_radius(verts, np.arange(N), r, active=active, nthreads=orc.max_threads())
+    # inactive query vertices get empty rows in the whole-roadmap call
+    lens = np.diff(orp.astype(np.int64))
+    lens[off] = 0
+    want_rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    np.testing.assert_array_equal(rp, want_rp)
+    keep = np.repeat(active.astype(bool), np.diff(orp.astype(np.int64)))
+    np.testing.assert_array_equal(col, ocol[keep])
+    np.testing.assert_array_equal(dist, odist[keep])
+    # symmetry: u in row(v) <=> v in row(u)
+    rows = np.repeat(np.arange(N), np.diff(rp.astype(np.int64)))
+    a = set(zip(rows.tolist(), col.tolist()))
+    assert all((c, r_) in a for r_, c in list(a)[:5000])
+    ctx.close()
+
+
+def test_neighbors_ties_and_duplicates(capi, orc):
+    verts = np.array([[0.0, 0.0], [0.3, 0.0], [0.0, 0.3], [0.5, 0.0], [0.3, 0.0], [0.0, 0.0]])
+    ctx = capi.Context(2, 0.01)
+    ctx.vertices_append(verts)
+    rp, col, dist = ctx.neighbors_radius([0, 3], 0.3)
+    orp, ocol, odist = orc.neighbors_radius(verts, [0, 3], 0.3)
+    np.testing.assert_array_equal(rp, orp)
+    np.testing.assert_array_equal(col, ocol)
+    np.testing.assert_array_equal(dist, odist)
+    assert col[:rp[1]].tolist() == [0, 5, 1, 2, 4]
+    ctx.close()
+
+
+@pytest.mark.parametrize("d,M,nq,K", [(7, 5000, 3000, 15), (2, 300, 1000, 15), (7, 7, 100, 15), (3, 40000, 500, 15),
+                                      (7, 2000, 200, 1), (5, 1000, 300, 32)])
+def test_belief_estimate_parity(capi, orc, wl, d, M, nq, K):
+    pts = wl.uniform(31, (M, d))
+    vals = (wl.uniform(32, (M,)) < 0.3).astype(np.float64)
+    q = wl.uniform(33, (nq, d))
+    q[: min(nq, M) // 2] = pts[: min(nq, M) // 2]  # exact hits -> the 1e-4 distance clamp
+    ctx = capi.Context(d, wl.segment_length(d))
+    ctx.belief_config(K, 0.5, 0.25)
+    assert np.all(ctx.belief_estimate(q[:10]) == 0.5)  # empty model -> prior
+    ctx.belief_append(pts[: M // 2], vals[: M // 2])
+    ctx.belief_append(pts[M // 2:], vals[M // 2:])
+    assert ctx.belief_size() == M
+    got = ctx.belief_estimate(q)
+    want = orc.belief_estimate(pts, vals, q, K=K, nthreads=orc.max_threads())
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
+    ctx.close()
+
+
+def test_belief_duplicate_points_tie_break(capi, orc, wl):
+    d = 2
+    base = wl.uniform(41, (10, d))
+    pts = np.concatenate([base, base, base])  # every distance appears three times
+    vals = np.concatenate([np.zeros(10), np.ones(10), np.zeros(10)])
+    q = wl.uniform(42, (200, d))
+    ctx = capi.Context(d, 0.01)
+    ctx.belief_config(4, 0.5, 0.25)
+    ctx.belief_append(pts, vals)
+    np.testing.assert_array_equal(ctx.belief_estimate(q), orc.belief_estimate(pts, vals, q, K=4))
+    ctx.close()
+
+
+def test_belief_edge_pfree_and_append_checked(capi, orc, wl):
+    d = 7
+    ctx, L, lo, hi = _ctx_boxes(capi, wl, d, 500, seed=3)
+    frm, to = wl.random_edges(3000, d, seed=6, max_len=1.2)
+    # empty model: pfree = 0.5^(#query slots)
+    pf, nl = ctx.belief_edge_pfree(frm, to)
+    opf, onl = orc.belief_edge_pfree(frm, to, L, np.zeros((0, d)), np.zeros(0))
+    np.testing.assert_array_equal(nl, onl)
+    np.testing.assert_array_equal(pf, opf)
+    # replay the belief inserts of checkAndSetEdgeBlocked on the device and compare with a host replay
+    v, f, n = ctx.edges_check(frm, to)
+    ctx.belief_append_checked(frm, to, f)
+    pts, vals = [], []
+    for e in range(frm.shape[0]):
+        st = orc.edge_states(frm[e], to[e], L)
+        last = f[e] if f[e] >= 1 else n[e] - 2
+        for i in range(1, last + 1):
+            pts.append(st[i])
+            vals.append(1.0 if (f[e] >= 1 and i == f[e]) else 0.0)
+    pts, vals = np.array(pts), np.array(vals)
+    assert ctx.belief_size() == len(vals)
+    assert vals.sum() == (v == 0).sum()
+    pf, nl = ctx.belief_edge_pfree(frm[:800], to[:800])
+    opf, onl = orc.belief_edge_pfree(frm[:800], to[:800], L, pts, vals, nthreads=orc.max_threads())
+    np.testing.assert_array_equal(nl, onl)
+    np.testing.assert_array_equal(pf, opf)
+    ctx.close()
+
+
+def test_indexed_variants_match_explicit(capi, orc, wl):
+    d, N = 7, 5000
+    ctx, L, lo, hi = _ctx_boxes(capi, wl, d, 500, seed=3)
+    verts = wl.halton(N, d)
+    ctx.vertices_append(verts)
+    rng = np.random.default_rng(3)
+    fi = rng.integers(0, N, 40000).astype(np.uint32)
+    ti = rng.integers(0, N, 40000).astype(np.uint32)
+    v, f, n = ctx.edges_check_indexed(fi, ti)
+    ov, of, on = orc.edges_check_boxes(verts[fi], verts[ti], L, lo, hi, nthreads=orc.max_threads())
+    np.testing.assert_array_equal(n, on)
+    np.testing.assert_array_equal(v, ov)
+    np.testing.assert_array_equal(f, of)
+    ctx.belief_append(verts[:500], (np.arange(500) % 3 == 0).astype(np.float64))
+    pf, nl = ctx.belief_edge_pfree_indexed(fi[:500], ti[:500])
+    pf2, nl2 = ctx.belief_edge_pfree(verts[fi[:500]], verts[ti[:500]])
+    np.testing.assert_array_equal(pf, pf2)
+    np.testing.assert_array_equal(nl, nl2)
+    with pytest.raises(capi.BpompError):
+        ctx.edges_check_indexed(np.array([N], dtype=np.uint32), np.array([0], dtype=np.uint32))
+    ctx.close()
+
+
+def test_edge_states_match_oracle(capi, orc, wl):
+    d = 7
+    L = wl.segment_length(d)
+    ctx = capi.Context(d, L)
+    a, b = wl.uniform(51, (d,)), wl.uniform(52, (d,))
+    np.testing.assert_array_equal(ctx.edge_states(a, b), orc.edge_states(a, b, L))
+    ctx.close()
+
+
+def test_device_pointer_api_with_torch(capi, orc, wl):
+    import torch
+    d = 7
+    ctx, L, lo, hi = _ctx_boxes(capi, wl, d, 500, seed=3)
+    frm, to = wl.random_edges(100000, d, seed=8, max_len=0.35)
+    dev = torch.device("cuda:0")
+    tf = torch.from_numpy(frm).to(dev)
+    tt = torch.from_numpy(to).to(dev)
+    tv = torch.empty(frm.shape[0], dtype=torch.uint8, device=dev)
+    tfi = torch.empty(frm.shape[0], dtype=torch.int32, device=dev)
+    tn = torch.empty(frm.shape[0], dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    ctx.edges_check_dev(tf.data_ptr(), tt.data_ptr(), frm.shape[0], tv.data_ptr(), tfi.data_ptr(), tn.data_ptr())
+    ctx.sync()
+    ov, of, on = orc.edges_check_boxes(frm, to, L, lo, hi, nthreads=orc.max_threads())
+    np.testing.assert_array_equal(tv.cpu().numpy(), ov)
+    np.testing.assert_array_equal(tfi.cpu().numpy(), of)
+    np.testing.assert_array_equal(tn.cpu().numpy().astype(np.uint32), on)
+    ctx.close()
+
+
+def test_full_size_properties_config4(capi, wl):
+    """BASELINE config 4 at full size (10^7 edges, 7-DoF, 500 boxes): size-independent properties.
+    (a) a chunked evaluation equals the one-shot evaluation; (b) an edge is BLOCKED iff its first
+    invalid slot is in 1..n-2; (c) the state at the reported slot is invalid and every earlier slot
+    state is valid (checked through the independent batched isValid kernel on a sample)."""
+    d = 7
+    count = 10 ** 7
+    ctx, L, lo, hi = _ctx_boxes(capi, wl, d, 500, seed=3)
+    frm, to = wl.random_edges(count, d, seed=4, max_len=wl.halton_radius(10 ** 6, d))
+    v, f, n = ctx.edges_check(frm, to)
+    assert np.all((v == 0) == (f >= 1))
+    assert np.all(f[v == 0] <= n[v == 0].astype(np.int64) - 2)
+    assert np.all(n >= 2) and n.max() <= 13
+    vc = np.concatenate([ctx.edges_check(frm[i:i + 2500000], to[i:i + 2500000])[0] for i in range(0, count, 2500000)])
+    np.testing.assert_array_equal(v, vc)
+    from batching_pomp_b200.capi import bisect_perm
+    idx = np.nonzero(v == 0)[0][:20000]
+    slot_states, prev_states = [], []
+    for e in idx:
+        p = bisect_perm(int(n[e]))
+        t = (1 + p[f[e]]) / (n[e] + 1.0)
+        slot_states.append(frm[e] + (to[e] - frm[e]) * t)
+        for i in range(1, f[e]):
+            prev_states.append(frm[e] + (to[e] - frm[e]) * ((1 + p[i]) / (n[e] + 1.0)))
+    assert ctx.states_valid(np.array(slot_states)).sum() == 0
+    if prev_states:
+        assert ctx.states_valid(np.array(prev_states)).all()
+    ctx.close()
