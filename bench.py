@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark: batched edge evaluation (BASELINE.json config 4).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--edges E]
+
+Workload: 10^7 random 7-DoF edges (explicit endpoints, lengths ~U[0, haltonRadius(10^6,7)]) against
+500 axis-aligned box obstacles in the unit hypercube, default OMPL resolution (1 % of the extent).
+One "step" = one pass of the hot path (checkAndSetEdgeBlocked's isValid loop,
+/root/reference/src/BatchingPOMP.cpp:496-544) over the whole batch.
+
+  value        edge checks / s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e          the same through the host-buffer C-ABI call bpomp_edges_check (pinned host inputs,
+               H2D + kernel + D2H inside the timed region)
+  roofline     117 algorithmic bytes per edge (2*7*8 in + 1 + 4 out) / kernel time
+  cpu_baseline the CPU oracle (port of the reference loop) on all host cores, bounded sample
+
+N > 1 (torchrun, one rank per GPU): every rank evaluates its own 10^7-edge shard (weak scaling, world
+replicated) and the first-invalid-slot results are merged with an NCCL all-gather that overlaps the
+next chunk's kernel.  --impl reference times the CPU oracle only (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from batching_pomp_b200 import workloads  # noqa: E402
+
+DIM = 7
+NBOXES = 500
+ALGO_BYTES_PER_EDGE = 2 * DIM * 8 + 1 + 4
+METRIC = "edge_checks_per_s"
+UNIT = "edges/s"
+
+
+def make_workload(edges, seed=4):
+    L = workloads.segment_length(DIM)
+    lo, hi = workloads.box_world(DIM, NBOXES, seed=3)
+    frm, to = workloads.random_edges(edges, DIM, seed=seed, max_len=workloads.halton_radius(10 ** 6, DIM))
+    return L, lo, hi, frm, to
+
+
+def config_dict(edges, n_gpus, extra=None):
+    cfg = {
+        "workload": "config4: batched edge evaluation, %d random 7-DoF edges per GPU (explicit endpoints), "
+                    "%d box obstacles, resolution 1%% (L=%.7f)" % (edges, NBOXES, workloads.segment_length(DIM)),
+        "edges_per_gpu": edges, "dim": DIM, "boxes": NBOXES,
+        "l2": "inputs (%.0f MB per step) larger than the 126 MB L2" % (edges * 2 * DIM * 8 / 1e6),
+        "sharding": "edges sharded across %d rank(s), world replicated" % n_gpus,
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# --------------------------------------------------------------------------------------------
+# CPU baseline (the oracle is test infrastructure; this and --impl reference are the only
+# places bench.py executes it)
+# --------------------------------------------------------------------------------------------
+def cpu_baseline_run(L, lo, hi, frm, to, target_s=12.0, steps=1, warmup=0):
+    from oracle import oracle
+    cores = oracle.max_threads()
+    probe = min(20000, frm.shape[0])
+    t0 = time.perf_counter()
+    oracle.edges_check_boxes(frm[:probe], to[:probe], L, lo, hi, nthreads=cores)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    per_step = target_s / max(steps + warmup, 1)
+    sample = int(min(frm.shape[0], max(probe, probe * per_step / dt)))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        oracle.edges_check_boxes(frm[:sample], to[:sample], L, lo, hi, nthreads=cores)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    # single-thread figure on a smaller sample (the reference itself is single-threaded)
+    s1 = max(1000, sample // (4 * cores))
+    t0 = time.perf_counter()
+    oracle.edges_check_boxes(frm[:s1], to[:s1], L, lo, hi, nthreads=1)
+    v1 = s1 / max(time.perf_counter() - t0, 1e-9)
+    return {"value": sample * len(times) / total, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "first %d edges of the same batch, %d timed pass(es), OpenMP over edges; "
+                      "single-thread: %.4g edges/s" % (sample, len(times), v1),
+            "single_thread_value": v1, "ms_per_step": 1e3 * total / len(times)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    L, lo, hi, frm, to = make_workload(min(args.edges, 2_000_000))
+    cb = cpu_baseline_run(L, lo, hi, frm, to, target_s=60.0, steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args.edges, args.gpus, {"note": "CPU oracle port of the reference loop (the reference "
+                                                      "needs OMPL/Boost/Eigen and cannot be built here); each step is "
+                                                      "a bounded sample of the batch"}),
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.stop_flag = False
+        self.active = False
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self.stop_flag:
+            if self.active:
+                try:
+                    self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                    r = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    for bit, name in self.REASONS.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.004)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from batching_pomp_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    E = args.edges
+    L, lo, hi, frm, to = make_workload(E, seed=4 + 100 * rank)  # every rank owns a different shard
+    ctx = capi.Context(DIM, L, device=local_rank)
+    ctx.set_world_boxes(lo, hi)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    # pinned host copies (e2e) and device-resident copies (value)
+    h_from = torch.from_numpy(frm).pin_memory()
+    h_to = torch.from_numpy(to).pin_memory()
+    h_valid = torch.empty(E, dtype=torch.uint8).pin_memory()
+    h_first = torch.empty(E, dtype=torch.int32).pin_memory()
+    h_ns = torch.empty(E, dtype=torch.int32).pin_memory()
+    d_from = h_from.to(dev, non_blocking=True)
+    d_to = h_to.to(dev, non_blocking=True)
+    d_valid = torch.empty(E, dtype=torch.uint8, device=dev)
+    d_first = torch.empty(E, dtype=torch.int32, device=dev)
+    d_ns = torch.empty(E, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    nchunk = 4 if world > 1 else 1
+    bounds = [(E * c) // nchunk for c in range(nchunk + 1)]
+    gathered = [torch.empty(world * (bounds[c + 1] - bounds[c]), dtype=torch.int32, device=dev)
+                for c in range(nchunk)] if world > 1 else None
+    comm_stream = torch.cuda.Stream() if world > 1 else None
+    kernel_ms = []
+
+    def step(timed):
+        works = []
+        for c in range(nchunk):
+            a, b = bounds[c], bounds[c + 1]
+            if timed:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+            ctx.edges_check_dev(d_from.data_ptr() + a * DIM * 8, d_to.data_ptr() + a * DIM * 8, b - a,
+                                d_valid.data_ptr() + a, d_first.data_ptr() + a * 4, d_ns.data_ptr() + a * 4)
+            if timed:
+                e1.record(stream)
+                kernel_ms.append((e0, e1, b - a))
+            if world > 1:
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                with torch.cuda.stream(comm_stream):
+                    comm_stream.wait_event(ev)
+                    works.append(dist.all_gather_into_tensor(gathered[c], d_first[a:b], async_op=True))
+        for w in works:
+            w.wait()
+        if world > 1:
+            stream.wait_stream(comm_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- device-resident throughput ("value") ------------------------------------------------
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    launches0 = ctx.launches
+    t_beg = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    sampler.active = True
+    t_beg.record(stream)
+    for _ in range(args.steps):
+        step(True)
+    t_end.record(stream)
+    barrier()
+    sampler.active = False
+    launches = ctx.launches - launches0
+    ctx.sync()  # also surfaces deferred / range flags
+    elapsed_ms = t_beg.elapsed_time(t_end)
+    per_launch = [(e0.elapsed_time(e1), n) for e0, e1, n in kernel_ms]
+    kern_ms_per_step = sum(ms for ms, _ in per_launch) / args.steps
+    avg_launch_ms = sum(ms for ms, _ in per_launch) / len(per_launch)
+    edges_per_launch = sum(n for _, n in per_launch) / len(per_launch)
+
+    # ---- end to end through the host-buffer C ABI ("e2e") -------------------------------------
+    f_np, t_np = h_from.numpy(), h_to.numpy()
+    v_np, fi_np, ns_np = h_valid.numpy(), h_first.numpy(), h_ns.numpy().view(np.uint32)
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        ctx.edges_check_into(f_np, t_np, v_np, fi_np, ns_np)
+    barrier()
+    sampler.active = True
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.edges_check_into(f_np, t_np, v_np, fi_np, ns_np)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - w0
+    sampler.active = False
+    sampler.stop_flag = True
+    # the device-resident and the end-to-end paths must agree
+    assert np.array_equal(fi_np, d_first.cpu().numpy()), "e2e and device-resident results differ"
+
+    if world > 1:
+        t = torch.tensor([elapsed_ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, e2e_s = float(t[0]), float(t[1])
+        # merged result sanity: this rank's shard must sit at its slot of the gathered buffer
+        a, b = bounds[0], bounds[1]
+        assert torch.equal(gathered[0][rank * (b - a):(rank + 1) * (b - a)], d_first[a:b])
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak = float(json.load(open(peaks_path))["hbm_gbs"])
+            peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        else:
+            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        achieved = ALGO_BYTES_PER_EDGE * edges_per_launch / (avg_launch_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "edge_check_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        cb = cpu_baseline_run(L, lo, hi, frm, to, target_s=12.0) if not args.no_cpu else None
+        value = world * E * args.steps / (elapsed_ms * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(E, world, {
+                "merge": ("nccl all_gather of first_invalid_slot (4 B/edge) per chunk, overlapped with the next "
+                          "chunk's kernel") if world > 1 else "none (single GPU)",
+                "chunks_per_step": nchunk}),
+            "kernel_ms_per_step": kern_ms_per_step,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_edge": ALGO_BYTES_PER_EDGE,
+                         "kernel": "edge_check_boxes_kernel<7,false,true>", "avg_launch_ms": avg_launch_ms,
+                         "note": "FP64-issue bound well before HBM (DESIGN.md); both ceilings reported there"},
+            "e2e": {"value": world * E * e2e_steps / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": int(2 * E * DIM * 8), "d2h_bytes_per_step": int(E * 9),
+                    "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                    "call": "bpomp_edges_check (host buffers, pinned)"},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "blocked_fraction": float((fi_np >= 1).mean()),
+        }
+        if cb:
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--edges", type=int, default=10 ** 7)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl != "reference":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
