@@ -181,7 +181,9 @@ def run_gpu(args):
     L, lo, hi, frm, to = make_workload(E, seed=4 + 100 * rank)  # every rank owns a different shard
     ctx = capi.Context(DIM, L, device=local_rank)
     ctx.set_world_boxes(lo, hi)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: the ctx launches on it and the CUDA events are recorded on it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
     # pinned host copies (e2e) and device-resident copies (value)
