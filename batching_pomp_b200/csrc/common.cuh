@@ -11,8 +11,7 @@
 #include "bpomp_cuda.h"
 
 #define BP_ABSENT 0xFFFFFFFFu
-#define BP_GRID_C 16                                  // broad-phase cells per dimension
-#define BP_GRID_TRI (BP_GRID_C * (BP_GRID_C + 1) / 2)  // (c0 <= c1) cell ranges per dimension
+#define BP_GRID_C 64  // broad-phase cells per dimension
 
 // ---------------------------------------------------------------------------
 // Error handling: no exception crosses the ABI.
@@ -59,7 +58,8 @@ struct BoxWorldView {
   int w4;                       // candidate-mask width in uint4 units (power of two >= ceil(B/128))
   int lohi_stride;              // row stride of lohi in double2 units (dim | 1)
   const double2* lohi;          // [B][lohi_stride]  (.x = lo, .y = hi)
-  const uint4* rmask;           // [dim][BP_GRID_TRI][w4] swizzled, boxes overlapping cell range [c0,c1]
+  const uint4* rmask;           // [dim][2][BP_GRID_C][w4] swizzled prefix masks: [j][0][c] = boxes whose
+                                // lowest cell in dim j is <= c, [j][1][c] = boxes whose highest cell is >= c
   double g0[BPOMP_DIM_MAX];     // grid origin per dim
   double gs[BPOMP_DIM_MAX];     // cells per unit length per dim
   size_t rmask_bytes, lohi_bytes;
@@ -180,7 +180,8 @@ __host__ __device__ __forceinline__ int bp_cell(double x, double g0, double gs) 
   return (int)v;
 }
 
-__host__ __device__ __forceinline__ int bp_tri(int c0, int c1) { return c1 * (c1 + 1) / 2 + c0; }
+// Row of the prefix-mask table: which = 0 -> "lowest cell <= c", which = 1 -> "highest cell >= c".
+__host__ __device__ __forceinline__ int bp_row(int j, int which, int c) { return (j * 2 + which) * BP_GRID_C + c; }
 
 // Position of uint4 group w4i of row r inside the row (bank-conflict swizzle, see world.cu).
 __host__ __device__ __forceinline__ int bp_swz(int r, int w4i, int w4) {

@@ -2,15 +2,10 @@
 // /root/reference/src/BatchingPOMP.cpp:496-544, over edges discretised as
 // initializeEdgePoints does, :435-461) against the device-resident collision world.
 //
-// One thread per edge (DESIGN.md explains why not warp-per-edge: an FP64 instruction costs the
-// same issue slots for 1 or 32 active lanes, and a 7-DoF edge at the default resolution has
-// only ~5 checked samples).  Per edge:
-//   A. load both endpoints, distance (sequential unfused FP64), nStates;
-//   B. broad phase: AND the per-dimension cell-range masks of the edge's AABB (shared memory,
-//      staged once per CTA with a bulk async copy), exact AABB filter -> short candidate list;
-//   C. walk the samples in the reference's bisection order and test each against the
-//      candidates only; stop at the first invalid one.
-// Edges with no candidate box are FREE without interpolating a single state.
+// See the comment above edge_check_boxes_kernel for the work decomposition (lane = edge for the
+// per-edge phases, lane = sample for the collision tests; DESIGN.md explains why neither a plain
+// thread-per-edge nor a warp-per-edge mapping fits: an FP64 instruction costs the same issue slots
+// for 1 or 32 active lanes, and a 7-DoF edge at the default resolution has only ~5 checked samples).
 #include <cfloat>
 
 #include "world.cuh"
@@ -91,7 +86,7 @@ __device__ __forceinline__ void load_endpoints(const EdgeArgs& a, int64_t e, dou
   }
 }
 
-// Phase A shared by both worlds.  Returns false when the edge is already decided.
+// Phase A shared by both worlds.  Returns false when the edge is already decided (outputs written).
 template <int D, bool INDEXED>
 __device__ __forceinline__ bool edge_prologue(const EdgeArgs& a, const PermView& pv, int64_t e, double* f, double* t,
                                               uint32_t& n, uint32_t& off) {
@@ -124,19 +119,44 @@ __device__ __forceinline__ bool edge_prologue(const EdgeArgs& a, const PermView&
 }
 
 // ---------------------------------------------------------------------------
-// Box world
+// Box world.
+//
+// A warp owns 32 consecutive edges at a time and runs three phases with uniform control flow:
+//   A/B (lane = edge)   endpoints, distance, nStates; broad phase = AND over the dimensions of the
+//                       prefix masks of the edge's cell range (shared memory) -> candidate boxes;
+//                       edges without candidates are FREE at once.  Endpoint data of the remaining
+//                       edges is parked in a per-warp shared-memory scratch.
+//   C   (lane = sample) the (edge, slot) pairs of the 32 edges are flattened by a warp prefix sum
+//                       and dealt to the lanes 32 at a time, whatever the mix of nStates — a long
+//                       edge simply spreads over many lanes.  Each lane interpolates its state with
+//                       the reference's arithmetic and tests it against its edge's candidates; the
+//                       first invalid slot is a shared-memory atomicMin.
 // ---------------------------------------------------------------------------
+#define EC_WARPS (EC_THREADS / 32)
+
+template <int D>
+struct WarpScratch {
+  static constexpr int kStride = 2 * D + 1;  // doubles per edge (from, to-from), odd -> conflict-free rows
+  double ef[32 * kStride];
+  uint32_t start[33];                        // exclusive prefix of the slots to test per edge
+  uint32_t off[32];                          // offset of the edge's sample-order row
+  int32_t nc[32];                            // candidates (-1: list overflow -> test every box)
+  int32_t first[32];                         // first invalid slot found so far
+  unsigned short list[EC_MAXCAND * 32];      // [c][lane]
+};
+
 template <int D, bool INDEXED, bool STAGE>
 __global__ void __launch_bounds__(EC_THREADS, 1)
     edge_check_boxes_kernel(EdgeArgs a, BoxWorldView w, PermView pv) {
   extern __shared__ __align__(16) unsigned char smem[];
-  // layout: [cand list EC_MAXCAND x EC_THREADS u16][mbarrier 16 B][rmask][lohi]
-  unsigned short* s_list = reinterpret_cast<unsigned short*>(smem);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + EC_MAXCAND * EC_THREADS * 2);
+  // layout: [WarpScratch x EC_WARPS][mbarrier 16 B][prefix masks][lohi]
+  WarpScratch<D>* ws = reinterpret_cast<WarpScratch<D>*>(smem) + (threadIdx.x >> 5);
+  constexpr size_t kScratch = (sizeof(WarpScratch<D>) * EC_WARPS + 15) / 16 * 16;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + kScratch);
   const uint4* rmask = w.rmask;
   const double2* lohi = w.lohi;
   if (STAGE) {
-    uint4* s_rmask = reinterpret_cast<uint4*>(smem + EC_MAXCAND * EC_THREADS * 2 + 16);
+    uint4* s_rmask = reinterpret_cast<uint4*>(smem + kScratch + 16);
     double2* s_lohi = reinterpret_cast<double2*>(reinterpret_cast<unsigned char*>(s_rmask) + w.rmask_bytes);
     if (threadIdx.x == 0) {
       mbar_init(s_bar, 1);
@@ -155,81 +175,119 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
     lohi = s_lohi;
   }
 
-  const int tid = threadIdx.x;
-  for (int64_t e = (int64_t)blockIdx.x * EC_THREADS + tid; e < a.count; e += (int64_t)gridDim.x * EC_THREADS) {
-    double f[D], t[D];
-    uint32_t n, off;
-    if (!edge_prologue<D, INDEXED>(a, pv, e, f, t, n, off)) continue;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * EC_WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * EC_WARPS;
+  constexpr int kS = WarpScratch<D>::kStride;
+  volatile int32_t* vfirst = ws->first;
 
-    // ---- B. broad phase --------------------------------------------------------------
+  for (int64_t base = warp0 * 32; base < a.count; base += nwarps * 32) {
+    const int64_t e = base + lane;
+    // ---- A. endpoints, distance, nStates (lane = edge) --------------------------------------
+    double f[D], t[D];
+    uint32_t n = 0, off = 0;
+    bool need = e < a.count && edge_prologue<D, INDEXED>(a, pv, e, f, t, n, off);
+
+    // ---- B. broad phase ------------------------------------------------------------------------
     int nc = 0;
-    bool overflow = false;
-    if (w.nboxes > 0) {
-      int row[D];
+    if (need && w.nboxes > 0) {
+      int ra[D], rb[D];
 #pragma unroll
       for (int j = 0; j < D; ++j) {
-        int c0 = bp_cell(fmin(f[j], t[j]), w.g0[j], w.gs[j]);
-        int c1 = bp_cell(fmax(f[j], t[j]), w.g0[j], w.gs[j]);
-        row[j] = j * BP_GRID_TRI + bp_tri(c0, c1);
+        ra[j] = bp_row(j, 0, bp_cell(fmax(f[j], t[j]), w.g0[j], w.gs[j]));  // lowest cell <= c1
+        rb[j] = bp_row(j, 1, bp_cell(fmin(f[j], t[j]), w.g0[j], w.gs[j]));  // highest cell >= c0
       }
       for (int g = 0; g < w.w4; ++g) {
         uint4 m = make_uint4(~0u, ~0u, ~0u, ~0u);
 #pragma unroll
         for (int j = 0; j < D; ++j) {
-          uint4 v = rmask[(size_t)row[j] * w.w4 + bp_swz(row[j], g, w.w4)];
-          m.x &= v.x; m.y &= v.y; m.z &= v.z; m.w &= v.w;
+          uint4 va = rmask[(size_t)ra[j] * w.w4 + bp_swz(ra[j], g, w.w4)];
+          uint4 vb = rmask[(size_t)rb[j] * w.w4 + bp_swz(rb[j], g, w.w4)];
+          m.x &= va.x & vb.x; m.y &= va.y & vb.y; m.z &= va.z & vb.z; m.w &= va.w & vb.w;
         }
-        unsigned words[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          unsigned word = words[k];
-          while (word) {
-            int b = (g * 4 + k) * 32 + (__ffs(word) - 1);
-            word &= word - 1;
-            // exact AABB filter: every sample lies inside the endpoints' box
-            const double2* lh = lohi + (size_t)b * w.lohi_stride;
-            bool hit = true;
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-              double2 v = lh[j];
-              if (fmax(f[j], t[j]) < v.x || fmin(f[j], t[j]) > v.y) { hit = false; break; }
-            }
-            if (hit) {
-              if (nc < EC_MAXCAND) s_list[nc++ * EC_THREADS + tid] = (unsigned short)b;
-              else overflow = true;
-            }
-          }
+        unsigned long long m01 = (unsigned long long)m.x | ((unsigned long long)m.y << 32);
+        unsigned long long m23 = (unsigned long long)m.z | ((unsigned long long)m.w << 32);
+        while (m01) {
+          int b = g * 128 + (__ffsll((long long)m01) - 1);
+          m01 &= m01 - 1;
+          if (nc < EC_MAXCAND) ws->list[nc * 32 + lane] = (unsigned short)b;
+          ++nc;
+        }
+        while (m23) {
+          int b = g * 128 + 64 + (__ffsll((long long)m23) - 1);
+          m23 &= m23 - 1;
+          if (nc < EC_MAXCAND) ws->list[nc * 32 + lane] = (unsigned short)b;
+          ++nc;
         }
       }
     }
+    if (need && nc == 0) {  // no box can touch the edge: FREE without interpolating a state
+      a.valid[e] = BPOMP_EDGE_FREE;
+      a.first[e] = -1;
+      need = false;
+    }
+    uint32_t cnt = need ? n - 2u : 0u;  // slots 1..n-2, BP.cpp:510
+    if (need) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        ws->ef[lane * kS + j] = f[j];
+        ws->ef[lane * kS + D + j] = __dsub_rn(t[j], f[j]);  // interpolate: (to - from)
+      }
+      ws->off[lane] = off;
+      ws->nc[lane] = nc > EC_MAXCAND ? -1 : nc;
+    }
+    ws->first[lane] = 0x7fffffff;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    ws->start[lane] = incl - cnt;
+    if (lane == 31) ws->start[32] = incl;
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    __syncwarp();
 
-    // ---- C. samples in bisection order -------------------------------------------------
-    int32_t bad = -1;
-    if (nc > 0) {
-      double dtf[D];
+    // ---- C. flattened (edge, slot) pairs (lane = sample) ---------------------------------------
+    for (uint32_t ib = 0; ib < total; ib += 32) {
+      const uint32_t it = ib + lane;
+      if (it < total) {
+        int lo_i = 0, hi_i = 32;  // last edge whose first item is <= it
 #pragma unroll
-      for (int j = 0; j < D; ++j) dtf[j] = __dsub_rn(t[j], f[j]);  // interpolate: (to - from)
-      const double* tf = pv.tfrac + off;
-      for (uint32_t i = 1; i + 1 < n; ++i) {  // BP.cpp:510
-        double tt = __ldg(tf + i);            // (1+perm[i])/(n+1), BP.cpp:459
-        double x[D];
-#pragma unroll
-        for (int j = 0; j < D; ++j) x[j] = __dadd_rn(f[j], __dmul_rn(dtf[j], tt));
-        bool inside = false;
-        if (!overflow) {
-          for (int c = 0; c < nc; ++c) {
-            int b = s_list[c * EC_THREADS + tid];
-            if (bp_inside_box<D>(x, lohi + (size_t)b * w.lohi_stride)) { inside = true; break; }
-          }
-        } else {  // more candidates than the list holds: test every box (rare)
-          for (int b = 0; b < w.nboxes; ++b)
-            if (bp_inside_box<D>(x, lohi + (size_t)b * w.lohi_stride)) { inside = true; break; }
+        for (int s = 0; s < 5; ++s) {
+          int mid = (lo_i + hi_i) >> 1;
+          if (ws->start[mid] <= it) lo_i = mid; else hi_i = mid;
         }
-        if (inside) { bad = (int32_t)i; break; }
+        const int el = lo_i;
+        const int32_t slot = (int32_t)(1u + it - ws->start[el]);
+        if (slot < vfirst[el]) {  // a smaller invalid slot is already known: nothing to add
+          const double tt = __ldg(pv.tfrac + ws->off[el] + slot);  // (1+perm[i])/(n+1), BP.cpp:459
+          double x[D];
+#pragma unroll
+          for (int j = 0; j < D; ++j)
+            x[j] = __dadd_rn(ws->ef[el * kS + j], __dmul_rn(ws->ef[el * kS + D + j], tt));
+          const int ncl = ws->nc[el];
+          bool inside = false;
+          if (ncl >= 0) {
+            for (int c = 0; c < ncl; ++c) {
+              const int b = ws->list[c * 32 + el];
+              if (bp_inside_box<D>(x, lohi + (size_t)b * w.lohi_stride)) { inside = true; break; }
+            }
+          } else {  // more candidates than the list holds: test every box (rare)
+            for (int b = 0; b < w.nboxes; ++b)
+              if (bp_inside_box<D>(x, lohi + (size_t)b * w.lohi_stride)) { inside = true; break; }
+          }
+          if (inside) atomicMin(&ws->first[el], slot);
+        }
       }
     }
-    a.valid[e] = bad < 0 ? BPOMP_EDGE_FREE : BPOMP_EDGE_BLOCKED;
-    a.first[e] = bad;
+    __syncwarp();
+    if (need) {
+      const int32_t bad = vfirst[lane] == 0x7fffffff ? -1 : vfirst[lane];
+      a.valid[e] = bad < 0 ? BPOMP_EDGE_FREE : BPOMP_EDGE_BLOCKED;
+      a.first[e] = bad;
+    }
+    __syncwarp();
   }
 }
 
@@ -263,7 +321,7 @@ __global__ void __launch_bounds__(256) edge_check_image_kernel(EdgeArgs a, Image
 template <int D, bool INDEXED>
 static int launch_boxes(bpomp_ctx* ctx, const EdgeArgs& a) {
   const BoxWorldView& w = ctx->boxes;
-  size_t base = (size_t)EC_MAXCAND * EC_THREADS * 2 + 16;
+  size_t base = (sizeof(WarpScratch<D>) * EC_WARPS + 15) / 16 * 16 + 16;
   size_t staged = base + w.rmask_bytes + w.lohi_bytes;
   bool stage = staged <= (size_t)ctx->smem_optin && w.rmask_bytes + w.lohi_bytes < (1u << 20) && w.nboxes > 0;
   int64_t tiles = (a.count + EC_THREADS - 1) / EC_THREADS;

@@ -58,10 +58,12 @@ extern "C" int bpomp_world_set_boxes(bpomp_ctx* ctx, const double* lo, const dou
     w.gs[j] = (nboxes > 0 && std::isfinite(span) && span > 0.0) ? (double)BP_GRID_C / span : 0.0;
     if (!std::isfinite(w.gs[j])) w.gs[j] = 0.0;
   }
-  // rmask[j][tri(c0,c1)] = boxes whose cell interval [cell(lo_j), cell(hi_j)] meets [c0,c1].
-  // bp_cell is monotone, so any x in [lo_j,hi_j] has cell(x) inside the box's interval: the mask
-  // of the cell range spanned by a segment's endpoints is a superset of the boxes it can touch.
-  size_t rows = (size_t)D * BP_GRID_TRI;
+  // Prefix masks per dimension j and cell c (bp_row): "lowest cell of the box <= c" and "highest cell
+  // of the box >= c".  A box's cell interval [cell(lo_j), cell(hi_j)] meets the cell range [c0,c1] iff
+  // lowest <= c1 and highest >= c0, i.e. mask(j,0,c1) & mask(j,1,c0).  bp_cell is monotone, so any x in
+  // [lo_j,hi_j] has cell(x) inside the box's interval: the AND over all dimensions of the masks of the
+  // cell range spanned by a segment's endpoints is a superset of the boxes the segment can touch.
+  size_t rows = (size_t)D * 2 * BP_GRID_C;
   std::vector<uint32_t> rmask(rows * w4 * 4, 0u);
   std::vector<double2> lohi((size_t)std::max(nboxes, 1) * w.lohi_stride, make_double2(1.0, 0.0));
   for (int b = 0; b < nboxes; ++b) {
@@ -72,17 +74,20 @@ extern "C" int bpomp_world_set_boxes(bpomp_ctx* ctx, const double* lo, const dou
       if (!(l <= h)) empty = true;  // contains nothing (also NaN bounds)
     }
     if (empty) continue;
+    const int word = b >> 5, g = word >> 2;
     for (int j = 0; j < D; ++j) {
       int cl = bp_cell(lo[(size_t)b * D + j], w.g0[j], w.gs[j]);
       int ch = bp_cell(hi[(size_t)b * D + j], w.g0[j], w.gs[j]);
-      for (int c1 = 0; c1 < BP_GRID_C; ++c1)
-        for (int c0 = 0; c0 <= c1; ++c0) {
-          if (!(cl <= c1 && ch >= c0)) continue;
-          int row = j * BP_GRID_TRI + bp_tri(c0, c1);
-          int word = b >> 5, g = word >> 2;
-          size_t u4 = (size_t)row * w4 + bp_swz(row, g, w4);
-          rmask[u4 * 4 + (word & 3)] |= 1u << (b & 31);
+      for (int c = 0; c < BP_GRID_C; ++c) {
+        if (cl <= c) {
+          int row = bp_row(j, 0, c);
+          rmask[((size_t)row * w4 + bp_swz(row, g, w4)) * 4 + (word & 3)] |= 1u << (b & 31);
         }
+        if (ch >= c) {
+          int row = bp_row(j, 1, c);
+          rmask[((size_t)row * w4 + bp_swz(row, g, w4)) * 4 + (word & 3)] |= 1u << (b & 31);
+        }
+      }
     }
   }
   w.rmask_bytes = rmask.size() * sizeof(uint32_t);

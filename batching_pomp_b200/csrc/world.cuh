@@ -28,23 +28,22 @@ __device__ __forceinline__ bool bp_inside_box(const double* x, const double2* lo
   return true;
 }
 
-// Point query through the cell-range masks (range [c,c]).  rmask/lohi may point to shared or global.
+// Point query through the prefix masks (cell range [c,c]).  rmask/lohi may point to shared or global.
 template <int D>
 __device__ __forceinline__ bool bp_valid_boxes(const double* x, const BoxWorldView& w, const uint4* rmask,
                                                const double2* lohi) {
   if (w.nboxes == 0) return true;
-  int row[D];
+  int cell[D];
 #pragma unroll
-  for (int j = 0; j < D; ++j) {
-    int c = bp_cell(x[j], w.g0[j], w.gs[j]);
-    row[j] = j * BP_GRID_TRI + bp_tri(c, c);
-  }
+  for (int j = 0; j < D; ++j) cell[j] = bp_cell(x[j], w.g0[j], w.gs[j]);
   for (int g = 0; g < w.w4; ++g) {
     uint4 m = make_uint4(~0u, ~0u, ~0u, ~0u);
 #pragma unroll
     for (int j = 0; j < D; ++j) {
-      uint4 v = rmask[(size_t)row[j] * w.w4 + bp_swz(row[j], g, w.w4)];
-      m.x &= v.x; m.y &= v.y; m.z &= v.z; m.w &= v.w;
+      int ra = bp_row(j, 0, cell[j]), rb = bp_row(j, 1, cell[j]);
+      uint4 va = rmask[(size_t)ra * w.w4 + bp_swz(ra, g, w.w4)];
+      uint4 vb = rmask[(size_t)rb * w.w4 + bp_swz(rb, g, w.w4)];
+      m.x &= va.x & vb.x; m.y &= va.y & vb.y; m.z &= va.z & vb.z; m.w &= va.w & vb.w;
     }
     unsigned words[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
