@@ -58,8 +58,9 @@ struct BoxWorldView {
   int w4;                       // candidate-mask width in uint4 units (power of two >= ceil(B/128))
   int lohi_stride;              // row stride of lohi in double2 units (dim | 1)
   const double2* lohi;          // [B][lohi_stride]  (.x = lo, .y = hi)
-  const uint4* rmask;           // [dim][2][BP_GRID_C][w4] swizzled prefix masks: [j][0][c] = boxes whose
-                                // lowest cell in dim j is <= c, [j][1][c] = boxes whose highest cell is >= c
+  const uint4* rmask;           // [w4][rows] prefix masks, rows = dim*2*BP_GRID_C (bp_row): row (j,0,c) = boxes
+                                // whose lowest cell in dim j is <= c, row (j,1,c) = boxes whose highest cell is >= c
+  int rows;
   double g0[BPOMP_DIM_MAX];     // grid origin per dim
   double gs[BPOMP_DIM_MAX];     // cells per unit length per dim
   size_t rmask_bytes, lohi_bytes;
@@ -183,10 +184,8 @@ __host__ __device__ __forceinline__ int bp_cell(double x, double g0, double gs) 
 // Row of the prefix-mask table: which = 0 -> "lowest cell <= c", which = 1 -> "highest cell >= c".
 __host__ __device__ __forceinline__ int bp_row(int j, int which, int c) { return (j * 2 + which) * BP_GRID_C + c; }
 
-// Position of uint4 group w4i of row r inside the row (bank-conflict swizzle, see world.cu).
-__host__ __device__ __forceinline__ int bp_swz(int r, int w4i, int w4) {
-  int rows128 = w4 >= 8 ? 1 : 8 / w4;
-  return w4i ^ ((r / rows128) & (w4 - 1));
-}
+// Index of uint4 group g (boxes 128g .. 128g+127) of mask row `row`: the table is group-major,
+// [w4][rows], so the lanes of a warp (different rows, same g) spread over all shared-memory banks.
+__host__ __device__ __forceinline__ size_t bp_midx(int row, int g, int rows) { return (size_t)g * rows + row; }
 
 #endif  // __CUDACC__

@@ -183,6 +183,17 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
 
   for (int64_t base = warp0 * 32; base < a.count; base += nwarps * 32) {
     const int64_t e = base + lane;
+    if (!INDEXED) {  // pull the next tile's endpoint rows (contiguous) towards L2 while this one is processed
+      const int64_t nb = base + nwarps * 32;
+      constexpr int kLines = (32 * D * 8 + 127) / 128 + 1;
+      if (nb < a.count && lane < kLines) {
+        const size_t o = (size_t)nb * D * 8 + (size_t)lane * 128;
+        if (o < (size_t)a.count * D * 8) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(a.from) + o));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(a.to) + o));
+        }
+      }
+    }
     // ---- A. endpoints, distance, nStates (lane = edge) --------------------------------------
     double f[D], t[D];
     uint32_t n = 0, off = 0;
@@ -201,8 +212,8 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
         uint4 m = make_uint4(~0u, ~0u, ~0u, ~0u);
 #pragma unroll
         for (int j = 0; j < D; ++j) {
-          uint4 va = rmask[(size_t)ra[j] * w.w4 + bp_swz(ra[j], g, w.w4)];
-          uint4 vb = rmask[(size_t)rb[j] * w.w4 + bp_swz(rb[j], g, w.w4)];
+          uint4 va = rmask[bp_midx(ra[j], g, w.rows)];
+          uint4 vb = rmask[bp_midx(rb[j], g, w.rows)];
           m.x &= va.x & vb.x; m.y &= va.y & vb.y; m.z &= va.z & vb.z; m.w &= va.w & vb.w;
         }
         unsigned long long m01 = (unsigned long long)m.x | ((unsigned long long)m.y << 32);

@@ -63,8 +63,9 @@ extern "C" int bpomp_world_set_boxes(bpomp_ctx* ctx, const double* lo, const dou
   // lowest <= c1 and highest >= c0, i.e. mask(j,0,c1) & mask(j,1,c0).  bp_cell is monotone, so any x in
   // [lo_j,hi_j] has cell(x) inside the box's interval: the AND over all dimensions of the masks of the
   // cell range spanned by a segment's endpoints is a superset of the boxes the segment can touch.
-  size_t rows = (size_t)D * 2 * BP_GRID_C;
-  std::vector<uint32_t> rmask(rows * w4 * 4, 0u);
+  const int rows = D * 2 * BP_GRID_C;
+  w.rows = rows;
+  std::vector<uint32_t> rmask((size_t)rows * w4 * 4, 0u);
   std::vector<double2> lohi((size_t)std::max(nboxes, 1) * w.lohi_stride, make_double2(1.0, 0.0));
   for (int b = 0; b < nboxes; ++b) {
     bool empty = false;
@@ -81,11 +82,11 @@ extern "C" int bpomp_world_set_boxes(bpomp_ctx* ctx, const double* lo, const dou
       for (int c = 0; c < BP_GRID_C; ++c) {
         if (cl <= c) {
           int row = bp_row(j, 0, c);
-          rmask[((size_t)row * w4 + bp_swz(row, g, w4)) * 4 + (word & 3)] |= 1u << (b & 31);
+          rmask[bp_midx(row, g, rows) * 4 + (word & 3)] |= 1u << (b & 31);
         }
         if (ch >= c) {
           int row = bp_row(j, 1, c);
-          rmask[((size_t)row * w4 + bp_swz(row, g, w4)) * 4 + (word & 3)] |= 1u << (b & 31);
+          rmask[bp_midx(row, g, rows) * 4 + (word & 3)] |= 1u << (b & 31);
         }
       }
     }

@@ -41,8 +41,8 @@ __device__ __forceinline__ bool bp_valid_boxes(const double* x, const BoxWorldVi
 #pragma unroll
     for (int j = 0; j < D; ++j) {
       int ra = bp_row(j, 0, cell[j]), rb = bp_row(j, 1, cell[j]);
-      uint4 va = rmask[(size_t)ra * w.w4 + bp_swz(ra, g, w.w4)];
-      uint4 vb = rmask[(size_t)rb * w.w4 + bp_swz(rb, g, w.w4)];
+      uint4 va = rmask[bp_midx(ra, g, w.rows)];
+      uint4 vb = rmask[bp_midx(rb, g, w.rows)];
       m.x &= va.x & vb.x; m.y &= va.y & vb.y; m.z &= va.z & vb.z; m.w &= va.w & vb.w;
     }
     unsigned words[4] = {m.x, m.y, m.z, m.w};
