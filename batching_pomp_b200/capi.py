@@ -35,6 +35,7 @@ SIGNATURES = {
     "bpomp_states_valid": (C.c_int, [vp, vp, C.c_int64, vp]),
     "bpomp_states_valid_dev": (C.c_int, [vp, vp, C.c_int64, vp]),
     "bpomp_states_prune": (C.c_int, [vp, vp, C.c_int64, vp, vp, C.c_double, C.c_int, vp]),
+    "bpomp_vertices_prune": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_double, C.c_int, vp]),
     "bpomp_vertices_append": (C.c_int, [vp, vp, C.c_uint32, c_u32p]),
     "bpomp_vertices_set_active": (C.c_int, [vp, vp, C.c_uint32, C.c_int]),
     "bpomp_vertices_count": (C.c_int, [vp, c_u32p]),
@@ -161,6 +162,12 @@ class Context:
         out = np.empty(s.shape[0], dtype=np.uint8)
         self._ck(self.lib.bpomp_states_prune(self.h, _ptr(s), s.shape[0], _ptr(st), _ptr(go), float(best_cost),
                                              1 if check_validity else 0, _ptr(out)))
+        return out
+
+    def vertices_prune(self, start_id, goal_id, best_cost, check_validity=False):
+        out = np.empty(self.vertices_count(), dtype=np.uint8)
+        self._ck(self.lib.bpomp_vertices_prune(self.h, int(start_id), int(goal_id), float(best_cost),
+                                               1 if check_validity else 0, _ptr(out)))
         return out
 
     # ---- vertices / neighbours -----------------------------------------------------------

@@ -313,11 +313,11 @@ __global__ void nb_rowptr_kernel(const uint64_t* __restrict__ offs, uint32_t nq,
 }
 
 // ---------------------------------------------------------------------------
-// Row sort by (dist, id).  Rank sort out of shared memory: small rows one warp each, medium rows
-// one block each; rows beyond NB_MEDIUM use a global bitonic network (rare: huge radius).
+// Row sort by (dist, id).  Small rows: rank sort, one warp each.  Medium rows: bitonic network in
+// shared memory, one block each.  Rows beyond NB_MEDIUM: global bitonic network (huge radius only).
 // ---------------------------------------------------------------------------
 #define NB_SMALL 128
-#define NB_MEDIUM 4096
+#define NB_MEDIUM 8192
 
 __device__ __forceinline__ bool nb_less(double da, uint32_t ia, double db, uint32_t ib) {
   return da < db || (da == db && ia < ib);
@@ -348,7 +348,9 @@ __global__ void __launch_bounds__(256) nb_sort_small(const uint64_t* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(256) nb_sort_medium(const uint64_t* __restrict__ row_ptr, uint32_t nq,
+// Medium rows: one block per row, ascending-only bitonic network in shared memory (virtual
+// power-of-two length; slots >= len act as +infinity and are never touched).
+__global__ void __launch_bounds__(512) nb_sort_medium(const uint64_t* __restrict__ row_ptr, uint32_t nq,
                                                       const double* __restrict__ in_d, const uint32_t* __restrict__ in_i,
                                                       double* __restrict__ out_d, uint32_t* __restrict__ out_i) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -358,17 +360,26 @@ __global__ void __launch_bounds__(256) nb_sort_medium(const uint64_t* __restrict
     uint64_t o = row_ptr[q];
     unsigned long long len64 = row_ptr[q + 1] - o;
     if (len64 <= NB_SMALL || len64 > NB_MEDIUM) continue;
-    uint32_t len = (uint32_t)len64;
+    const uint32_t len = (uint32_t)len64;
+    uint32_t npad = 1;
+    while (npad < len) npad <<= 1;
     for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) { sd[i] = in_d[o + i]; si[i] = in_i[o + i]; }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
-      double d = sd[i];
-      uint32_t id = si[i];
-      uint32_t rank = 0;
-      for (uint32_t k = 0; k < len; ++k) rank += nb_less(sd[k], si[k], d, id) ? 1u : 0u;
-      out_d[o + rank] = d;
-      out_i[o + rank] = id;
+    for (uint32_t k = 2; k <= npad; k <<= 1) {
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        const uint32_t mask = (j == (k >> 1)) ? k - 1 : j;  // first step of a merge mirrors, the rest shift
+        for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) {
+          uint32_t l = i ^ mask;
+          if (l > i && l < len) {
+            double di = sd[i], dl = sd[l];
+            uint32_t ii = si[i], il = si[l];
+            if (nb_less(dl, il, di, ii)) { sd[i] = dl; sd[l] = di; si[i] = il; si[l] = ii; }
+          }
+        }
+        __syncthreads();
+      }
     }
+    for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) { out_d[o + i] = sd[i]; out_i[o + i] = si[i]; }
     __syncthreads();
   }
 }
@@ -554,7 +565,7 @@ static int neighbors_impl(bpomp_ctx* ctx, const uint32_t* d_query, uint32_t nq, 
     if (maxrow > NB_SMALL) {
       size_t sm = NB_MEDIUM * (sizeof(double) + sizeof(uint32_t));
       BP_CUDA(ctx, cudaFuncSetAttribute(nb_sort_medium, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      nb_sort_medium<<<(int)std::min<uint32_t>(nq, (uint32_t)ctx->num_sms * 4), 256, sm, ctx->stream>>>(
+      nb_sort_medium<<<(int)std::min<uint32_t>(nq, (uint32_t)ctx->num_sms * 2), 512, sm, ctx->stream>>>(
           rp, nq, a.out_dist, a.out_id, ctx->d_nb_dist.as<double>(), ctx->d_nb_col.as<uint32_t>());
       ctx->launches++;
     }

@@ -251,3 +251,47 @@ extern "C" int bpomp_states_prune(bpomp_ctx* ctx, const double* states, int64_t 
   BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return BPOMP_OK;
 }
+
+extern "C" int bpomp_vertices_prune(bpomp_ctx* ctx, uint32_t start_id, uint32_t goal_id, double best_cost,
+                                    int check_validity, uint8_t* out) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  const uint32_t count = ctx->nverts;
+  if (count == 0) return BPOMP_OK;
+  if (!out) return bp_fail(ctx, BPOMP_ERR_INVALID, "out is NULL");
+  if (start_id >= count || goal_id >= count) return bp_fail(ctx, BPOMP_ERR_RANGE, "start/goal id out of range");
+  if (check_validity && ctx->world == WORLD_NONE) return bp_fail(ctx, BPOMP_ERR_NO_WORLD, "no collision world set");
+  const int D = ctx->dim;
+  BP_TRY(bp_reserve(ctx, ctx->s_c, (size_t)count, false));
+  BP_TRY(bp_reserve(ctx, ctx->s_d, (size_t)count, false));
+  const double* s = ctx->d_verts.as<double>();
+  const uint8_t* d_valid = nullptr;
+  if (check_validity) {
+    BP_TRY(bp_launch_states_valid(ctx, s, count, ctx->s_c.as<uint8_t>()));
+    d_valid = ctx->s_c.as<uint8_t>();
+  }
+  PruneArgs a;
+  memset(&a, 0, sizeof(a));
+  BP_CUDA(ctx, cudaMemcpyAsync(a.start, s + (size_t)start_id * D, D * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA(ctx, cudaMemcpyAsync(a.goal, s + (size_t)goal_id * D, D * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  a.best = best_cost;
+  a.use_cost = best_cost < DBL_MAX ? 1 : 0;
+  int grid = (int)std::min<int64_t>(((int64_t)count + 255) / 256, (int64_t)ctx->num_sms * 8);
+  uint8_t* o = ctx->s_d.as<uint8_t>();
+  switch (D) {
+    case 1: states_prune_kernel<1><<<grid, 256, 0, ctx->stream>>>(s, count, a, d_valid, o); break;
+    case 2: states_prune_kernel<2><<<grid, 256, 0, ctx->stream>>>(s, count, a, d_valid, o); break;
+    case 3: states_prune_kernel<3><<<grid, 256, 0, ctx->stream>>>(s, count, a, d_valid, o); break;
+    case 4: states_prune_kernel<4><<<grid, 256, 0, ctx->stream>>>(s, count, a, d_valid, o); break;
+    case 5: states_prune_kernel<5><<<grid, 256, 0, ctx->stream>>>(s, count, a, d_valid, o); break;
+    case 6: states_prune_kernel<6><<<grid, 256, 0, ctx->stream>>>(s, count, a, d_valid, o); break;
+    case 7: states_prune_kernel<7><<<grid, 256, 0, ctx->stream>>>(s, count, a, d_valid, o); break;
+    case 8: states_prune_kernel<8><<<grid, 256, 0, ctx->stream>>>(s, count, a, d_valid, o); break;
+    default: return bp_fail(ctx, BPOMP_ERR_INVALID, "unsupported dim %d", D);
+  }
+  ctx->launches++;
+  BP_CUDA(ctx, cudaGetLastError());
+  BP_CUDA(ctx, cudaMemcpyAsync(out, o, (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BPOMP_OK;
+}

@@ -1,0 +1,889 @@
+// BatchingPOMP.cpp — host planner of the B200 build.  Independent re-implementation of the
+// control flow of /root/reference/src/BatchingPOMP.cpp (cited as BP.cpp) on flat arrays, with the
+// hot operators batched into CUDA calls through include/bpomp_cuda.h:
+//   nearestR (BP.cpp:150)                       -> bpomp_neighbors_all / bpomp_neighbors_radius
+//   isValid loop (BP.cpp:510-538)               -> bpomp_edges_check_indexed (+ belief_append_checked)
+//   computeAndSetEdgeFreeProbability (:464-493) -> bpomp_belief_edge_pfree_indexed
+//   vertexPruneFunction (:650-656)              -> bpomp_states_prune / bpomp_vertices_prune
+// Batching never changes observable behaviour: results are committed in the reference's order
+// (edge creation order, path order, counters), see DESIGN.md "Host planner".
+#include "BatchingPOMP.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+#include "graphml.hpp"
+
+namespace batching_pomp {
+
+namespace {
+const double kInf = std::numeric_limits<double>::max();
+
+inline double closedPlus(double a, double b) {  // boost::closed_plus<double>(DBL_MAX), BP.cpp:893
+  if (a == kInf) return kInf;
+  if (b == kInf) return kInf;
+  return a + b;
+}
+inline uint64_t edgeKey(uint32_t u, uint32_t v) {
+  uint32_t a = u < v ? u : v, b = u < v ? v : u;
+  return ((uint64_t)a << 32) | b;
+}
+// RealVectorStateSpace::distance (host copy, used for the few scalar evaluations the host needs)
+inline double rvDistance(const double* a, const double* b, unsigned d) {
+  double dist = 0.0;
+  for (unsigned j = 0; j < d; ++j) {
+    double diff = a[j] - b[j];
+    dist += diff * diff;
+  }
+  return std::sqrt(dist);
+}
+inline double now() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// SpaceInformation
+// ---------------------------------------------------------------------------
+double SpaceInformation::getMaximumExtent() const {
+  double e = 0.0;
+  for (unsigned j = 0; j < dim; ++j) {
+    double d = high[j] - low[j];
+    e += d * d;
+  }
+  return std::sqrt(e);
+}
+double SpaceInformation::getLongestValidSegmentLength() const {
+  return getMaximumExtent() * longestValidSegmentFraction;
+}
+double SpaceInformation::getSpaceMeasure() const {
+  double m = 1.0;
+  for (unsigned j = 0; j < dim; ++j) m *= high[j] - low[j];
+  return m;
+}
+
+// ---------------------------------------------------------------------------
+// construction
+// ---------------------------------------------------------------------------
+BatchingPOMP::BatchingPOMP(const SpaceInformation& si)
+    : mSi(si), mDim(si.dim), mCtx(nullptr), mCurrentAlpha(0.0), mIncrement(0.2), mStartGoalRadius(0.0),
+      mPruneThreshold(1.05), mIsInitSearchBatch(true), mIsPathFound(false), mUsingSelector(false),
+      mBestPathCost(kInf), mSelType("normal"), mN(0), mFlushed(0), mStartVertex(0), mGoalVertex(0),
+      mHaveProblem(false), mEpoch(0), mCsrValid(false), mCsrRadius(0.0), mCsrBudget(30000000ull), bmNumBatches(0),
+      bmExhausted(false), bmCurrRadius(0.0), bmNumVerticesAdded(0), bmNextVertexTarget(0), bmVertInfl(2.0),
+      bmRadiusInfl(1.0), bmInitRadius(0.0), bmMaxRadius(0.0), bmCurrVertex(0), bmEdgeMode(false), mNumSolutions(0),
+      mBeliefEmpty(true), mNumEdgeChecks(0), mNumCollChecks(0), mNumSearches(0), mNumLookups(0), mLookupTime(0.0),
+      mCollCheckTime(0.0), mSearchTime(0.0) {
+  if (mDim == 0 || si.low.size() != mDim || si.high.size() != mDim)
+    throw Exception("SpaceInformation: bounds must have `dim` entries");
+  // mCheckRadius = 0.5*getLongestValidSegmentLength() is captured at construction (BP.cpp:241,278);
+  // 2.0*mCheckRadius == L exactly, which is what the device library takes.
+  mL = si.getLongestValidSegmentLength();
+  mMaxExtent = si.getMaximumExtent();
+  mSpaceMeasure = si.getSpaceMeasure();
+  int rc = bpomp_create(si.device, (int)mDim, mL, &mCtx);
+  if (rc != BPOMP_OK) throw Exception(std::string("bpomp_create: ") + bpomp_last_error(nullptr));
+  try {
+    if (si.world == SpaceInformation::World::BOXES) {
+      int nb = (int)(si.boxLo.size() / mDim);
+      check(bpomp_world_set_boxes(mCtx, si.boxLo.data(), si.boxHi.data(), nb));
+    } else if (si.world == SpaceInformation::World::IMAGE) {
+      check(bpomp_world_set_image(mCtx, si.image.data(), si.imageWidth, si.imageHeight, si.imageThreshold));
+    } else {
+      throw Exception("the StateValidityChecker must be described as a device world (boxes or image); "
+                      "there is no CPU fallback");
+    }
+    // default belief model: KNNModel(15, 0.5, 0.25, ...) (BP.cpp:300)
+    check(bpomp_belief_config(mCtx, 15, 0.5, 0.25));
+  } catch (...) {
+    bpomp_destroy(mCtx);
+    mCtx = nullptr;
+    throw;
+  }
+}
+
+BatchingPOMP::~BatchingPOMP() {
+  if (mCtx) bpomp_destroy(mCtx);
+}
+
+void BatchingPOMP::check(int rc) const {
+  if (rc != BPOMP_OK) throw Exception(std::string("bpomp: ") + bpomp_last_error(mCtx));
+}
+
+void BatchingPOMP::setParam(const std::string& name, const std::string& value) {
+  if (name == "increment") setIncrement(std::stod(value));
+  else if (name == "start_goal_radius") setStartGoalRadius(std::stod(value));
+  else if (name == "prune_threshold") setPruneThreshold(std::stod(value));
+  else if (name == "graph_type") setGraphType(value);
+  else if (name == "batching_type") setBatchingType(value);
+  else if (name == "selector_type") setSelectorType(value);
+  else if (name == "roadmap_filename") setRoadmapFileName(value);
+  else throw Exception("unknown parameter " + name);
+}
+
+std::string BatchingPOMP::getParam(const std::string& name) const {
+  if (name == "increment") return std::to_string(mIncrement);
+  if (name == "start_goal_radius") return std::to_string(mStartGoalRadius);
+  if (name == "prune_threshold") return std::to_string(mPruneThreshold);
+  if (name == "graph_type") return mGraphType;
+  if (name == "batching_type") return mBatchingType;
+  if (name == "selector_type") return mSelectorType;
+  if (name == "roadmap_filename") return mRoadmapName;
+  throw Exception("unknown parameter " + name);
+}
+
+void BatchingPOMP::setRoadmap(const std::vector<double>& states,
+                              const std::vector<std::pair<uint32_t, uint32_t>>& edges) {
+  if (states.size() % mDim) throw Exception("roadmap states must be [n][dim]");
+  mRoadmap = states;
+  mRoadmapEdges = edges;
+  mN = (uint32_t)(states.size() / mDim);
+  if (mRoadmapName.empty()) mRoadmapName = "<memory>";
+}
+
+std::vector<double> BatchingPOMP::getSolutionStates() const {
+  std::vector<double> out;
+  for (Vertex v : mSolutionVertices) out.insert(out.end(), vertexState(v), vertexState(v) + mDim);
+  return out;
+}
+
+// ---------------------------------------------------------------------------
+// graph
+// ---------------------------------------------------------------------------
+BatchingPOMP::Vertex BatchingPOMP::addVertex(const double* state, bool inNN) {
+  mVState.insert(mVState.end(), state, state + mDim);
+  mOut.emplace_back();
+  mNNActive.push_back(inNN ? 1 : 0);
+  return (Vertex)mOut.size() - 1;
+}
+
+BatchingPOMP::Edge BatchingPOMP::addEdge(Vertex u, Vertex v) {
+  EProps e;
+  e.source = u;
+  e.target = v;
+  e.distance = 0.0;
+  e.probFree = 0.0;
+  e.blockedStatus = UNKNOWN;
+  e.nStates = 0;
+  e.removed = false;
+  mEdges.push_back(e);
+  Edge id = (Edge)mEdges.size() - 1;
+  mOut[u].push_back({v, id});
+  mOut[v].push_back({u, id});
+  mEdgeIndex.emplace(edgeKey(u, v), id);  // first edge wins, as boost::edge's scan returns the first
+  mEdgeMarked.push_back(0);
+  return id;
+}
+
+bool BatchingPOMP::hasEdge(Vertex u, Vertex v) const { return mEdgeIndex.find(edgeKey(u, v)) != mEdgeIndex.end(); }
+
+BatchingPOMP::Edge BatchingPOMP::findEdge(Vertex u, Vertex v) const {
+  auto it = mEdgeIndex.find(edgeKey(u, v));
+  if (it == mEdgeIndex.end()) return (Edge)-1;
+  return it->second;
+}
+
+void BatchingPOMP::clearVertex(Vertex v) {  // boost::clear_vertex, BatchingManager.hpp:163
+  for (const OutEdge& oe : mOut[v]) {
+    mEdges[oe.eid].removed = true;
+    auto it = mEdgeIndex.find(edgeKey(v, oe.target));
+    if (it != mEdgeIndex.end() && it->second == oe.eid) mEdgeIndex.erase(it);
+    if (oe.target == v) continue;
+    std::vector<OutEdge>& o = mOut[oe.target];
+    o.erase(std::remove_if(o.begin(), o.end(), [&](const OutEdge& x) { return x.eid == oe.eid; }), o.end());
+  }
+  mOut[v].clear();
+}
+
+// Appends not-yet-resident vertices to the device table (ids coincide with the g vertex ids).
+void BatchingPOMP::flushVertices() {
+  uint32_t nv = (uint32_t)mOut.size();
+  if (mFlushed < nv) {
+    uint32_t first = 0;
+    check(bpomp_vertices_append(mCtx, &mVState[(size_t)mFlushed * mDim], nv - mFlushed, &first));
+    if (first != mFlushed) throw Exception("internal: device vertex ids out of step with the roadmap");
+    std::vector<uint32_t> off;
+    for (uint32_t v = mFlushed; v < nv; ++v)
+      if (!mNNActive[v]) off.push_back(v);
+    if (!off.empty()) check(bpomp_vertices_set_active(mCtx, off.data(), (uint32_t)off.size(), 0));
+    mFlushed = nv;
+  }
+  if (!mPendingDeactivate.empty()) {
+    check(bpomp_vertices_set_active(mCtx, mPendingDeactivate.data(), (uint32_t)mPendingDeactivate.size(), 0));
+    mPendingDeactivate.clear();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// radius functions — BP.cpp:548-574 (host libm; results are passed to the device as doubles)
+// ---------------------------------------------------------------------------
+double BatchingPOMP::radiusFun(unsigned int n) const {
+  auto dimDbl = static_cast<double>(mDim);
+  auto cardDbl = static_cast<double>(n);
+  if (mGraphType == "halton") return 2.5 * std::pow(1.0 / cardDbl, 1 / dimDbl);
+  double approximationMeasure = mSpaceMeasure;
+  if (!std::isfinite(approximationMeasure)) throw Exception("Measure of space is unbounded!");
+  // ompl::unitNBallMeasure
+  double unitBall = std::pow(std::sqrt(M_PI), dimDbl) / std::tgamma(dimDbl / 2.0 + 1.0);
+  double minRggR = 2.0 * std::pow((1.0 + 1.0 / dimDbl) * (approximationMeasure / unitBall), 1.0 / dimDbl);
+  return minRggR * std::pow(std::log(cardDbl) / cardDbl, 1 / dimDbl);
+}
+
+// ---------------------------------------------------------------------------
+// setup — BP.cpp:668-757
+// ---------------------------------------------------------------------------
+void BatchingPOMP::setup() {
+  if (mGraphType != "halton" && mGraphType != "rgg") {
+    if (mBatchingType == "edge" || mBatchingType == "hybrid")
+      throw Exception("Invalid graph type specified! Graph type needed for hybrid or edge batching!");
+  }
+  if (mRoadmapName == "") throw Exception("Roadmap name must be set before creating batching manager!");
+  if (mRoadmap.empty() && mRoadmapName != "<memory>") {
+    // RoadmapFromFile::generateVertices (util/RoadmapFromFile.hpp:136-147)
+    std::vector<double> states;
+    std::vector<std::pair<uint32_t, uint32_t>> edges;
+    util::readGraphml(mRoadmapName, mDim, states, edges);
+    mRoadmap.swap(states);
+    mRoadmapEdges.swap(edges);
+    mN = (uint32_t)(mRoadmap.size() / mDim);
+  }
+  if (mN == 0) throw Exception("Roadmap " + mRoadmapName + " has no vertices");
+
+  bmNumBatches = 0;
+  bmExhausted = false;
+  bmCurrRadius = 0.0;
+  if (mBatchingType == "vertex") {
+    bmNumVerticesAdded = 0;
+    bmNextVertexTarget = 100u;  // initNumVertices, BP.cpp:692
+    bmVertInfl = 2.0;           // vertInflFactor, BP.cpp:693
+    bmCurrRadius = kInf;        // VertexBatching.hpp:71
+    bmCurrVertex = 0;
+  } else if (mBatchingType == "edge") {
+    bmRadiusInfl = std::pow(2.0, 1 / static_cast<double>(mDim));  // BP.cpp:704
+    bmMaxRadius = mMaxExtent;                                      // BP.cpp:705
+    bmInitRadius = radiusFun(mN);                                  // EdgeBatching.hpp:74
+  } else if (mBatchingType == "hybrid") {
+    bmNumVerticesAdded = 0;
+    bmNextVertexTarget = 100u;
+    bmVertInfl = 2.0;
+    bmRadiusInfl = std::pow(2.0, 1 / static_cast<double>(mDim));
+    bmMaxRadius = mMaxExtent;
+    bmInitRadius = radiusFun(100u);  // HybridBatching.hpp:83
+    bmCurrRadius = bmInitRadius;
+    bmCurrVertex = 0;
+    bmEdgeMode = false;
+  } else if (mBatchingType == "single") {
+    // SingleBatching.hpp:65: g = full_g; then initializeEdgePoints for every edge (BP.cpp:739-743).
+    if (mHaveProblem)
+      throw Exception("single batching requires setup() before setProblemDefinition() (SingleBatching.hpp:65)");
+    for (uint32_t i = 0; i < mN; ++i) addVertex(&mRoadmap[(size_t)i * mDim], false);
+    for (auto& pr : mRoadmapEdges) {
+      if (pr.first >= mN || pr.second >= mN) throw Exception("roadmap edge references an unknown node");
+      Edge e = addEdge(pr.first, pr.second);
+      mEdges[e].distance = rvDistance(vertexState(pr.first), vertexState(pr.second), mDim);  // RoadmapFromFile.hpp:158
+      mEdges[e].nStates = 0;
+    }
+    for (EProps& e : mEdges) {  // initializeEdgePoints, BP.cpp:440-445
+      unsigned int n = static_cast<unsigned int>(std::floor(e.distance / mL));
+      e.nStates = n < 2u ? 2u : n;
+    }
+  } else {
+    throw Exception("Invalid batching type specified - " + mBatchingType + "!");
+  }
+
+  if (mSelectorType == "") {
+    mSelType = "normal";
+  } else {
+    if (mSelectorType != "normal" && mSelectorType != "alternate" && mSelectorType != "failfast" &&
+        mSelectorType != "maxinf")
+      throw std::invalid_argument("Invalid selector type specified - " + mSelectorType + "!");  // Selector.hpp:74
+    mUsingSelector = true;
+    mSelType = mSelectorType;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// setProblemDefinition — BP.cpp:760-816
+// ---------------------------------------------------------------------------
+void BatchingPOMP::setProblemDefinition(const std::vector<double>& start, const std::vector<double>& goal) {
+  if (start.size() != mDim || goal.size() != mDim) throw Exception("start/goal must have `dim` entries");
+  std::vector<double> sg(start);
+  sg.insert(sg.end(), goal.begin(), goal.end());
+  uint8_t ok[2] = {0, 0};
+  check(bpomp_states_valid(mCtx, sg.data(), 2, ok));
+  if (!ok[0]) throw Exception("Start configuration is in collision!");
+  mStartVertex = addVertex(start.data(), true);
+  if (!ok[1]) throw Exception("Goal configuration is in collision!");
+  mGoalVertex = addVertex(goal.data(), true);
+  mHaveProblem = true;
+
+  if (mBatchingType == "single") {
+    for (Vertex vi = 0; vi < mOut.size(); ++vi) {
+      if (vi == mStartVertex || vi == mGoalVertex) continue;
+      double startDist = rvDistance(vertexState(mStartVertex), vertexState(vi), mDim);
+      if (startDist < mStartGoalRadius) {
+        Edge e = addEdge(vi, mStartVertex);
+        mEdges[e].blockedStatus = UNKNOWN;
+        mEdges[e].distance = startDist;
+        unsigned int n = static_cast<unsigned int>(std::floor(startDist / mL));
+        mEdges[e].nStates = n < 2u ? 2u : n;
+      }
+      double goalDist = rvDistance(vertexState(mGoalVertex), vertexState(vi), mDim);
+      if (goalDist < mStartGoalRadius) {
+        Edge e = addEdge(vi, mGoalVertex);
+        mEdges[e].blockedStatus = UNKNOWN;
+        mEdges[e].distance = goalDist;
+        unsigned int n = static_cast<unsigned int>(std::floor(goalDist / mL));
+        mEdges[e].nStates = n < 2u ? 2u : n;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// batching managers — VertexBatching.hpp:94-138, EdgeBatching.hpp:116-159,
+// HybridBatching.hpp:146-202, SingleBatching.hpp:55-91.  Vertex admission
+// (vertexPruneFunction per candidate) is one batched device call per batch.
+// ---------------------------------------------------------------------------
+void BatchingPOMP::nextBatch() {
+  if (bmExhausted) return;
+  ++bmNumBatches;
+  auto admitRange = [&](uint32_t first, uint32_t count) {
+    if (count == 0) return;
+    std::vector<uint8_t> prune(count);
+    check(bpomp_states_prune(mCtx, &mRoadmap[(size_t)first * mDim], count, vertexState(mStartVertex),
+                             vertexState(mGoalVertex), mBestPathCost, 1, prune.data()));
+    for (uint32_t i = 0; i < count; ++i)
+      if (!prune[i]) addVertex(&mRoadmap[(size_t)(first + i) * mDim], true);
+  };
+  if (mBatchingType == "vertex" || (mBatchingType == "hybrid" && !bmEdgeMode)) {
+    // the while loop adds candidates until the target is met or the file ends
+    uint32_t want = bmNextVertexTarget > bmNumVerticesAdded ? bmNextVertexTarget - bmNumVerticesAdded : 0;
+    uint32_t avail = mN - bmCurrVertex;
+    uint32_t take = want < avail ? want : avail;
+    admitRange(bmCurrVertex, take);
+    bmCurrVertex += take;
+    bmNumVerticesAdded += take;
+    if (take > 0 && bmCurrVertex == mN) {
+      if (mBatchingType == "vertex") bmExhausted = true;
+      else bmEdgeMode = true;
+    }
+    if (mBatchingType == "hybrid") bmCurrRadius = radiusFun(std::min(bmNextVertexTarget, mN));  // HybridBatching.hpp:187-189
+    bmNextVertexTarget = static_cast<unsigned int>(bmNextVertexTarget * bmVertInfl);
+  } else if (mBatchingType == "edge") {
+    if (bmNumBatches == 1u) {
+      admitRange(0, mN);
+      bmCurrRadius = bmInitRadius;
+    } else {
+      bmCurrRadius = bmCurrRadius * bmRadiusInfl;
+    }
+    if (bmCurrRadius > bmMaxRadius) {
+      bmCurrRadius = bmMaxRadius;
+      bmExhausted = true;
+    }
+  } else if (mBatchingType == "hybrid") {
+    bmCurrRadius = bmCurrRadius * bmRadiusInfl;
+    if (bmCurrRadius > bmMaxRadius) {
+      bmCurrRadius = bmMaxRadius;
+      bmExhausted = true;
+    }
+  } else if (mBatchingType == "single") {
+    pruneVertices(true);
+    bmExhausted = true;
+  }
+  mCsrValid = false;
+}
+
+void BatchingPOMP::updateWithNewSolutionCost(double c) {
+  if (mBatchingType == "edge" || mBatchingType == "hybrid") bmMaxRadius = std::min(bmMaxRadius, c);
+}
+
+// BatchingManager::pruneVertices — BatchingManager.hpp:144-165 — over every vertex of g.
+void BatchingPOMP::pruneVertices(bool withValidity) {
+  flushVertices();
+  uint32_t nv = (uint32_t)mOut.size();
+  if (nv == 0) return;
+  std::vector<uint8_t> prune(nv);
+  check(bpomp_vertices_prune(mCtx, mStartVertex, mGoalVertex, mBestPathCost, withValidity ? 1 : 0, prune.data()));
+  for (Vertex v = 0; v < nv; ++v) {
+    if (!prune[v]) continue;
+    if (mNNActive[v]) {
+      mNNActive[v] = 0;
+      mPendingDeactivate.push_back(v);
+    }
+    clearVertex(v);
+  }
+  flushVertices();
+}
+
+// ---------------------------------------------------------------------------
+// neighbour rows
+// ---------------------------------------------------------------------------
+void BatchingPOMP::prepareNeighbourCache(double radius) {
+  flushVertices();
+  mCsrValid = false;
+  uint32_t nv = (uint32_t)mOut.size();
+  uint32_t nactive = 0;
+  for (uint32_t v = 0; v < nv; ++v) nactive += mNNActive[v];
+  // estimate the CSR size: complete graph for an unbounded radius, else from a sample of rows
+  double est;
+  if (radius >= kInf || nactive <= 64) {
+    est = (double)nactive * (double)nactive;
+  } else {
+    std::vector<uint32_t> q;
+    uint32_t stride = nv / 64 ? nv / 64 : 1;
+    for (uint32_t v = 0; v < nv && q.size() < 64; v += stride) q.push_back(v);
+    uint64_t nnz = 0;
+    check(bpomp_neighbors_radius(mCtx, q.data(), (uint32_t)q.size(), radius, &nnz));
+    est = (double)nnz / (double)q.size() * (double)nactive;
+  }
+  if (est > (double)mCsrBudget) return;  // rows are fetched on demand instead
+  uint64_t nnz = 0;
+  check(bpomp_neighbors_all(mCtx, radius, &nnz));
+  mCsrRowPtr.resize((size_t)nv + 1);
+  mCsrCol.resize(nnz ? nnz : 1);
+  mCsrDist.resize(nnz ? nnz : 1);
+  check(bpomp_neighbors_fetch(mCtx, mCsrRowPtr.data(), mCsrCol.data(), mCsrDist.data()));
+  mCsrValid = true;
+  mCsrRadius = radius;
+}
+
+const std::vector<std::pair<double, BatchingPOMP::Vertex>>& BatchingPOMP::neighbourRow(Vertex u, double radius) {
+  mRowScratch.clear();
+  // the cached CSR has rows for the vertices that were ACTIVE when it was built; rows of vertices
+  // that have since been deactivated, or were never in the NN structure, are fetched on demand
+  if (mCsrValid && radius == mCsrRadius && u + 1 < mCsrRowPtr.size() && mNNActive[u]) {
+    for (uint64_t k = mCsrRowPtr[u]; k < mCsrRowPtr[u + 1]; ++k) {
+      Vertex v = mCsrCol[k];
+      if (mNNActive[v]) mRowScratch.emplace_back(mCsrDist[k], v);  // pruned since the CSR was built
+    }
+    return mRowScratch;
+  }
+  flushVertices();
+  uint64_t nnz = 0;
+  check(bpomp_neighbors_radius(mCtx, &u, 1, radius, &nnz));
+  std::vector<uint64_t> rp(2);
+  std::vector<uint32_t> col(nnz ? nnz : 1);
+  std::vector<double> dist(nnz ? nnz : 1);
+  check(bpomp_neighbors_fetch(mCtx, rp.data(), col.data(), dist.data()));
+  for (uint64_t k = 0; k < nnz; ++k) mRowScratch.emplace_back(dist[k], col[k]);
+  return mRowScratch;
+}
+
+// neighbours_visitor::examine_vertex after the goal test — BP.cpp:149-168
+void BatchingPOMP::expandVertex(Vertex u, double radius) {
+  const auto& row = neighbourRow(u, radius);
+  std::vector<Edge> created;
+  for (const auto& pr : row) {
+    Vertex nbr = pr.second;
+    if (nbr == u) continue;
+    if (!hasEdge(u, nbr)) {
+      Edge e = addEdge(u, nbr);
+      mEdges[e].distance = pr.first;  // bit-equal to vertexDistFun(source, target)
+      mEdges[e].blockedStatus = UNKNOWN;
+      unsigned int n = static_cast<unsigned int>(std::floor(pr.first / mL));  // BP.cpp:440-445
+      mEdges[e].nStates = n < 2u ? 2u : n;
+      created.push_back(e);
+    }
+  }
+  computeFreeProbabilities(created);  // BP.cpp:166, batched: the belief model is read-only during a search
+}
+
+// throw_visitor::examine_edge (single batching) recomputes probFree of every examined edge, BP.cpp:108-111
+void BatchingPOMP::refreshOutEdgeProbabilities(Vertex u) {
+  std::vector<Edge> es;
+  es.reserve(mOut[u].size());
+  for (const OutEdge& oe : mOut[u]) es.push_back(oe.eid);
+  computeFreeProbabilities(es);
+}
+
+// computeAndSetEdgeFreeProbability for a set of edges — BP.cpp:464-493
+void BatchingPOMP::computeFreeProbabilities(const std::vector<Edge>& edges) {
+  if (edges.empty()) return;
+  double t0 = now();
+  if (mBeliefEmpty) {
+    // KNNModel::estimate returns the prior while the model has no points (KNNModel.hpp:104-106)
+    const double prior = 0.5;
+    for (Edge e : edges) {
+      size_t nStates = mEdges[e].nStates;
+      unsigned int stepSize = static_cast<unsigned int>(nStates / std::log(nStates));
+      double result = 1.0;
+      for (unsigned int i = 1; i < nStates - 1; i += stepSize) {
+        mNumLookups++;
+        result *= (1.0 - prior);
+      }
+      mEdges[e].probFree = result;
+    }
+  } else {
+    std::vector<uint32_t> from(edges.size()), to(edges.size()), nl(edges.size());
+    std::vector<double> pf(edges.size());
+    for (size_t i = 0; i < edges.size(); ++i) {
+      from[i] = mEdges[edges[i]].source;
+      to[i] = mEdges[edges[i]].target;
+    }
+    flushVertices();
+    check(bpomp_belief_edge_pfree_indexed(mCtx, from.data(), to.data(), (int64_t)edges.size(), pf.data(), nl.data()));
+    for (size_t i = 0; i < edges.size(); ++i) {
+      mEdges[edges[i]].probFree = pf[i];
+      mNumLookups += nl[i];
+    }
+  }
+  mLookupTime += now() - t0;
+}
+
+// Selector — util/Selector.hpp:95-146
+std::vector<BatchingPOMP::Edge> BatchingPOMP::selectEdges(const std::vector<Edge>& ePath) const {
+  if (mSelType == "normal") return ePath;
+  std::vector<Edge> r(ePath);
+  if (mSelType == "alternate") {
+    std::reverse(r.begin(), r.end());
+    return r;
+  }
+  // failfast: ascending probFree; maxinf: ascending |probFree-0.5|.  Exact ties: path position
+  // (std::sort over pair<double,Edge> orders them by edge descriptor in the reference — unpinned).
+  std::vector<std::pair<std::pair<double, size_t>, Edge>> lst;
+  for (size_t i = 0; i < ePath.size(); ++i) {
+    double p = mEdges[ePath[i]].probFree;
+    lst.push_back({{mSelType == "failfast" ? p : std::fabs(p - 0.5), i}, ePath[i]});
+  }
+  std::sort(lst.begin(), lst.end());
+  for (size_t i = 0; i < lst.size(); ++i) r[i] = lst[i].second;
+  return r;
+}
+
+// checkAndUpdatePathBlocked + checkAndSetEdgeBlocked — BP.cpp:577-598, 496-544.
+// All UNKNOWN edges of the (re-ordered) path are evaluated in ONE device call; the results are then
+// committed in order exactly as the reference's sequential loop would (stop at the first blocked
+// edge when a selector type was set), so counters, statuses and belief inserts are identical.
+bool BatchingPOMP::checkAndUpdatePathBlocked(const std::vector<Edge>& ePath) {
+  std::vector<Edge> sel = selectEdges(ePath);
+  std::vector<Edge> unknown;
+  for (Edge e : sel)
+    if (mEdges[e].blockedStatus == UNKNOWN) unknown.push_back(e);
+  if (unknown.empty()) return false;
+  double t0 = now();
+  size_t m = unknown.size();
+  std::vector<uint32_t> from(m), to(m), ns(m);
+  std::vector<uint8_t> valid(m);
+  std::vector<int32_t> first(m);
+  for (size_t i = 0; i < m; ++i) {
+    from[i] = mEdges[unknown[i]].source;
+    to[i] = mEdges[unknown[i]].target;
+  }
+  flushVertices();
+  check(bpomp_edges_check_indexed(mCtx, from.data(), to.data(), (int64_t)m, valid.data(), first.data(), ns.data()));
+  bool pathBlocked = false;
+  size_t committed = 0;
+  for (size_t i = 0; i < m; ++i) {
+    Edge e = unknown[i];
+    EProps& ep = mEdges[e];
+    mNumEdgeChecks++;  // BP.cpp:499
+    // addAffectedEdges, BP.cpp:600-620
+    for (Vertex x : {ep.source, ep.target})
+      for (const OutEdge& oe : mOut[x])
+        if (!mEdgeMarked[oe.eid]) {
+          mEdgeMarked[oe.eid] = 1;
+          mEdgesToUpdate.push_back(oe.eid);
+        }
+    if (ns[i] != ep.nStates) throw Exception("internal: device and host disagree on nStates");
+    committed = i + 1;
+    if (!valid[i]) {
+      mNumCollChecks += (unsigned int)first[i];  // one isValid per slot up to the invalid one, BP.cpp:516
+      ep.blockedStatus = BLOCKED;                 // BP.cpp:529-531
+      ep.distance = kInf;
+      ep.probFree = 0.0;
+      pathBlocked = true;
+      if (mUsingSelector) break;  // BP.cpp:591-593
+    } else {
+      mNumCollChecks += ep.nStates - 2u;
+      ep.blockedStatus = FREE;  // BP.cpp:541-542
+      ep.probFree = 1.0;
+    }
+  }
+  // belief inserts of the committed edges, in check order (BP.cpp:523-537), replayed on the device
+  std::vector<double> fs(committed * mDim), ts(committed * mDim);
+  uint64_t added = 0;
+  for (size_t i = 0; i < committed; ++i) {
+    std::memcpy(&fs[i * mDim], vertexState(from[i]), sizeof(double) * mDim);
+    std::memcpy(&ts[i * mDim], vertexState(to[i]), sizeof(double) * mDim);
+    added += valid[i] ? ns[i] - 2u : (uint32_t)first[i];
+  }
+  if (added > 0) {
+    check(bpomp_belief_append_checked(mCtx, fs.data(), ts.data(), first.data(), (int64_t)committed));
+    mBeliefEmpty = false;
+  }
+  mCollCheckTime += now() - t0;
+  return pathBlocked;
+}
+
+// updateAffectedEdgeWeights — BP.cpp:623-633
+void BatchingPOMP::updateAffectedEdgeWeights() {
+  std::vector<Edge> todo;
+  for (Edge e : mEdgesToUpdate) {
+    mEdgeMarked[e] = 0;
+    if (!mEdges[e].removed && mEdges[e].blockedStatus == UNKNOWN) todo.push_back(e);
+  }
+  mEdgesToUpdate.clear();
+  computeFreeProbabilities(todo);
+}
+
+// EdgeWeightMap get — BP.cpp:66-83
+double BatchingPOMP::edgeWeight(Edge e) const {
+  const EProps& ep = mEdges[e];
+  if (ep.blockedStatus == BLOCKED) return kInf;
+  double alpha = mCurrentAlpha;
+  if (ep.blockedStatus == FREE) return alpha * ep.distance;
+  double w_m = -std::log(ep.probFree);
+  double w_l = ep.distance;
+  double exp_cost = alpha * w_l + (1 - alpha) * w_m;
+  return exp_cost;
+}
+
+// ---------------------------------------------------------------------------
+// 4-ary indirect heap keyed on f (boost::d_ary_heap_indirect<Vertex,4,...>):
+// sift-up while strictly smaller than the parent; pop moves the last element to the root and
+// sifts down choosing the first strictly-smallest child.
+// ---------------------------------------------------------------------------
+void BatchingPOMP::touch(Vertex v) {
+  if (mStamp[v] != mEpoch) {  // lazily applies astar_search's initialisation loop to v
+    mStamp[v] = mEpoch;
+    mDist[v] = kInf;
+    mCost[v] = kInf;
+    mPred[v] = v;
+    mColor[v] = 0;
+    mHeapIndex[v] = -1;
+  }
+}
+
+void BatchingPOMP::heapUp(size_t index) {
+  if (index == 0) return;
+  size_t orig = index, moved = 0;
+  Vertex moving = mHeap[index];
+  double key = mCost[moving];
+  for (;;) {
+    if (index == 0) break;
+    size_t parent = (index - 1) / 4;
+    if (key < mCost[mHeap[parent]]) {
+      ++moved;
+      index = parent;
+      continue;
+    }
+    break;
+  }
+  index = orig;
+  for (size_t i = 0; i < moved; ++i) {
+    size_t parent = (index - 1) / 4;
+    Vertex pv = mHeap[parent];
+    mHeapIndex[pv] = (int64_t)index;
+    mHeap[index] = pv;
+    index = parent;
+  }
+  mHeap[index] = moving;
+  mHeapIndex[moving] = (int64_t)index;
+}
+
+void BatchingPOMP::heapPush(Vertex v) {
+  mHeap.push_back(v);
+  mHeapIndex[v] = (int64_t)mHeap.size() - 1;
+  heapUp(mHeap.size() - 1);
+}
+
+void BatchingPOMP::heapDown() {
+  if (mHeap.empty()) return;
+  size_t index = 0, size = mHeap.size();
+  double key = mCost[mHeap[0]];
+  for (;;) {
+    size_t firstChild = 4 * index + 1;
+    if (firstChild >= size) break;
+    size_t nchild = std::min<size_t>(4, size - firstChild);
+    size_t best = 0;
+    double bestKey = mCost[mHeap[firstChild]];
+    for (size_t i = 1; i < nchild; ++i) {
+      double k = mCost[mHeap[firstChild + i]];
+      if (k < bestKey) {
+        best = i;
+        bestKey = k;
+      }
+    }
+    if (bestKey < key) {
+      size_t c = firstChild + best;
+      std::swap(mHeap[c], mHeap[index]);
+      mHeapIndex[mHeap[c]] = (int64_t)c;
+      mHeapIndex[mHeap[index]] = (int64_t)index;
+      index = c;
+      continue;
+    }
+    break;
+  }
+}
+
+void BatchingPOMP::heapPop() {
+  mHeapIndex[mHeap[0]] = -1;
+  if (mHeap.size() != 1) {
+    mHeap[0] = mHeap.back();
+    mHeapIndex[mHeap[0]] = 0;
+    mHeap.pop_back();
+    heapDown();
+  } else {
+    mHeap.pop_back();
+  }
+}
+
+// boost::astar_search (initialising overload) with neighbours_visitor / throw_visitor —
+// BP.cpp:860-924, 88-175; semantics in SURVEY.md A.4.  Returns true when the goal is popped.
+bool BatchingPOMP::astar(bool zeroHeuristic, bool single) {
+  size_t nv = mOut.size();
+  if (mStamp.size() < nv) {
+    mStamp.resize(nv, 0);
+    mDist.resize(nv);
+    mCost.resize(nv);
+    mPred.resize(nv);
+    mColor.resize(nv);
+    mHeapIndex.resize(nv);
+  }
+  if (++mEpoch == 0) {  // stamp wrap-around
+    std::fill(mStamp.begin(), mStamp.end(), 0);
+    mEpoch = 1;
+  }
+  mHeap.clear();
+  const double alpha = mCurrentAlpha;
+  const double* goalState = vertexState(mGoalVertex);
+  auto h = [&](Vertex u) -> double {
+    if (zeroHeuristic) return 0.0;                                 // zero_heuristic, BP.cpp:203-206
+    return alpha * rvDistance(vertexState(u), goalState, mDim);     // exp_distance_heuristic, BP.cpp:187-190
+  };
+  const double radius = bmCurrRadius;  // captured when the visitor is built, BP.cpp:904
+  Vertex s = mStartVertex;
+  touch(s);
+  mDist[s] = 0.0;
+  mCost[s] = h(s);
+  mColor[s] = 1;
+  heapPush(s);
+  while (!mHeap.empty()) {
+    Vertex u = mHeap[0];
+    heapPop();
+    if (u == mGoalVertex) return true;  // examine_vertex throws, BP.cpp:104-106 / 145-147
+    if (single) refreshOutEdgeProbabilities(u);
+    else expandVertex(u, radius);
+    const std::vector<OutEdge>& out = mOut[u];
+    for (size_t k = 0; k < out.size(); ++k) {
+      Edge eid = out[k].eid;
+      Vertex v = out[k].target;
+      double w_e = edgeWeight(eid);
+      if (w_e < 0.0) throw Exception("negative edge weight");  // boost::negative_edge
+      touch(v);
+      double d_u = mDist[u], d_v = mDist[v];
+      bool decreased = false;
+      double cand = closedPlus(d_u, w_e);
+      if (cand < d_v) {  // relax_target
+        mDist[v] = cand;
+        mPred[v] = u;
+        decreased = true;
+      }
+      if (mColor[v] == 0) {  // tree_edge: pushed even if the relaxation failed
+        if (decreased) mCost[v] = closedPlus(mDist[v], h(v));
+        mColor[v] = 1;
+        heapPush(v);
+      } else if (mColor[v] == 1) {  // gray_target
+        if (decreased) {
+          mCost[v] = closedPlus(mDist[v], h(v));
+          heapUp((size_t)mHeapIndex[v]);
+        }
+      } else {  // black_target: re-open
+        if (decreased) {
+          mCost[v] = closedPlus(mDist[v], h(v));
+          heapPush(v);
+          mColor[v] = 1;
+        }
+      }
+    }
+    mColor[u] = 2;
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------------------
+// solve — BP.cpp:819-1017
+// ---------------------------------------------------------------------------
+PlannerStatus BatchingPOMP::solve(const PlannerTerminationCondition& ptc) {
+  if (!mHaveProblem) throw Exception("setProblemDefinition() has not been called");
+  double currSolnCost = kInf;
+  mIsPathFound = false;
+  std::vector<Edge> ePath;
+  std::vector<Vertex> vPath;
+
+  while (currSolnCost >= mBestPathCost) {
+    if (bmExhausted && mIsInitSearchBatch) {
+      if (mBestPathCost < kInf) return PlannerStatus::EXACT_SOLUTION;
+      return PlannerStatus::TIMEOUT;
+    }
+    if (ptc && ptc()) return PlannerStatus::TIMEOUT;
+
+    if (mIsInitSearchBatch) {
+      mCurrentAlpha = 0.0;
+      nextBatch();
+      if (mBatchingType != "single") prepareNeighbourCache(bmCurrRadius);
+    }
+    flushVertices();
+
+    mNumSearches++;
+    bool zeroH = mIsInitSearchBatch;
+    mIsInitSearchBatch = false;
+    double t0 = now();
+    astar(zeroH, mBatchingType == "single");
+    if (mBatchingType != "single") mSearchTime += now() - t0;
+
+    touch(mGoalVertex);
+    if (mDist[mGoalVertex] == kInf) {
+      if (bmExhausted) {
+        if (mBestPathCost < kInf) return PlannerStatus::EXACT_SOLUTION;
+        return PlannerStatus::TIMEOUT;
+      }
+      mIsInitSearchBatch = true;
+      if (mBestPathCost < kInf) return PlannerStatus::APPROXIMATE_SOLUTION;
+      return PlannerStatus::ABORT;
+    }
+
+    Vertex vWalk = mGoalVertex;
+    ePath.clear();
+    vPath.clear();
+    while (vWalk != mStartVertex) {
+      Vertex vPred = mPred[vWalk];
+      Edge e = findEdge(vPred, vWalk);
+      if (e == (Edge)-1) throw Exception("Error! Edge present during search no longer exists in graph!");
+      ePath.push_back(e);
+      vPath.push_back(vWalk);
+      vWalk = vPred;
+    }
+    std::reverse(ePath.begin(), ePath.end());
+    std::reverse(vPath.begin(), vPath.end());
+
+    bool pathBlocked = checkAndUpdatePathBlocked(ePath);
+    updateAffectedEdgeWeights();
+
+    if (!pathBlocked) {
+      mIsPathFound = true;
+      currSolnCost = 0.0;
+      for (Edge e : ePath) currSolnCost += mEdges[e].distance;  // getPathDistance, BP.cpp:658-666
+      if (mCurrentAlpha >= 1.0) mIsInitSearchBatch = true;
+      else mCurrentAlpha = std::min(mCurrentAlpha + mIncrement, 1.0);
+    }
+  }
+
+  double improvementFactor = mBestPathCost / currSolnCost;
+  mBestPathCost = currSolnCost;
+  mCurrBestPath = ePath;
+  updateWithNewSolutionCost(mBestPathCost);
+
+  mSolutionVertices.clear();
+  mSolutionVertices.push_back(mStartVertex);
+  for (Vertex v : vPath) mSolutionVertices.push_back(v);  // target(e) for e on the path, BP.cpp:1001-1004
+  ++mNumSolutions;
+
+  if (improvementFactor > mPruneThreshold) pruneVertices(false);  // BP.cpp:1009-1013
+  return PlannerStatus::APPROXIMATE_SOLUTION;
+}
+
+}  // namespace batching_pomp

@@ -106,6 +106,12 @@ BPOMP_API int bpomp_states_valid_dev(bpomp_ctx* ctx, const double* d_states, int
 BPOMP_API int bpomp_states_prune(bpomp_ctx* ctx, const double* states, int64_t count, const double* start,
                                  const double* goal, double best_cost, int check_validity, uint8_t* out);
 
+/* The same predicate over the resident vertex table (BatchingManager::pruneVertices,
+ * BatchingManager.hpp:144-165, walks every vertex of the current roadmap): out[v] for v in
+ * 0..count-1, start/goal given as vertex ids. */
+BPOMP_API int bpomp_vertices_prune(bpomp_ctx* ctx, uint32_t start_id, uint32_t goal_id, double best_cost,
+                                   int check_validity, uint8_t* out);
+
 /* ---- vertex table = the elements of mVertexNN ------------------------------------------- */
 
 /* mVertexNN->add — src/BatchingPOMP.cpp:782,789; VertexBatching.hpp:133; EdgeBatching.hpp:146;

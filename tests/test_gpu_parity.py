@@ -195,6 +195,21 @@ def test_neighbors_parity(capi, orc, wl, d, N, nq, rfun):
     ctx.close()
 
 
+def test_neighbors_huge_rows_global_sort(capi, orc, wl):
+    """Rows longer than the shared-memory sort handles (vertex batching's r = DBL_MAX on many vertices)."""
+    d, N = 2, 9000
+    verts = wl.halton(N, d)
+    ctx = capi.Context(d, wl.segment_length(d))
+    ctx.vertices_append(verts)
+    q = np.array([0, 4321, 8999], dtype=np.uint32)
+    rp, col, dist = ctx.neighbors_radius(q, np.finfo(np.float64).max)
+    orp, ocol, odist = orc.neighbors_radius(verts, q, np.finfo(np.float64).max, nthreads=orc.max_threads())
+    np.testing.assert_array_equal(rp, orp)
+    np.testing.assert_array_equal(col, ocol)
+    np.testing.assert_array_equal(dist, odist)
+    ctx.close()
+
+
 def test_neighbors_all_matches_per_query(capi, orc, wl):
     d, N = 2, 30000
     verts = wl.halton(N, d)
