@@ -165,7 +165,7 @@ class ClockSampler(threading.Thread):
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from batching_pomp_b200 import capi
+    from batching_pomp_b200 import capi, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -200,7 +200,7 @@ def run_gpu(args):
     torch.cuda.synchronize()
 
     nchunk = 4 if world > 1 else 1
-    bounds = [(E * c) // nchunk for c in range(nchunk + 1)]
+    bounds = sharding.chunk_bounds(E, nchunk)
     gathered = [torch.empty(world * (bounds[c + 1] - bounds[c]), dtype=torch.int32, device=dev)
                 for c in range(nchunk)] if world > 1 else None
     comm_stream = torch.cuda.Stream() if world > 1 else None
@@ -224,7 +224,7 @@ def run_gpu(args):
                 ev.record(stream)
                 with torch.cuda.stream(comm_stream):
                     comm_stream.wait_event(ev)
-                    works.append(dist.all_gather_into_tensor(gathered[c], d_first[a:b], async_op=True))
+                    works.append(sharding.allgather_equal(d_first[a:b], gathered[c], async_op=True)[1])
         for w in works:
             w.wait()
         if world > 1:

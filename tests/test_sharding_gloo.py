@@ -1,0 +1,74 @@
+"""world_size-2 gloo test (CPU) of the N>1 host logic: shard the edge batch, evaluate each shard
+independently (the CPU oracle stands in for the device here), merge with the all-gather helpers and
+compare with the unsharded evaluation."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, count, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from batching_pomp_b200 import sharding, workloads
+    from oracle import oracle
+    d = 7
+    L = workloads.segment_length(d)
+    lo, hi = workloads.box_world(d, 500, seed=3)
+    frm, to = workloads.random_edges(count, d, seed=4, max_len=0.35)
+    b = sharding.shard_bounds(count, world)
+    v, f, n = oracle.edges_check_boxes(frm[b[rank]:b[rank + 1]], to[b[rank]:b[rank + 1]], L, lo, hi)
+    merged = sharding.allgather_ragged(torch.from_numpy(f.copy()))
+    if count % world == 0:
+        eq, _ = sharding.allgather_equal(torch.from_numpy(f.copy()))
+        assert torch.equal(eq, merged)
+    if rank == 0:
+        q.put(merged.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("count", [4000, 4001])
+def test_sharded_edge_check_merges_to_unsharded(orc, count):
+    from batching_pomp_b200 import workloads
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, count, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    merged = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    d = 7
+    lo, hi = workloads.box_world(d, 500, seed=3)
+    frm, to = workloads.random_edges(count, d, seed=4, max_len=0.35)
+    v, f, n = orc.edges_check_boxes(frm, to, workloads.segment_length(d), lo, hi)
+    np.testing.assert_array_equal(merged, f)
+
+
+def test_shard_bounds_cover_everything():
+    from batching_pomp_b200 import sharding
+    for count in (0, 1, 7, 10 ** 7, 10 ** 7 + 3):
+        for world in (1, 2, 4, 8):
+            b = sharding.shard_bounds(count, world)
+            assert b[0] == 0 and b[-1] == count and all(b[i] <= b[i + 1] for i in range(world))
+            assert max(b[i + 1] - b[i] for i in range(world)) - min(b[i + 1] - b[i] for i in range(world)) <= 1
