@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Secondary benchmarks: the BASELINE.json configs other than the headline (bench.py = config 4).
 
-  python benchmarks/run_configs.py [--quick] [--out FILE] [--only NAME[,NAME]]
+  python benchmarks/run_configs.py [--quick] [--out FILE(jsonl, appended)] [--only NAME[,NAME]]
 
 Sections (each prints one JSON line and is also collected into --out):
   config2_neighbors      whole-roadmap densification, 2-D Halton N=10^6, r = haltonRadius(N) -> device CSR
@@ -33,10 +33,17 @@ except Exception:
 RESULTS = {}
 
 
+OUT = [None]
+
+
 def emit(name, d):
     d = dict(section=name, **d)
     RESULTS[name] = d
-    print(json.dumps(d), flush=True)
+    line = json.dumps(d)
+    print(line, flush=True)
+    if OUT[0]:
+        with open(OUT[0], "a") as f:
+            f.write(line + "\n")
 
 
 def timed(fn, reps=3, warm=1):
@@ -200,7 +207,7 @@ def belief(quick):
     ctx.close()
 
 
-def _plan(make, label, max_calls, oracle_too=True):
+def _plan(make, label, max_calls, max_solutions=3, time_cap=60.0):
     from batching_pomp_b200.planner import Planner  # noqa: F401
     gp, op, start, goal, single = make()
     res = {}
@@ -214,21 +221,27 @@ def _plan(make, label, max_calls, oracle_too=True):
             p.set_problem(start, goal); p.setup()
         first = None
         costs = []
+        st = "UNKNOWN"
         for _ in range(max_calls):
-            st = p.solve()
+            left = time_cap - (time.perf_counter() - t0)
+            if left <= 0:
+                st = "BENCH_TIME_CAP"
+                break
+            st = p.solve(max_seconds=left)
             if len(p.path()) and (not costs or p.best_cost < costs[-1][1]):
                 costs.append((time.perf_counter() - t0, p.best_cost))
                 if first is None:
                     first = time.perf_counter() - t0
-            if st in ("EXACT_SOLUTION", "TIMEOUT"):
+            if st in ("EXACT_SOLUTION", "TIMEOUT") or len(costs) >= max_solutions:
                 break
         res[name] = {"time_to_first_path_s": first, "time_to_best_path_s": costs[-1][0] if costs else None,
                      "best_cost": costs[-1][1] if costs else None, "solutions": len(costs), "final_status": st,
                      "total_s": time.perf_counter() - t0, "counters": p.counters(),
                      "path": [int(v) for v in p.path()]}
     if "cpu_oracle" in res:
-        res["paths_identical"] = res["gpu"]["path"] == res["cpu_oracle"]["path"] and \
-            res["gpu"]["best_cost"] == res["cpu_oracle"]["best_cost"]
+        same_work = res["gpu"]["solutions"] == res["cpu_oracle"]["solutions"]
+        res["paths_identical"] = (res["gpu"]["path"] == res["cpu_oracle"]["path"] and
+                                  res["gpu"]["best_cost"] == res["cpu_oracle"]["best_cost"]) if same_work else None
     for k in ("gpu", "cpu_oracle"):
         if k in res:
             res[k].pop("path")
@@ -252,7 +265,7 @@ def planner_config1(quick):
             for k, v in params.items():
                 p.set_param(k, v)
         return gp, op, [0.1, 0.1], [0.9, 0.9], False
-    _plan(make, "planner_config1", 200)
+    _plan(make, "planner_config1", 60)
 
 
 def planner_config3(quick):
@@ -283,7 +296,6 @@ if __name__ == "__main__":
     ap.add_argument("--only", default=None)
     a = ap.parse_args()
     names = a.only.split(",") if a.only else list(SECTIONS)
+    OUT[0] = a.out
     for n in names:
         SECTIONS[n](a.quick)
-    if a.out:
-        json.dump(RESULTS, open(a.out, "w"), indent=1)

@@ -296,7 +296,12 @@ class OraclePlanner:
     def set_ptc_budget(self, n):
         self._l.orcp_set_ptc_budget(self._h, C.c_long(n))
 
-    def solve(self):
+    def set_time_limit(self, seconds):
+        self._l.orcp_set_time_limit(self._h, C.c_double(seconds))
+
+    def solve(self, max_seconds=0.0):
+        if max_seconds:
+            self.set_time_limit(max_seconds)
         return STATUS[int(self._l.orcp_solve(self._h))]
 
     @property

@@ -11,6 +11,7 @@
 // File:line citations are relative to /root/reference/ (BP.cpp = src/BatchingPOMP.cpp).
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -580,6 +581,10 @@ struct Planner {
 
   // BP.cpp:819-1017.  ptcBudget: number of loop iterations allowed before ptc becomes true (<0 = never).
   long ptcBudget = -1;
+  double ptcDeadline = 0.0;  // steady_clock seconds; 0 = none
+  static double nowSeconds() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  }
   int solve() {
     double currSolnCost = kInf;
     mIsPathFound = false;
@@ -589,6 +594,7 @@ struct Planner {
         if (mBestPathCost < kInf) return ST_EXACT;
         return ST_TIMEOUT;
       }
+      if (ptcDeadline > 0.0 && nowSeconds() >= ptcDeadline) return ST_TIMEOUT;
       if (ptcBudget == 0) return ST_TIMEOUT;
       if (ptcBudget > 0) --ptcBudget;
       if (mIsInitSearchBatch) {
@@ -692,6 +698,10 @@ ORC_API int orcp_set_problem(void* h, const double* start, const double* goal) {
   return ((Planner*)h)->setProblemDefinition(start, goal);
 }
 ORC_API void orcp_set_ptc_budget(void* h, long n) { ((Planner*)h)->ptcBudget = n; }
+ORC_API void orcp_set_time_limit(void* h, double seconds) {
+  Planner* p = (Planner*)h;
+  p->ptcDeadline = seconds > 0.0 ? Planner::nowSeconds() + seconds : 0.0;
+}
 ORC_API int orcp_solve(void* h) { return ((Planner*)h)->solve(); }
 ORC_API const char* orcp_error(void* h) { return ((Planner*)h)->error.c_str(); }
 ORC_API double orcp_best_cost(void* h) { return ((Planner*)h)->mBestPathCost; }
