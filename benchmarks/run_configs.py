@@ -235,6 +235,7 @@ def _plan(make, label, max_calls, max_solutions=3, time_cap=60.0):
             if st in ("EXACT_SOLUTION", "TIMEOUT") or len(costs) >= max_solutions:
                 break
         res[name] = {"time_to_first_path_s": first, "time_to_best_path_s": costs[-1][0] if costs else None,
+                     "anytime_curve": [[round(t, 4), c] for t, c in costs],
                      "best_cost": costs[-1][1] if costs else None, "solutions": len(costs), "final_status": st,
                      "total_s": time.perf_counter() - t0, "counters": p.counters(),
                      "path": [int(v) for v in p.path()]}
@@ -265,7 +266,7 @@ def planner_config1(quick):
             for k, v in params.items():
                 p.set_param(k, v)
         return gp, op, [0.1, 0.1], [0.9, 0.9], False
-    _plan(make, "planner_config1", 60)
+    _plan(make, "planner_config1", 400, max_solutions=(6 if quick else 12), time_cap=(30.0 if quick else 100.0))
 
 
 def planner_config3(quick):
@@ -283,7 +284,7 @@ def planner_config3(quick):
             p.set_roadmap(roadmap)
             p.set_param("batching_type", "vertex")
         return gp, op, np.full(d, 0.1), np.full(d, 0.9), False
-    _plan(make, "planner_config3", 12 if quick else 16)
+    _plan(make, "planner_config3", 400, max_solutions=(5 if quick else 9), time_cap=(30.0 if quick else 100.0))
 
 
 SECTIONS = {"config2": config2, "config3": config3, "belief": belief, "planner_config1": planner_config1,
