@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbpomp_cuda.so")
+LIB_PATH = os.environ.get("BPOMP_CUDA_LIB") or os.path.join(_HERE, "libbpomp_cuda.so")  # env: tuning builds only
 
 c_dp = C.POINTER(C.c_double)
 c_u8p = C.POINTER(C.c_uint8)

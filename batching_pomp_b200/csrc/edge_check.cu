@@ -10,7 +10,9 @@
 
 #include "world.cuh"
 
-#define EC_THREADS 512
+#ifndef EC_THREADS
+#define EC_THREADS 768
+#endif
 #define EC_MAXCAND 16
 
 struct EdgeArgs {
@@ -124,8 +126,10 @@ __device__ __forceinline__ bool edge_prologue(const EdgeArgs& a, const PermView&
 // A warp owns 32 consecutive edges at a time and runs three phases with uniform control flow:
 //   A/B (lane = edge)   endpoints, distance, nStates; broad phase = AND over the dimensions of the
 //                       prefix masks of the edge's cell range (shared memory) -> candidate boxes;
-//                       edges without candidates are FREE at once.  Endpoint data of the remaining
-//                       edges is parked in a per-warp shared-memory scratch.
+//                       edges without candidates are FREE at once.  Endpoint data stays in the
+//                       owner lane's registers (phase C fetches it with warp shuffles), which keeps
+//                       the per-warp shared-memory scratch at 1.1 KB and lets 24 warps share an SM
+//                       with the 113 KB of staged tables.
 //   C   (lane = sample) the (edge, slot) pairs of the 32 edges are flattened by a warp prefix sum
 //                       and dealt to the lanes 32 at a time, whatever the mix of nStates — a long
 //                       edge simply spreads over many lanes.  Each lane interpolates its state with
@@ -134,15 +138,9 @@ __device__ __forceinline__ bool edge_prologue(const EdgeArgs& a, const PermView&
 // ---------------------------------------------------------------------------
 #define EC_WARPS (EC_THREADS / 32)
 
-template <int D>
 struct WarpScratch {
-  static constexpr int kStride = 2 * D + 1;  // doubles per edge (from, to-from), odd -> conflict-free rows
-  double ef[32 * kStride];
-  uint32_t start[33];                        // exclusive prefix of the slots to test per edge
-  uint32_t off[32];                          // offset of the edge's sample-order row
-  int32_t nc[32];                            // candidates (-1: list overflow -> test every box)
-  int32_t first[32];                         // first invalid slot found so far
-  unsigned short list[EC_MAXCAND * 32];      // [c][lane]
+  int32_t first[32];                         // first invalid slot found so far, per edge of the tile
+  unsigned short list[EC_MAXCAND * 32];      // candidate boxes [c][lane]
 };
 
 template <int D, bool INDEXED, bool STAGE>
@@ -150,8 +148,8 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
     edge_check_boxes_kernel(EdgeArgs a, BoxWorldView w, PermView pv) {
   extern __shared__ __align__(16) unsigned char smem[];
   // layout: [WarpScratch x EC_WARPS][mbarrier 16 B][prefix masks][lohi]
-  WarpScratch<D>* ws = reinterpret_cast<WarpScratch<D>*>(smem) + (threadIdx.x >> 5);
-  constexpr size_t kScratch = (sizeof(WarpScratch<D>) * EC_WARPS + 15) / 16 * 16;
+  WarpScratch* ws = reinterpret_cast<WarpScratch*>(smem) + (threadIdx.x >> 5);
+  constexpr size_t kScratch = (sizeof(WarpScratch) * EC_WARPS + 15) / 16 * 16;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + kScratch);
   const uint4* rmask = w.rmask;
   const double2* lohi = w.lohi;
@@ -178,7 +176,6 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * EC_WARPS + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * EC_WARPS;
-  constexpr int kS = WarpScratch<D>::kStride;
   volatile int32_t* vfirst = ws->first;
 
   for (int64_t base = warp0 * 32; base < a.count; base += nwarps * 32) {
@@ -196,6 +193,8 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
     }
     // ---- A. endpoints, distance, nStates (lane = edge) --------------------------------------
     double f[D], t[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) { f[j] = 0.0; t[j] = 0.0; }
     uint32_t n = 0, off = 0;
     bool need = e < a.count && edge_prologue<D, INDEXED>(a, pv, e, f, t, n, off);
 
@@ -237,16 +236,10 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
       a.first[e] = -1;
       need = false;
     }
-    uint32_t cnt = need ? n - 2u : 0u;  // slots 1..n-2, BP.cpp:510
-    if (need) {
 #pragma unroll
-      for (int j = 0; j < D; ++j) {
-        ws->ef[lane * kS + j] = f[j];
-        ws->ef[lane * kS + D + j] = __dsub_rn(t[j], f[j]);  // interpolate: (to - from)
-      }
-      ws->off[lane] = off;
-      ws->nc[lane] = nc > EC_MAXCAND ? -1 : nc;
-    }
+    for (int j = 0; j < D; ++j) t[j] = __dsub_rn(t[j], f[j]);  // interpolate: (to - from); t now holds it
+    const uint32_t cnt = need ? n - 2u : 0u;                    // slots 1..n-2, BP.cpp:510
+    const int ncl = nc > EC_MAXCAND ? -1 : nc;                  // -1: list overflow -> test every box
     ws->first[lane] = 0x7fffffff;
     uint32_t incl = cnt;
 #pragma unroll
@@ -254,42 +247,47 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
       uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += y;
     }
-    ws->start[lane] = incl - cnt;
-    if (lane == 31) ws->start[32] = incl;
+    const uint32_t start = incl - cnt;  // exclusive prefix of the slots to test per edge
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     __syncwarp();
 
-    // ---- C. flattened (edge, slot) pairs (lane = sample) ---------------------------------------
+    // ---- C. flattened (edge, slot) pairs (lane = sample).  The edge data stays in the owner lane's
+    // registers and is fetched with warp shuffles; every lane executes the shuffles of every round. ----
     for (uint32_t ib = 0; ib < total; ib += 32) {
       const uint32_t it = ib + lane;
-      if (it < total) {
-        int lo_i = 0, hi_i = 32;  // last edge whose first item is <= it
+      int lo_i = 0, hi_i = 32;  // last edge whose first item is <= it
 #pragma unroll
-        for (int s = 0; s < 5; ++s) {
-          int mid = (lo_i + hi_i) >> 1;
-          if (ws->start[mid] <= it) lo_i = mid; else hi_i = mid;
-        }
-        const int el = lo_i;
-        const int32_t slot = (int32_t)(1u + it - ws->start[el]);
-        if (slot < vfirst[el]) {  // a smaller invalid slot is already known: nothing to add
-          const double tt = __ldg(pv.tfrac + ws->off[el] + slot);  // (1+perm[i])/(n+1), BP.cpp:459
-          double x[D];
+      for (int s = 0; s < 5; ++s) {
+        const int mid = (lo_i + hi_i) >> 1;
+        const uint32_t sm = __shfl_sync(0xffffffffu, start, mid);
+        if (sm <= it) lo_i = mid; else hi_i = mid;
+      }
+      const int el = lo_i;
+      const int32_t slot = (int32_t)(1u + it - __shfl_sync(0xffffffffu, start, el));
+      const uint32_t off_el = __shfl_sync(0xffffffffu, off, el);
+      const int ncl_el = __shfl_sync(0xffffffffu, ncl, el);
+      const bool act = it < total && slot < vfirst[el];  // a smaller invalid slot already known: skip
+      double tt = 0.0;
+      if (act) tt = __ldg(pv.tfrac + off_el + slot);    // (1+perm[i])/(n+1), BP.cpp:459
+      double x[D];
 #pragma unroll
-          for (int j = 0; j < D; ++j)
-            x[j] = __dadd_rn(ws->ef[el * kS + j], __dmul_rn(ws->ef[el * kS + D + j], tt));
-          const int ncl = ws->nc[el];
-          bool inside = false;
-          if (ncl >= 0) {
-            for (int c = 0; c < ncl; ++c) {
-              const int b = ws->list[c * 32 + el];
-              if (bp_inside_box<D>(x, lohi + (size_t)b * w.lohi_stride)) { inside = true; break; }
-            }
-          } else {  // more candidates than the list holds: test every box (rare)
-            for (int b = 0; b < w.nboxes; ++b)
-              if (bp_inside_box<D>(x, lohi + (size_t)b * w.lohi_stride)) { inside = true; break; }
+      for (int j = 0; j < D; ++j) {
+        const double fj = __shfl_sync(0xffffffffu, f[j], el);
+        const double dj = __shfl_sync(0xffffffffu, t[j], el);
+        x[j] = __dadd_rn(fj, __dmul_rn(dj, tt));
+      }
+      if (act) {
+        bool inside = false;
+        if (ncl_el >= 0) {
+          for (int c = 0; c < ncl_el; ++c) {
+            const int b = ws->list[c * 32 + el];
+            if (bp_inside_box_grouped<D>(x, lohi + (size_t)b * w.lohi_stride)) { inside = true; break; }
           }
-          if (inside) atomicMin(&ws->first[el], slot);
+        } else {  // more candidates than the list holds: test every box (rare)
+          for (int b = 0; b < w.nboxes; ++b)
+            if (bp_inside_box<D>(x, lohi + (size_t)b * w.lohi_stride)) { inside = true; break; }
         }
+        if (inside) atomicMin(&ws->first[el], slot);
       }
     }
     __syncwarp();
@@ -332,7 +330,7 @@ __global__ void __launch_bounds__(256) edge_check_image_kernel(EdgeArgs a, Image
 template <int D, bool INDEXED>
 static int launch_boxes(bpomp_ctx* ctx, const EdgeArgs& a) {
   const BoxWorldView& w = ctx->boxes;
-  size_t base = (sizeof(WarpScratch<D>) * EC_WARPS + 15) / 16 * 16 + 16;
+  size_t base = (sizeof(WarpScratch) * EC_WARPS + 15) / 16 * 16 + 16;
   size_t staged = base + w.rmask_bytes + w.lohi_bytes;
   bool stage = staged <= (size_t)ctx->smem_optin && w.rmask_bytes + w.lohi_bytes < (1u << 20) && w.nboxes > 0;
   int64_t tiles = (a.count + EC_THREADS - 1) / EC_THREADS;

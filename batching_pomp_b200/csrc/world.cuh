@@ -28,6 +28,31 @@ __device__ __forceinline__ bool bp_inside_box(const double* x, const double2* lo
   return true;
 }
 
+// Same test with the loads of a group of dimensions issued together (one shared-memory round trip per
+// group instead of one per dimension): dims [0,D1) first, the rest only if those all pass.  Measured on
+// the headline config: D1 = 2 / 3 / 4 / 7 -> 1.048 / 1.042 / 1.041 / 1.016 ms, so all loads go first.
+template <int D>
+__device__ __forceinline__ bool bp_inside_box_grouped(const double* x, const double2* lohi_row) {
+#ifndef BP_D1
+#define BP_D1 7
+#endif
+  constexpr int D1 = D < BP_D1 ? D : BP_D1;
+  double2 lh[D];
+#pragma unroll
+  for (int j = 0; j < D1; ++j) lh[j] = lohi_row[j];
+  bool in = true;
+#pragma unroll
+  for (int j = 0; j < D1; ++j) in = in && (lh[j].x <= x[j]) && (x[j] <= lh[j].y);
+  if (!in) return false;
+  if (D > D1) {
+#pragma unroll
+    for (int j = D1; j < D; ++j) lh[j] = lohi_row[j];
+#pragma unroll
+    for (int j = D1; j < D; ++j) in = in && (lh[j].x <= x[j]) && (x[j] <= lh[j].y);
+  }
+  return in;
+}
+
 // Point query through the prefix masks (cell range [c,c]).  rmask/lohi may point to shared or global.
 template <int D>
 __device__ __forceinline__ bool bp_valid_boxes(const double* x, const BoxWorldView& w, const uint4* rmask,
