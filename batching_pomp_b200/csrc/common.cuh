@@ -11,7 +11,8 @@
 #include "bpomp_cuda.h"
 
 #define BP_ABSENT 0xFFFFFFFFu
-#define BP_GRID_C 64  // broad-phase cells per dimension
+#define BP_GRID_C 32   // broad-phase cells per dimension
+#define BP_SPAN 8      // cell ranges [c0, c0+span], span < BP_SPAN, have a combined mask row
 
 // ---------------------------------------------------------------------------
 // Error handling: no exception crosses the ABI.
@@ -58,9 +59,12 @@ struct BoxWorldView {
   int w4;                       // candidate-mask width in uint4 units (power of two >= ceil(B/128))
   int lohi_stride;              // row stride of lohi in double2 units (dim | 1)
   const double2* lohi;          // [B][lohi_stride]  (.x = lo, .y = hi)
-  const uint4* rmask;           // [w4][rows] prefix masks, rows = dim*2*BP_GRID_C (bp_row): row (j,0,c) = boxes
-                                // whose lowest cell in dim j is <= c, row (j,1,c) = boxes whose highest cell is >= c
-  int rows;
+  const uint4* rmask;           // [w4][rows] range masks: row bp_rrow(j,c0,span) = boxes whose cell interval in
+                                // dim j meets [c0, c0+span]; then (for longer ranges) [w4][rows_ab] prefix masks:
+                                // row bp_row(j,0,c) = lowest cell <= c, bp_row(j,1,c) = highest cell >= c
+  int rows;                     // dim*BP_GRID_C*BP_SPAN
+  int rows_ab;                  // dim*2*BP_GRID_C
+  size_t ab_off;                // uint4 offset of the prefix masks inside rmask (kept in global memory)
   double g0[BPOMP_DIM_MAX];     // grid origin per dim
   double gs[BPOMP_DIM_MAX];     // cells per unit length per dim
   size_t rmask_bytes, lohi_bytes;
@@ -181,6 +185,8 @@ __host__ __device__ __forceinline__ int bp_cell(double x, double g0, double gs) 
   return (int)v;
 }
 
+// Row of the range-mask table for cells [c0, c0+span] of dimension j (span < BP_SPAN).
+__host__ __device__ __forceinline__ int bp_rrow(int j, int c0, int span) { return (j * BP_GRID_C + c0) * BP_SPAN + span; }
 // Row of the prefix-mask table: which = 0 -> "lowest cell <= c", which = 1 -> "highest cell >= c".
 __host__ __device__ __forceinline__ int bp_row(int j, int which, int c) { return (j * 2 + which) * BP_GRID_C + c; }
 

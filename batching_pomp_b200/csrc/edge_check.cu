@@ -201,19 +201,27 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
     // ---- B. broad phase ------------------------------------------------------------------------
     int nc = 0;
     if (need && w.nboxes > 0) {
-      int ra[D], rb[D];
+      int rr[D];  // >= 0: combined range row; < 0: -(1 + c0*BP_GRID_C + c1), prefix rows from global memory
 #pragma unroll
       for (int j = 0; j < D; ++j) {
-        ra[j] = bp_row(j, 0, bp_cell(fmax(f[j], t[j]), w.g0[j], w.gs[j]));  // lowest cell <= c1
-        rb[j] = bp_row(j, 1, bp_cell(fmin(f[j], t[j]), w.g0[j], w.gs[j]));  // highest cell >= c0
+        const int c0 = bp_cell(fmin(f[j], t[j]), w.g0[j], w.gs[j]);
+        const int c1 = bp_cell(fmax(f[j], t[j]), w.g0[j], w.gs[j]);
+        rr[j] = (c1 - c0 < BP_SPAN) ? bp_rrow(j, c0, c1 - c0) : -(1 + c0 * BP_GRID_C + c1);
       }
       for (int g = 0; g < w.w4; ++g) {
         uint4 m = make_uint4(~0u, ~0u, ~0u, ~0u);
 #pragma unroll
         for (int j = 0; j < D; ++j) {
-          uint4 va = rmask[bp_midx(ra[j], g, w.rows)];
-          uint4 vb = rmask[bp_midx(rb[j], g, w.rows)];
-          m.x &= va.x & vb.x; m.y &= va.y & vb.y; m.z &= va.z & vb.z; m.w &= va.w & vb.w;
+          uint4 v;
+          if (rr[j] >= 0) {
+            v = rmask[bp_midx(rr[j], g, w.rows)];
+          } else {  // long range in this dimension (rare): lowest cell <= c1 and highest cell >= c0
+            const int cc = -rr[j] - 1, c0 = cc / BP_GRID_C, c1 = cc % BP_GRID_C;
+            const uint4 va = __ldg(w.rmask + w.ab_off + bp_midx(bp_row(j, 0, c1), g, w.rows_ab));
+            const uint4 vb = __ldg(w.rmask + w.ab_off + bp_midx(bp_row(j, 1, c0), g, w.rows_ab));
+            v = make_uint4(va.x & vb.x, va.y & vb.y, va.z & vb.z, va.w & vb.w);
+          }
+          m.x &= v.x; m.y &= v.y; m.z &= v.z; m.w &= v.w;
         }
         unsigned long long m01 = (unsigned long long)m.x | ((unsigned long long)m.y << 32);
         unsigned long long m23 = (unsigned long long)m.z | ((unsigned long long)m.w << 32);

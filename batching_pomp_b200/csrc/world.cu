@@ -58,14 +58,18 @@ extern "C" int bpomp_world_set_boxes(bpomp_ctx* ctx, const double* lo, const dou
     w.gs[j] = (nboxes > 0 && std::isfinite(span) && span > 0.0) ? (double)BP_GRID_C / span : 0.0;
     if (!std::isfinite(w.gs[j])) w.gs[j] = 0.0;
   }
-  // Prefix masks per dimension j and cell c (bp_row): "lowest cell of the box <= c" and "highest cell
-  // of the box >= c".  A box's cell interval [cell(lo_j), cell(hi_j)] meets the cell range [c0,c1] iff
-  // lowest <= c1 and highest >= c0, i.e. mask(j,0,c1) & mask(j,1,c0).  bp_cell is monotone, so any x in
-  // [lo_j,hi_j] has cell(x) inside the box's interval: the AND over all dimensions of the masks of the
-  // cell range spanned by a segment's endpoints is a superset of the boxes the segment can touch.
-  const int rows = D * 2 * BP_GRID_C;
+  // Broad-phase masks (one bit per box).  bp_cell is monotone, so any x in [lo_j,hi_j] has cell(x) inside
+  // the box's cell interval [cl,ch]; a segment whose endpoints span cells [c0,c1] in dimension j can only
+  // touch boxes with cl <= c1 and ch >= c0.  Short ranges (c1-c0 < BP_SPAN) get one combined row
+  // bp_rrow(j,c0,span); longer ones use two prefix rows, bp_row(j,0,c1) & bp_row(j,1,c0).  The AND over
+  // all dimensions is a superset of the boxes the segment can touch.
+  const int rows = D * BP_GRID_C * BP_SPAN;
+  const int rows_ab = D * 2 * BP_GRID_C;
   w.rows = rows;
-  std::vector<uint32_t> rmask((size_t)rows * w4 * 4, 0u);
+  w.rows_ab = rows_ab;
+  w.ab_off = (size_t)rows * w4;
+  std::vector<uint32_t> rmask(((size_t)rows + rows_ab) * w4 * 4, 0u);
+  uint32_t* ab = rmask.data() + w.ab_off * 4;
   std::vector<double2> lohi((size_t)std::max(nboxes, 1) * w.lohi_stride, make_double2(1.0, 0.0));
   for (int b = 0; b < nboxes; ++b) {
     bool empty = false;
@@ -76,26 +80,24 @@ extern "C" int bpomp_world_set_boxes(bpomp_ctx* ctx, const double* lo, const dou
     }
     if (empty) continue;
     const int word = b >> 5, g = word >> 2;
+    const uint32_t bit = 1u << (b & 31);
     for (int j = 0; j < D; ++j) {
       int cl = bp_cell(lo[(size_t)b * D + j], w.g0[j], w.gs[j]);
       int ch = bp_cell(hi[(size_t)b * D + j], w.g0[j], w.gs[j]);
       for (int c = 0; c < BP_GRID_C; ++c) {
-        if (cl <= c) {
-          int row = bp_row(j, 0, c);
-          rmask[bp_midx(row, g, rows) * 4 + (word & 3)] |= 1u << (b & 31);
-        }
-        if (ch >= c) {
-          int row = bp_row(j, 1, c);
-          rmask[bp_midx(row, g, rows) * 4 + (word & 3)] |= 1u << (b & 31);
-        }
+        if (cl <= c) ab[bp_midx(bp_row(j, 0, c), g, rows_ab) * 4 + (word & 3)] |= bit;
+        if (ch >= c) ab[bp_midx(bp_row(j, 1, c), g, rows_ab) * 4 + (word & 3)] |= bit;
+        for (int s = 0; s < BP_SPAN; ++s)
+          if (cl <= c + s && ch >= c) rmask[bp_midx(bp_rrow(j, c, s), g, rows) * 4 + (word & 3)] |= bit;
       }
     }
   }
-  w.rmask_bytes = rmask.size() * sizeof(uint32_t);
+  w.rmask_bytes = (size_t)rows * w4 * 16;  // the part staged into shared memory (range masks only)
   w.lohi_bytes = (size_t)nboxes * w.lohi_stride * sizeof(double2);
-  BP_TRY(bp_reserve(ctx, ctx->d_rmask, w.rmask_bytes, false));
+  BP_TRY(bp_reserve(ctx, ctx->d_rmask, rmask.size() * sizeof(uint32_t), false));
   BP_TRY(bp_reserve(ctx, ctx->d_lohi, lohi.size() * sizeof(double2), false));
-  BP_CUDA(ctx, cudaMemcpyAsync(ctx->d_rmask.p, rmask.data(), w.rmask_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  BP_CUDA(ctx, cudaMemcpyAsync(ctx->d_rmask.p, rmask.data(), rmask.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                               ctx->stream));
   BP_CUDA(ctx, cudaMemcpyAsync(ctx->d_lohi.p, lohi.data(), lohi.size() * sizeof(double2), cudaMemcpyHostToDevice,
                                ctx->stream));
   BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

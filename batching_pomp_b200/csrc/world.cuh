@@ -53,7 +53,7 @@ __device__ __forceinline__ bool bp_inside_box_grouped(const double* x, const dou
   return in;
 }
 
-// Point query through the prefix masks (cell range [c,c]).  rmask/lohi may point to shared or global.
+// Point query through the range masks (cell range [c,c]).  rmask/lohi may point to shared or global.
 template <int D>
 __device__ __forceinline__ bool bp_valid_boxes(const double* x, const BoxWorldView& w, const uint4* rmask,
                                                const double2* lohi) {
@@ -65,10 +65,8 @@ __device__ __forceinline__ bool bp_valid_boxes(const double* x, const BoxWorldVi
     uint4 m = make_uint4(~0u, ~0u, ~0u, ~0u);
 #pragma unroll
     for (int j = 0; j < D; ++j) {
-      int ra = bp_row(j, 0, cell[j]), rb = bp_row(j, 1, cell[j]);
-      uint4 va = rmask[bp_midx(ra, g, w.rows)];
-      uint4 vb = rmask[bp_midx(rb, g, w.rows)];
-      m.x &= va.x & vb.x; m.y &= va.y & vb.y; m.z &= va.z & vb.z; m.w &= va.w & vb.w;
+      uint4 v = rmask[bp_midx(bp_rrow(j, cell[j], 0), g, w.rows)];
+      m.x &= v.x; m.y &= v.y; m.z &= v.z; m.w &= v.w;
     }
     unsigned words[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
