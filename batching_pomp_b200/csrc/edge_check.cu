@@ -143,7 +143,14 @@ struct WarpScratch {
   unsigned short list[EC_MAXCAND * 32];      // candidate boxes [c][lane]
 };
 
-template <int D, bool INDEXED, bool STAGE>
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+// W4 = number of 128-box groups when it is 1, 2, 4 or 8 (compile-time fast path), 0 = any (runtime loop).
+template <int D, bool INDEXED, bool STAGE, int W4>
 __global__ void __launch_bounds__(EC_THREADS, 1)
     edge_check_boxes_kernel(EdgeArgs a, BoxWorldView w, PermView pv) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -153,6 +160,7 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + kScratch);
   const uint4* rmask = w.rmask;
   const double2* lohi = w.lohi;
+  uint32_t s_rmask_addr = 0;
   if (STAGE) {
     uint4* s_rmask = reinterpret_cast<uint4*>(smem + kScratch + 16);
     double2* s_lohi = reinterpret_cast<double2*>(reinterpret_cast<unsigned char*>(s_rmask) + w.rmask_bytes);
@@ -171,6 +179,7 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
     mbar_wait(s_bar, 0);
     rmask = s_rmask;
     lohi = s_lohi;
+    s_rmask_addr = smem_u32(s_rmask);
   }
 
   const int lane = threadIdx.x & 31;
@@ -202,27 +211,15 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
     int nc = 0;
     if (need && w.nboxes > 0) {
       int rr[D];  // >= 0: combined range row; < 0: -(1 + c0*BP_GRID_C + c1), prefix rows from global memory
+      bool longspan = false;
 #pragma unroll
       for (int j = 0; j < D; ++j) {
         const int c0 = bp_cell(fmin(f[j], t[j]), w.g0[j], w.gs[j]);
         const int c1 = bp_cell(fmax(f[j], t[j]), w.g0[j], w.gs[j]);
         rr[j] = (c1 - c0 < BP_SPAN) ? bp_rrow(j, c0, c1 - c0) : -(1 + c0 * BP_GRID_C + c1);
+        longspan = longspan || rr[j] < 0;
       }
-      for (int g = 0; g < w.w4; ++g) {
-        uint4 m = make_uint4(~0u, ~0u, ~0u, ~0u);
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-          uint4 v;
-          if (rr[j] >= 0) {
-            v = rmask[bp_midx(rr[j], g, w.rows)];
-          } else {  // long range in this dimension (rare): lowest cell <= c1 and highest cell >= c0
-            const int cc = -rr[j] - 1, c0 = cc / BP_GRID_C, c1 = cc % BP_GRID_C;
-            const uint4 va = __ldg(w.rmask + w.ab_off + bp_midx(bp_row(j, 0, c1), g, w.rows_ab));
-            const uint4 vb = __ldg(w.rmask + w.ab_off + bp_midx(bp_row(j, 1, c0), g, w.rows_ab));
-            v = make_uint4(va.x & vb.x, va.y & vb.y, va.z & vb.z, va.w & vb.w);
-          }
-          m.x &= v.x; m.y &= v.y; m.z &= v.z; m.w &= v.w;
-        }
+      auto emit = [&](int g, uint4 m) {  // append the set bits of one 128-box group to the candidate list
         unsigned long long m01 = (unsigned long long)m.x | ((unsigned long long)m.y << 32);
         unsigned long long m23 = (unsigned long long)m.z | ((unsigned long long)m.w << 32);
         while (m01) {
@@ -236,6 +233,42 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
           m23 &= m23 - 1;
           if (nc < EC_MAXCAND) ws->list[nc * 32 + lane] = (unsigned short)b;
           ++nc;
+        }
+      };
+      if (STAGE && W4 > 0 && !longspan) {
+        // fast path: table in shared memory, group count and row count known at compile time, so every
+        // load is one LDS.128 at (row address + immediate)
+        constexpr int kRows = D * BP_GRID_C * BP_SPAN;
+        uint32_t ra[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) ra[j] = s_rmask_addr + (uint32_t)rr[j] * 16u;
+#pragma unroll 1
+        for (int g = 0; g < (W4 > 0 ? W4 : 1); ++g) {
+          uint4 m = lds128(ra[0] + (uint32_t)(g * kRows * 16));
+#pragma unroll
+          for (int j = 1; j < D; ++j) {
+            const uint4 v = lds128(ra[j] + (uint32_t)(g * kRows * 16));
+            m.x &= v.x; m.y &= v.y; m.z &= v.z; m.w &= v.w;
+          }
+          emit(g, m);
+        }
+      } else {
+        for (int g = 0; g < w.w4; ++g) {
+          uint4 m = make_uint4(~0u, ~0u, ~0u, ~0u);
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            uint4 v;
+            if (rr[j] >= 0) {
+              v = rmask[bp_midx(rr[j], g, w.rows)];
+            } else {  // long range in this dimension (rare): lowest cell <= c1 and highest cell >= c0
+              const int cc = -rr[j] - 1, c0 = cc / BP_GRID_C, c1 = cc % BP_GRID_C;
+              const uint4 va = __ldg(w.rmask + w.ab_off + bp_midx(bp_row(j, 0, c1), g, w.rows_ab));
+              const uint4 vb = __ldg(w.rmask + w.ab_off + bp_midx(bp_row(j, 1, c0), g, w.rows_ab));
+              v = make_uint4(va.x & vb.x, va.y & vb.y, va.z & vb.z, va.w & vb.w);
+            }
+            m.x &= v.x; m.y &= v.y; m.z &= v.z; m.w &= v.w;
+          }
+          emit(g, m);
         }
       }
     }
@@ -344,11 +377,17 @@ static int launch_boxes(bpomp_ctx* ctx, const EdgeArgs& a) {
   int64_t tiles = (a.count + EC_THREADS - 1) / EC_THREADS;
   int grid = (int)std::min<int64_t>(tiles, ctx->num_sms);
   if (stage) {
-    auto k = edge_check_boxes_kernel<D, INDEXED, true>;
+    void (*k)(EdgeArgs, BoxWorldView, PermView);
+    switch (w.w4) {
+      case 1: k = edge_check_boxes_kernel<D, INDEXED, true, 1>; break;
+      case 2: k = edge_check_boxes_kernel<D, INDEXED, true, 2>; break;
+      case 4: k = edge_check_boxes_kernel<D, INDEXED, true, 4>; break;
+      default: k = edge_check_boxes_kernel<D, INDEXED, true, 0>; break;
+    }
     BP_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged));
     k<<<grid, EC_THREADS, staged, ctx->stream>>>(a, w, ctx->perm_view());
   } else {
-    auto k = edge_check_boxes_kernel<D, INDEXED, false>;
+    auto k = edge_check_boxes_kernel<D, INDEXED, false, 0>;
     BP_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base));
     k<<<grid, EC_THREADS, base, ctx->stream>>>(a, w, ctx->perm_view());
   }
