@@ -104,7 +104,7 @@ struct bpomp_ctx {
   int world = WORLD_NONE;
   BoxWorldView boxes{};
   ImageWorldView image{};
-  DevBuf d_lohi, d_rmask, d_bits;
+  DevBuf d_lohi, d_rmask, d_bits, d_work;
 
   // vertex table (elements of mVertexNN)
   DevBuf d_verts, d_active;

@@ -228,7 +228,7 @@ extern "C" void bpomp_destroy(bpomp_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->d_perm_off, &ctx->d_tfrac, &ctx->d_step, &ctx->d_need, &ctx->d_lohi, &ctx->d_rmask,
-                    &ctx->d_bits, &ctx->d_verts, &ctx->d_active, &ctx->d_nb_rowptr, &ctx->d_nb_col,
+                    &ctx->d_bits, &ctx->d_work, &ctx->d_verts, &ctx->d_active, &ctx->d_nb_rowptr, &ctx->d_nb_col,
                     &ctx->d_nb_dist, &ctx->d_nb_query, &ctx->d_nb_tmp, &ctx->d_nb_tmp2, &ctx->d_grid_cell_start,
                     &ctx->d_grid_ids, &ctx->d_grid_pts, &ctx->d_grid_keys, &ctx->d_bel_pts, &ctx->d_bel_vals,
                     &ctx->s_a, &ctx->s_b, &ctx->s_c, &ctx->s_d, &ctx->s_e, &ctx->s_f, &ctx->s_g, &ctx->s_h, &ctx->s_i,

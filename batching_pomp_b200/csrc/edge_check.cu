@@ -14,6 +14,7 @@
 #define EC_THREADS 768
 #endif
 #define EC_MAXCAND 16
+#define EC_CHUNK 8   // tiles of 32 edges claimed per atomic
 
 struct EdgeArgs {
   const double* from;        // [count][D] or null (indexed)
@@ -27,6 +28,7 @@ struct EdgeArgs {
   uint32_t* nstates;         // may be null
   int deferred_only;         // re-run: only edges currently marked BPOMP_EDGE_DEFERRED
   double L;
+  unsigned long long* work;  // dynamic tile counter (zeroed before the launch)
 };
 
 // ---- bulk async copy global -> shared (TMA engine, 1-D), completion on an mbarrier ----------
@@ -183,14 +185,23 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
   }
 
   const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (int64_t)blockIdx.x * EC_WARPS + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * EC_WARPS;
   volatile int32_t* vfirst = ws->first;
 
-  for (int64_t base = warp0 * 32; base < a.count; base += nwarps * 32) {
+  // Dynamic work distribution: a warp claims EC_CHUNK consecutive tiles of 32 edges at a time from a
+  // global counter, so the kernel keeps its throughput when some SMs are busy with other work (e.g. the
+  // NCCL kernel that merges the previous step's results) and the tail is balanced.
+  for (;;) {
+    unsigned long long chunk = 0;
+    if (lane == 0) chunk = atomicAdd(a.work, 1ull);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    const int64_t chunk_base = (int64_t)chunk * (EC_CHUNK * 32);
+    if (chunk_base >= a.count) break;
+  for (int ti = 0; ti < EC_CHUNK; ++ti) {
+    const int64_t base = chunk_base + (int64_t)ti * 32;
+    if (base >= a.count) break;
     const int64_t e = base + lane;
-    if (!INDEXED) {  // pull the next tile's endpoint rows (contiguous) towards L2 while this one is processed
-      const int64_t nb = base + nwarps * 32;
+    if (!INDEXED && ti + 1 < EC_CHUNK) {  // pull the next tile's endpoint rows (contiguous) towards L2
+      const int64_t nb = base + 32;
       constexpr int kLines = (32 * D * 8 + 127) / 128 + 1;
       if (nb < a.count && lane < kLines) {
         const size_t o = (size_t)nb * D * 8 + (size_t)lane * 128;
@@ -339,6 +350,7 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
     }
     __syncwarp();
   }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -420,6 +432,9 @@ int bp_launch_edge_check(bpomp_ctx* ctx, const double* d_from, const double* d_t
   a.count = count; a.valid = d_valid; a.first = d_first; a.nstates = d_nstates;
   a.deferred_only = deferred_only ? 1 : 0;
   a.L = ctx->L;
+  BP_TRY(bp_reserve(ctx, ctx->d_work, 256, false));
+  a.work = ctx->d_work.as<unsigned long long>();
+  BP_CUDA(ctx, cudaMemsetAsync(a.work, 0, sizeof(unsigned long long), ctx->stream));
   const bool indexed = d_from_ids != nullptr;
   if (ctx->world == WORLD_IMAGE) {
     int grid = (int)std::min<int64_t>((count + 255) / 256, (int64_t)ctx->num_sms * 8);

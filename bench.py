@@ -15,8 +15,8 @@ One "step" = one pass of the hot path (checkAndSetEdgeBlocked's isValid loop,
   cpu_baseline the CPU oracle (port of the reference loop) on all host cores, bounded sample
 
 N > 1 (torchrun, one rank per GPU): every rank evaluates its own 10^7-edge shard (weak scaling, world
-replicated) and the first-invalid-slot results are merged with an NCCL all-gather that overlaps the
-next step's kernel.  --impl reference times the CPU oracle only (rank 0).
+replicated) and the edge status flags are merged with an NCCL all-gather that overlaps the next
+step's kernel.  --impl reference times the CPU oracle only (rank 0).
 """
 import argparse
 import json
@@ -205,7 +205,7 @@ def run_gpu(args):
     nbuf = 2 if world > 1 else 1
     d_valid = [d_valid] + [torch.empty_like(d_valid) for _ in range(nbuf - 1)]
     d_first = [d_first] + [torch.empty_like(d_first) for _ in range(nbuf - 1)]
-    gathered = [torch.empty(world * E, dtype=torch.int32, device=dev) for _ in range(nbuf)] if world > 1 else None
+    gathered = [torch.empty(world * E, dtype=torch.uint8, device=dev) for _ in range(nbuf)] if world > 1 else None
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
     kernel_ms = []
     pending = [None] * nbuf
@@ -231,7 +231,7 @@ def run_gpu(args):
             ev.record(stream)
             with torch.cuda.stream(comm_stream):
                 comm_stream.wait_event(ev)
-                pending[k] = sharding.allgather_equal(d_first[k], gathered[k], async_op=True)[1]
+                pending[k] = sharding.allgather_equal(d_valid[k], gathered[k], async_op=True)[1]
 
     def drain():
         for k in range(nbuf):
@@ -296,7 +296,7 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms, e2e_s = float(t[0]), float(t[1])
         # merged result sanity: this rank's shard must sit at its slot of the gathered buffer
-        assert torch.equal(gathered[0][rank * E:(rank + 1) * E], d_first[0])
+        assert torch.equal(gathered[0][rank * E:(rank + 1) * E], d_valid[0])
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -320,8 +320,9 @@ def run_gpu(args):
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(E, world, {
-                "merge": ("nccl all_gather of first_invalid_slot (4 B/edge) per step, overlapped with the next "
-                          "step's kernel (double-buffered results)") if world > 1 else "none (single GPU)"}),
+                "merge": ("nccl all_gather of the edge status flags (1 B/edge) per step, overlapped with the next "
+                          "step's kernel (double-buffered results); first-invalid slots stay with the shard "
+                          "owner, which replays the belief inserts") if world > 1 else "none (single GPU)"}),
             "kernel_ms_per_step": kern_ms_per_step,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
