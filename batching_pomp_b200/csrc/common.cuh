@@ -125,6 +125,11 @@ struct bpomp_ctx {
   DevBuf d_bel_pts, d_bel_vals;
   uint64_t bel_count = 0;
 
+  // pipelined host-buffer edge checks (edge_check.cu)
+  cudaStream_t lane_stream[3] = {nullptr, nullptr, nullptr};
+  DevBuf lane_a[3], lane_b[3], lane_o[3];
+  int work_slot = 0;
+
   // staging / scratch
   DevBuf s_a, s_b, s_c, s_d, s_e, s_f, s_g, s_h, s_i, s_j, s_scan;
 

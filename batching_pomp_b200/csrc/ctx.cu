@@ -234,6 +234,12 @@ extern "C" void bpomp_destroy(bpomp_ctx* ctx) {
                     &ctx->s_a, &ctx->s_b, &ctx->s_c, &ctx->s_d, &ctx->s_e, &ctx->s_f, &ctx->s_g, &ctx->s_h, &ctx->s_i,
                     &ctx->s_j, &ctx->s_scan};
   for (DevBuf* b : bufs) bp_free(*b);
+  for (int l = 0; l < 3; ++l) {
+    bp_free(ctx->lane_a[l]);
+    bp_free(ctx->lane_b[l]);
+    bp_free(ctx->lane_o[l]);
+    if (ctx->lane_stream[l]) cudaStreamDestroy(ctx->lane_stream[l]);
+  }
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   if (ctx->d_flags) cudaFree(ctx->d_flags);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

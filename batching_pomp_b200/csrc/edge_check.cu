@@ -433,7 +433,7 @@ int bp_launch_edge_check(bpomp_ctx* ctx, const double* d_from, const double* d_t
   a.deferred_only = deferred_only ? 1 : 0;
   a.L = ctx->L;
   BP_TRY(bp_reserve(ctx, ctx->d_work, 256, false));
-  a.work = ctx->d_work.as<unsigned long long>();
+  a.work = ctx->d_work.as<unsigned long long>() + ctx->work_slot;  // one counter per pipeline lane
   BP_CUDA(ctx, cudaMemsetAsync(a.work, 0, sizeof(unsigned long long), ctx->stream));
   const bool indexed = d_from_ids != nullptr;
   if (ctx->world == WORLD_IMAGE) {
@@ -498,22 +498,91 @@ static int resolve_deferred(bpomp_ctx* ctx, const double* d_from, const double* 
   return BPOMP_OK;
 }
 
+// Large host-buffer batches are pipelined: chunks of EC_PIPE_CHUNK edges alternate over EC_PIPE_LANES
+// streams, each doing H2D -> kernel -> D2H on its own staging buffers, so the copies of one chunk overlap
+// the kernel and the copies of the others (the call is PCIe-bound: 112 B in + 5..9 B out per 7-DoF edge).
+#define EC_PIPE_LANES 3
+#define EC_PIPE_CHUNK (1 << 20)
+
+static int edges_check_pipelined(bpomp_ctx* ctx, const double* from, const double* to, const uint32_t* fi,
+                                 const uint32_t* ti, int64_t count, uint8_t* valid, int32_t* first,
+                                 uint32_t* nstates) {
+  const bool indexed = fi != nullptr;
+  const size_t in_elem = indexed ? sizeof(uint32_t) : (size_t)ctx->dim * sizeof(double);
+  for (int l = 0; l < EC_PIPE_LANES; ++l) {
+    if (!ctx->lane_stream[l]) BP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking));
+    BP_TRY(bp_reserve(ctx, ctx->lane_a[l], EC_PIPE_CHUNK * in_elem, false));
+    BP_TRY(bp_reserve(ctx, ctx->lane_b[l], EC_PIPE_CHUNK * in_elem, false));
+    BP_TRY(bp_reserve(ctx, ctx->lane_o[l], (size_t)EC_PIPE_CHUNK * 9, false));
+  }
+  cudaEvent_t ev;
+  BP_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  BP_CUDA(ctx, cudaEventRecord(ev, ctx->stream));  // lanes start after whatever is queued on the ctx stream
+  cudaStream_t saved = ctx->stream;
+  int rc = BPOMP_OK;
+  for (int64_t c0 = 0, c = 0; c0 < count && rc == BPOMP_OK; c0 += EC_PIPE_CHUNK, ++c) {
+    const int l = (int)(c % EC_PIPE_LANES);
+    const int64_t m = std::min<int64_t>(EC_PIPE_CHUNK, count - c0);
+    cudaStream_t s = ctx->lane_stream[l];
+    if (c < EC_PIPE_LANES) cudaStreamWaitEvent(s, ev, 0);
+    const char* hf = indexed ? (const char*)(fi + c0) : (const char*)(from + c0 * ctx->dim);
+    const char* ht = indexed ? (const char*)(ti + c0) : (const char*)(to + c0 * ctx->dim);
+    cudaMemcpyAsync(ctx->lane_a[l].p, hf, (size_t)m * in_elem, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(ctx->lane_b[l].p, ht, (size_t)m * in_elem, cudaMemcpyHostToDevice, s);
+    uint8_t* dv = ctx->lane_o[l].as<uint8_t>();
+    int32_t* dfirst = reinterpret_cast<int32_t*>(dv + EC_PIPE_CHUNK);
+    uint32_t* dn = reinterpret_cast<uint32_t*>(dv + (size_t)EC_PIPE_CHUNK * 5);
+    ctx->stream = s;
+    ctx->work_slot = 1 + l;
+    rc = bp_launch_edge_check(ctx, indexed ? nullptr : ctx->lane_a[l].as<double>(),
+                              indexed ? nullptr : ctx->lane_b[l].as<double>(),
+                              indexed ? ctx->lane_a[l].as<uint32_t>() : nullptr,
+                              indexed ? ctx->lane_b[l].as<uint32_t>() : nullptr, m, dv, dfirst, dn, false);
+    ctx->stream = saved;
+    ctx->work_slot = 0;
+    cudaMemcpyAsync(valid + c0, dv, (size_t)m, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(first + c0, dfirst, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+    if (nstates) cudaMemcpyAsync(nstates + c0, dn, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
+  }
+  for (int l = 0; l < EC_PIPE_LANES; ++l) {
+    cudaError_t e2 = cudaStreamSynchronize(ctx->lane_stream[l]);
+    if (e2 != cudaSuccess && rc == BPOMP_OK)
+      rc = bp_fail(ctx, BPOMP_ERR_CUDA, "pipelined edge check failed: %s", cudaGetErrorString(e2));
+  }
+  cudaEventDestroy(ev);
+  BP_TRY(rc);
+  BP_TRY(bp_read_flags(ctx));
+  if (ctx->h_flags[1]) {
+    ctx->h_flags[1] = 0;
+    ctx->h_flags[0] = 0;
+    return bp_fail(ctx, BPOMP_ERR_RANGE, "an edge has more than %u states (segment_length too small)",
+                   BPOMP_NSTATES_MAX);
+  }
+  return ctx->h_flags[0] ? 1 : BPOMP_OK;  // 1: some sample orders were missing -> caller re-runs unpipelined
+}
+
 static int edges_check_host(bpomp_ctx* ctx, const double* from, const double* to, const uint32_t* fi,
                             const uint32_t* ti, int64_t count, uint8_t* valid, int32_t* first, uint32_t* nstates) {
   if (ctx->world == WORLD_NONE) return bp_fail(ctx, BPOMP_ERR_NO_WORLD, "no collision world set");
   if (count == 0) return BPOMP_OK;
   const bool indexed = fi != nullptr;
+  if (indexed) {
+    for (int64_t e = 0; e < count; ++e)
+      if (fi[e] >= ctx->nverts || ti[e] >= ctx->nverts)
+        return bp_fail(ctx, BPOMP_ERR_RANGE, "edge %lld references a vertex id out of range", (long long)e);
+  }
+  if (count >= 2 * (int64_t)EC_PIPE_CHUNK) {
+    int rc = edges_check_pipelined(ctx, from, to, fi, ti, count, valid, first, nstates);
+    if (rc <= 0) return rc;
+    // rc == 1: the missing sample orders get uploaded by the plain path below, which redoes the batch
+    ctx->h_flags[0] = 0;
+  }
   size_t in_bytes = indexed ? (size_t)count * sizeof(uint32_t) : (size_t)count * ctx->dim * sizeof(double);
   BP_TRY(bp_reserve(ctx, ctx->s_a, in_bytes, false));
   BP_TRY(bp_reserve(ctx, ctx->s_b, in_bytes, false));
   BP_TRY(bp_reserve(ctx, ctx->s_c, (size_t)count, false));
   BP_TRY(bp_reserve(ctx, ctx->s_d, (size_t)count * sizeof(int32_t), false));
   BP_TRY(bp_reserve(ctx, ctx->s_e, (size_t)count * sizeof(uint32_t), false));
-  if (indexed) {
-    for (int64_t e = 0; e < count; ++e)
-      if (fi[e] >= ctx->nverts || ti[e] >= ctx->nverts)
-        return bp_fail(ctx, BPOMP_ERR_RANGE, "edge %lld references a vertex id out of range", (long long)e);
-  }
   BP_CUDA(ctx, cudaMemcpyAsync(ctx->s_a.p, indexed ? (const void*)fi : (const void*)from, in_bytes,
                                cudaMemcpyHostToDevice, ctx->stream));
   BP_CUDA(ctx, cudaMemcpyAsync(ctx->s_b.p, indexed ? (const void*)ti : (const void*)to, in_bytes,

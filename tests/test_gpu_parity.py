@@ -67,6 +67,28 @@ def test_edge_check_long_edges_and_deferred_orders(capi, orc, wl):
         ctx.close()
 
 
+def test_edge_check_pipelined_host_path_with_deferred_orders(capi, orc, wl):
+    """> 2M edges take the chunked three-stream host path; long edges at a fine resolution need sample
+    orders that are not resident, which makes that path fall back and upload them."""
+    pix = wl.image_world(512, seed=1)
+    L = wl.segment_length(2, 0.002)
+    ctx = capi.Context(2, L)
+    ctx.set_world_image(pix)
+    count = 2200000
+    frm = wl.uniform(61, (count, 2))
+    to = wl.uniform(62, (count, 2))
+    v, f, n = ctx.edges_check(frm, to)
+    assert n.max() > 256
+    ov, of, on = orc.edges_check_image(frm, to, L, pix, nthreads=orc.max_threads())
+    np.testing.assert_array_equal(n, on)
+    np.testing.assert_array_equal(v, ov)
+    np.testing.assert_array_equal(f, of)
+    # second call: every order is resident now, the pipelined path completes on its own
+    v2, f2, n2 = ctx.edges_check(frm, to)
+    np.testing.assert_array_equal(f2, of)
+    ctx.close()
+
+
 def test_edge_check_dense_world_candidate_overflow(capi, orc, wl):
     """Many overlapping boxes around every edge: more than EC_MAXCAND candidates -> brute path."""
     d = 3
