@@ -238,6 +238,8 @@ def _plan(make, label, max_calls, max_solutions=3, time_cap=60.0):
                      "anytime_curve": [[round(t, 4), c] for t, c in costs],
                      "best_cost": costs[-1][1] if costs else None, "solutions": len(costs), "final_status": st,
                      "total_s": time.perf_counter() - t0, "counters": p.counters(),
+                     "phase_seconds": p.times() if hasattr(p, "times") else None,
+                     "gpu_launches": p.gpu_launches if hasattr(p, "gpu_launches") else None,
                      "path": [int(v) for v in p.path()]}
     if "cpu_oracle" in res:
         same_work = res["gpu"]["solutions"] == res["cpu_oracle"]["solutions"]
