@@ -488,7 +488,67 @@ void BatchingPOMP::expandVertex(Vertex u, double radius) {
       created.push_back(e);
     }
   }
-  computeFreeProbabilities(created);  // BP.cpp:166, batched: the belief model is read-only during a search
+  computeCreatedEdgeProbabilities(u, created);  // BP.cpp:166
+}
+
+// Free probabilities of the edges one expansion created.  The belief model is read-only during a
+// search, so probFree of an edge (source -> target) is the same whenever it is computed within that
+// search.  Each device call therefore also evaluates, speculatively, the edges that the vertices at
+// the head of the open list WOULD create when they are expanded (from the cached CSR rows), and keeps
+// those values for this search only.  Later expansions then find their values in the cache and need
+// no device call.  Values and the mNumLookups counter are taken only for edges that really get created,
+// so results equal the reference's one-estimate-per-edge sequence.
+void BatchingPOMP::computeCreatedEdgeProbabilities(Vertex u, const std::vector<Edge>& created) {
+  if (created.empty()) return;
+  if (mBeliefEmpty || !mCsrValid) {
+    computeFreeProbabilities(created);
+    return;
+  }
+  double t0 = now();
+  std::vector<Edge> miss;
+  for (Edge e : created) {
+    auto it = mSpecCache.find(((uint64_t)mEdges[e].source << 32) | mEdges[e].target);
+    if (it != mSpecCache.end()) {
+      mEdges[e].probFree = it->second.first;
+      mNumLookups += it->second.second;
+    } else {
+      miss.push_back(e);
+    }
+  }
+  if (!miss.empty()) {
+    std::vector<uint32_t> from, to;
+    for (Edge e : miss) {
+      from.push_back(mEdges[e].source);
+      to.push_back(mEdges[e].target);
+    }
+    const size_t nreal = from.size();
+    // speculative part: potential edges of the first vertices of the open list (smallest f first-ish)
+    const size_t kSpecVertices = 48, kSpecEdges = 4096;
+    size_t taken = 0;
+    for (size_t h = 0; h < mHeap.size() && taken < kSpecVertices && from.size() < nreal + kSpecEdges; ++h) {
+      Vertex v = mHeap[h];
+      if (v == u || mSpecStamp[v] == mEpoch || !mNNActive[v] || v + 1 >= mCsrRowPtr.size()) continue;
+      mSpecStamp[v] = mEpoch;
+      ++taken;
+      for (uint64_t k = mCsrRowPtr[v]; k < mCsrRowPtr[v + 1]; ++k) {
+        Vertex w2 = mCsrCol[k];
+        if (w2 == v || !mNNActive[w2] || hasEdge(v, w2)) continue;
+        from.push_back(v);
+        to.push_back(w2);
+      }
+    }
+    std::vector<uint32_t> nl(from.size());
+    std::vector<double> pf(from.size());
+    flushVertices();
+    check(bpomp_belief_edge_pfree_indexed(mCtx, from.data(), to.data(), (int64_t)from.size(), pf.data(), nl.data()));
+    for (size_t i = 0; i < nreal; ++i) {
+      mEdges[miss[i]].probFree = pf[i];
+      mNumLookups += nl[i];
+    }
+    for (size_t i = nreal; i < from.size(); ++i)
+      mSpecCache.emplace(((uint64_t)from[i] << 32) | to[i], std::make_pair(pf[i], nl[i]));
+  }
+  mLookupTime += now() - t0;
 }
 
 // throw_visitor::examine_edge (single batching) recomputes probFree of every examined edge, BP.cpp:108-111
@@ -745,9 +805,12 @@ bool BatchingPOMP::astar(bool zeroHeuristic, bool single) {
   }
   if (++mEpoch == 0) {  // stamp wrap-around
     std::fill(mStamp.begin(), mStamp.end(), 0);
+    std::fill(mSpecStamp.begin(), mSpecStamp.end(), 0);
     mEpoch = 1;
   }
   mHeap.clear();
+  mSpecCache.clear();  // speculative probFree values are valid for one search (one belief-model state)
+  if (mSpecStamp.size() < nv) mSpecStamp.resize(nv, 0);
   const double alpha = mCurrentAlpha;
   const double* goalState = vertexState(mGoalVertex);
   auto h = [&](Vertex u) -> double {

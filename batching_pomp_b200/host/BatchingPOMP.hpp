@@ -169,6 +169,7 @@ private:
   void expandVertex(Vertex u, double radius);
   void refreshOutEdgeProbabilities(Vertex u);
   void computeFreeProbabilities(const std::vector<Edge>& edges);
+  void computeCreatedEdgeProbabilities(Vertex u, const std::vector<Edge>& created);
   bool checkAndUpdatePathBlocked(const std::vector<Edge>& ePath);
   void updateAffectedEdgeWeights();
   std::vector<Edge> selectEdges(const std::vector<Edge>& ePath) const;
@@ -228,6 +229,9 @@ private:
   std::vector<double> mCsrDist;
   std::vector<std::pair<double, Vertex>> mRowScratch;
   uint64_t mCsrBudget;
+  // speculative probFree values for the current search: (source<<32 | target) -> (probFree, lookups)
+  std::unordered_map<uint64_t, std::pair<double, uint32_t>> mSpecCache;
+  std::vector<uint32_t> mSpecStamp;
 
   // ---- batching manager state ----
   unsigned int bmNumBatches;
