@@ -260,31 +260,44 @@ __global__ void __launch_bounds__(256) nb_query_kernel(QueryArgs a, GridView g) 
           const uint32_t first_cell = (uint32_t)(prefix * GL + c0[last]);
           const uint32_t last_cell = (uint32_t)(prefix * GL + c1[last]);
           uint32_t p0 = __ldg(g.cell_start + first_cell), p1 = __ldg(g.cell_start + last_cell + 1);
-          for (uint32_t pb = p0 + (uint32_t)s * 32u; pb < p1; pb += (uint32_t)a.S * 32u) {
-            uint32_t p = pb + lane;
-            bool hit = false;
-            double dist = 0.0;
-            uint32_t id = 0;
-            if (p < p1) {
-              double d2 = 0.0;
+          // U point groups per iteration: all coordinate loads are issued before the first use, so each
+          // lane has U*D independent loads in flight against the (L2-resident) point table
+          constexpr int U = D <= 3 ? 1 : 2;  // measured: 7-D rows 23.6 -> 15.4 ms with 2; no gain for 2-D rows
+          const uint32_t stride = (uint32_t)a.S * 32u;
+          for (uint32_t pb = p0 + (uint32_t)s * 32u; pb < p1; pb += U * stride) {
+            double c[U][D];
 #pragma unroll
-              for (int j = 0; j < D; ++j) {
-                double diff = __dsub_rn(q[j], __ldg(g.pts + (size_t)j * g.nactive + p));
-                d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
-              }
-              if (d2 <= a.r2pad) {  // cheap conservative prefilter, exact test below
-                dist = __dsqrt_rn(d2);
-                hit = dist <= a.r;  // inclusive, as GNAT nearestR
-                if (FILL && hit) id = __ldg(g.ids + p);
-              }
+            for (int u = 0; u < U; ++u) {
+              const uint32_t p = pb + u * stride + lane;
+#pragma unroll
+              for (int j = 0; j < D; ++j) c[u][j] = p < p1 ? __ldg(g.pts + (size_t)j * g.nactive + p) : 0.0;
             }
-            unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (FILL && hit) {
-              uint64_t o = base + cnt + __popc(m & ((1u << lane) - 1u));
-              a.out_dist[o] = dist;
-              a.out_id[o] = id;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (pb + u * stride >= p1) continue;  // warp-uniform
+              const uint32_t p = pb + u * stride + lane;
+              bool hit = false;
+              double dist = 0.0;
+              if (p < p1) {
+                double d2 = 0.0;
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                  double diff = __dsub_rn(q[j], c[u][j]);
+                  d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
+                }
+                if (d2 <= a.r2pad) {  // cheap conservative prefilter, exact test below
+                  dist = __dsqrt_rn(d2);
+                  hit = dist <= a.r;  // inclusive, as GNAT nearestR
+                }
+              }
+              unsigned m = __ballot_sync(0xffffffffu, hit);
+              if (FILL && hit) {
+                uint64_t o = base + cnt + __popc(m & ((1u << lane) - 1u));
+                a.out_dist[o] = dist;
+                a.out_id[o] = __ldg(g.ids + p);
+              }
+              cnt += __popc(m);
             }
-            cnt += __popc(m);
           }
         }
       }
