@@ -70,7 +70,7 @@ double SpaceInformation::getSpaceMeasure() const {
 BatchingPOMP::BatchingPOMP(const SpaceInformation& si)
     : mSi(si), mDim(si.dim), mCtx(nullptr), mCurrentAlpha(0.0), mIncrement(0.2), mStartGoalRadius(0.0),
       mPruneThreshold(1.05), mIsInitSearchBatch(true), mIsPathFound(false), mUsingSelector(false),
-      mBestPathCost(kInf), mSelType("normal"), mN(0), mFlushed(0), mStartVertex(0), mGoalVertex(0),
+      mBestPathCost(kInf), mSelType("normal"), mRoadmap(nullptr), mN(0), mFlushed(0), mStartVertex(0), mGoalVertex(0),
       mHaveProblem(false), mEpoch(0), mCsrValid(false), mCsrRadius(0.0), mCsrBudget(30000000ull), bmNumBatches(0),
       bmExhausted(false), bmCurrRadius(0.0), bmNumVerticesAdded(0), bmNextVertexTarget(0), bmVertInfl(2.0),
       bmRadiusInfl(1.0), bmInitRadius(0.0), bmMaxRadius(0.0), bmCurrVertex(0), bmEdgeMode(false), mNumSolutions(0),
@@ -137,9 +137,18 @@ std::string BatchingPOMP::getParam(const std::string& name) const {
 void BatchingPOMP::setRoadmap(const std::vector<double>& states,
                               const std::vector<std::pair<uint32_t, uint32_t>>& edges) {
   if (states.size() % mDim) throw Exception("roadmap states must be [n][dim]");
-  mRoadmap = states;
+  mRoadmapOwned = states;
+  mRoadmap = mRoadmapOwned.data();
   mRoadmapEdges = edges;
   mN = (uint32_t)(states.size() / mDim);
+  if (mRoadmapName.empty()) mRoadmapName = "<memory>";
+}
+
+void BatchingPOMP::setRoadmapView(const double* states, uint32_t n) {
+  mRoadmapOwned.clear();
+  mRoadmap = states;
+  mRoadmapEdges.clear();
+  mN = n;
   if (mRoadmapName.empty()) mRoadmapName = "<memory>";
 }
 
@@ -240,14 +249,15 @@ void BatchingPOMP::setup() {
       throw Exception("Invalid graph type specified! Graph type needed for hybrid or edge batching!");
   }
   if (mRoadmapName == "") throw Exception("Roadmap name must be set before creating batching manager!");
-  if (mRoadmap.empty() && mRoadmapName != "<memory>") {
+  if (mN == 0 && mRoadmapName != "<memory>") {
     // RoadmapFromFile::generateVertices (util/RoadmapFromFile.hpp:136-147)
     std::vector<double> states;
     std::vector<std::pair<uint32_t, uint32_t>> edges;
     util::readGraphml(mRoadmapName, mDim, states, edges);
-    mRoadmap.swap(states);
+    mRoadmapOwned.swap(states);
+    mRoadmap = mRoadmapOwned.data();
     mRoadmapEdges.swap(edges);
-    mN = (uint32_t)(mRoadmap.size() / mDim);
+    mN = (uint32_t)(mRoadmapOwned.size() / mDim);
   }
   if (mN == 0) throw Exception("Roadmap " + mRoadmapName + " has no vertices");
 

@@ -130,6 +130,9 @@ public:
   /// The roadmap may also be handed over in memory instead of through roadmap_filename
   /// (states [n][dim], optional edges for single batching).
   void setRoadmap(const std::vector<double>& states, const std::vector<std::pair<uint32_t, uint32_t>>& edges = {});
+  /// Non-owning variant: `states` ([n][dim]) must outlive the planner.  Lets many planner instances
+  /// (one per query, as in the reference) share one loaded roadmap.
+  void setRoadmapView(const double* states, uint32_t n);
 
   /// Solutions appended by solve() (pdef_->addSolutionPath, BP.cpp:1006): vertex ids and states.
   const std::vector<Vertex>& getSolutionVertices() const { return mSolutionVertices; }
@@ -192,7 +195,8 @@ private:
   std::string mSelType;
 
   // ---- roadmap file contents ----
-  std::vector<double> mRoadmap;
+  std::vector<double> mRoadmapOwned;
+  const double* mRoadmap;
   std::vector<std::pair<uint32_t, uint32_t>> mRoadmapEdges;
   uint32_t mN;
 

@@ -94,6 +94,10 @@ extern "C" int bpomp_planner_set_roadmap(bpomp_planner* p, const double* states,
   });
 }
 
+extern "C" int bpomp_planner_set_roadmap_view(bpomp_planner* p, const double* states, uint32_t n) {
+  return guarded(p, [&] { p->planner->setRoadmapView(states, n); });
+}
+
 extern "C" int bpomp_planner_setup(bpomp_planner* p) { return guarded(p, [&] { p->planner->setup(); }); }
 
 extern "C" int bpomp_planner_set_problem(bpomp_planner* p, const double* start, const double* goal) {

@@ -21,6 +21,7 @@ SIGNATURES = {
     "bpomp_planner_error": (C.c_char_p, [vp]),
     "bpomp_planner_set_param": (C.c_int, [vp, C.c_char_p, C.c_char_p]),
     "bpomp_planner_set_roadmap": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32]),
+    "bpomp_planner_set_roadmap_view": (C.c_int, [vp, vp, C.c_uint32]),
     "bpomp_planner_setup": (C.c_int, [vp]),
     "bpomp_planner_set_problem": (C.c_int, [vp, vp, vp]),
     "bpomp_planner_solve": (C.c_int, [vp, C.c_long, C.c_double, C.POINTER(C.c_int)]),
@@ -119,6 +120,12 @@ class Planner:
         else:
             e = np.ascontiguousarray(edges, dtype=np.uint32).reshape(-1, 2)
             self._ck(self.lib.bpomp_planner_set_roadmap(self.h, _p(s), s.shape[0], _p(e), e.shape[0]))
+
+    def set_roadmap_view(self, states):
+        """Non-owning: the (C-contiguous float64) array is kept alive by this object and not copied."""
+        assert states.dtype == np.float64 and states.flags["C_CONTIGUOUS"]
+        self._roadmap_ref = states
+        self._ck(self.lib.bpomp_planner_set_roadmap_view(self.h, _p(states), states.shape[0]))
 
     def setup(self):
         self._ck(self.lib.bpomp_planner_setup(self.h))

@@ -66,9 +66,12 @@ def main():
     mine = range(b[rank], b[rank + 1])
     t0 = time.perf_counter()
     out = []
+    t_create = 0.0
     for qi in mine:
+        c0 = time.perf_counter()
         p = Planner(d, boxes=(lo, hi), device=local)
-        p.set_roadmap(roadmap)
+        t_create += time.perf_counter() - c0
+        p.set_roadmap_view(roadmap)  # one loaded roadmap serves every planner instance of this rank
         p.set_param("batching_type", "vertex")
         q0 = time.perf_counter()
         found, cost, path = plan(p, cand[qi, 0], cand[qi, 1], a.solutions)
@@ -93,6 +96,8 @@ def main():
         dist.all_gather_object(gathered, (elapsed, out))
     else:
         gathered = [(elapsed, out)]
+    if rank == 0:
+        print("rank 0: %.3f s creating %d planner instances" % (t_create, len(out)), file=sys.stderr)
     if rank == 0:
         allq = [q for _, o in gathered for q in o]
         tmax = max(e for e, _ in gathered)

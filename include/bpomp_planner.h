@@ -41,6 +41,8 @@ BPOMP_PAPI const char* bpomp_planner_error(const bpomp_planner* p);
 BPOMP_PAPI int bpomp_planner_set_param(bpomp_planner* p, const char* name, const char* value);
 BPOMP_PAPI int bpomp_planner_set_roadmap(bpomp_planner* p, const double* states, uint32_t n, const uint32_t* edges,
                                          uint32_t nedges);
+/* Non-owning: `states` must outlive the planner (lets one loaded roadmap serve many planner instances). */
+BPOMP_PAPI int bpomp_planner_set_roadmap_view(bpomp_planner* p, const double* states, uint32_t n);
 BPOMP_PAPI int bpomp_planner_setup(bpomp_planner* p);
 BPOMP_PAPI int bpomp_planner_set_problem(bpomp_planner* p, const double* start, const double* goal);
 /* ptc: the planner termination condition becomes true after `max_iterations` evaluations
