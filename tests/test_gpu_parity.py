@@ -137,6 +137,45 @@ def test_edge_check_edge_cases(capi, orc, wl):
     ctx.close()
 
 
+def test_edge_check_too_many_states_is_a_range_error(capi, wl):
+    """nStates above BPOMP_NSTATES_MAX (65535): the call fails with BPOMP_ERR_RANGE instead of truncating."""
+    ctx = capi.Context(2, 1e-6)
+    ctx.set_world_boxes(np.array([[0.4, 0.4]]), np.array([[0.6, 0.6]]))
+    with pytest.raises(capi.BpompError) as ei:
+        ctx.edges_check(np.array([[0.0, 0.0]]), np.array([[1.0, 1.0]]))
+    assert ei.value.code == -4
+    # the context stays usable
+    v, f, n = ctx.edges_check(np.array([[0.0, 0.0]]), np.array([[0.01, 0.01]]))
+    assert n[0] == 14142 and v[0] == 1
+    with pytest.raises(capi.BpompError):
+        ctx.belief_edge_pfree(np.array([[0.0, 0.0]]), np.array([[1.0, 1.0]]))
+    ctx.close()
+
+
+def test_empty_and_degenerate_calls(capi, wl):
+    ctx = capi.Context(3, 0.01)
+    ctx.set_world_boxes(np.zeros((0, 3)), np.zeros((0, 3)))
+    assert ctx.states_valid(np.zeros((0, 3))).size == 0
+    assert ctx.belief_estimate(np.zeros((0, 3))).size == 0
+    pf, nl = ctx.belief_edge_pfree(np.zeros((0, 3)), np.zeros((0, 3)))
+    assert pf.size == 0
+    rp, col, dist = ctx.neighbors_radius(np.zeros(0, dtype=np.uint32), 0.1)
+    assert rp.tolist() == [0] and col.size == 0
+    assert ctx.neighbors_all(0.1, fetch=False) == 0
+    ctx.vertices_append(wl.halton(10, 3))
+    ctx.vertices_set_active(np.arange(10, dtype=np.uint32), 0)  # everything deactivated
+    rp, col, dist = ctx.neighbors_radius(np.array([3], dtype=np.uint32), 10.0)
+    assert rp.tolist() == [0, 0]
+    with pytest.raises(capi.BpompError):
+        ctx.neighbors_radius(np.array([10], dtype=np.uint32), 1.0)  # id out of range
+    ctx.belief_config(15, 0.5, 0.25)
+    ctx.belief_append(wl.halton(3, 3), np.array([1.0, 0.0, 1.0]))  # fewer points than k
+    import ctypes
+    got = ctx.belief_estimate(wl.halton(5, 3, first_index=20))
+    assert np.all((got > 0) & (got < 1))
+    ctx.close()
+
+
 def test_edge_check_no_world_is_an_error(capi):
     ctx = capi.Context(2, 0.01)
     with pytest.raises(capi.BpompError) as ei:
