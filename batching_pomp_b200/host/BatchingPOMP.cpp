@@ -174,6 +174,7 @@ BatchingPOMP::Edge BatchingPOMP::addEdge(Vertex u, Vertex v) {
   e.target = v;
   e.distance = 0.0;
   e.probFree = 0.0;
+  e.negLogProbFree = -std::log(0.0);
   e.blockedStatus = UNKNOWN;
   e.nStates = 0;
   e.removed = false;
@@ -484,6 +485,12 @@ const std::vector<std::pair<double, BatchingPOMP::Vertex>>& BatchingPOMP::neighb
 
 // neighbours_visitor::examine_vertex after the goal test — BP.cpp:149-168
 void BatchingPOMP::expandVertex(Vertex u, double radius) {
+  // Within one batch (same radius, no vertices added) a second expansion of u finds every neighbour
+  // already connected — by u's first expansion or by the neighbour's — so the row scan is skipped.
+  // Vertices pruned in between only lose edges and leave the rows.
+  if (mExpandedStamp.size() < mOut.size()) mExpandedStamp.resize(mOut.size(), 0);
+  if (mExpandedStamp[u] == bmNumBatches) return;
+  mExpandedStamp[u] = bmNumBatches;
   const auto& row = neighbourRow(u, radius);
   std::vector<Edge> created;
   for (const auto& pr : row) {
@@ -519,7 +526,7 @@ void BatchingPOMP::computeCreatedEdgeProbabilities(Vertex u, const std::vector<E
   for (Edge e : created) {
     auto it = mSpecCache.find(((uint64_t)mEdges[e].source << 32) | mEdges[e].target);
     if (it != mSpecCache.end()) {
-      mEdges[e].probFree = it->second.first;
+      setProbFree(mEdges[e], it->second.first);
       mNumLookups += it->second.second;
     } else {
       miss.push_back(e);
@@ -533,7 +540,10 @@ void BatchingPOMP::computeCreatedEdgeProbabilities(Vertex u, const std::vector<E
     }
     const size_t nreal = from.size();
     // speculative part: potential edges of the first vertices of the open list (smallest f first-ish)
-    const size_t kSpecVertices = 48, kSpecEdges = 4096;
+    // a device call costs about the same up to ~10^5 queries, so the speculative part grows with the
+    // open list (large frontiers = first search of a batch on a big roadmap)
+    const size_t kSpecVertices = std::min<size_t>(4096, std::max<size_t>(48, mHeap.size() / 8));
+    const size_t kSpecEdges = kSpecVertices * 24;
     size_t taken = 0;
     for (size_t h = 0; h < mHeap.size() && taken < kSpecVertices && from.size() < nreal + kSpecEdges; ++h) {
       Vertex v = mHeap[h];
@@ -552,7 +562,7 @@ void BatchingPOMP::computeCreatedEdgeProbabilities(Vertex u, const std::vector<E
     flushVertices();
     check(bpomp_belief_edge_pfree_indexed(mCtx, from.data(), to.data(), (int64_t)from.size(), pf.data(), nl.data()));
     for (size_t i = 0; i < nreal; ++i) {
-      mEdges[miss[i]].probFree = pf[i];
+      setProbFree(mEdges[miss[i]], pf[i]);
       mNumLookups += nl[i];
     }
     for (size_t i = nreal; i < from.size(); ++i)
@@ -567,6 +577,11 @@ void BatchingPOMP::refreshOutEdgeProbabilities(Vertex u) {
   es.reserve(mOut[u].size());
   for (const OutEdge& oe : mOut[u]) es.push_back(oe.eid);
   computeFreeProbabilities(es);
+}
+
+void BatchingPOMP::setProbFree(EProps& e, double p) {
+  e.probFree = p;
+  e.negLogProbFree = -std::log(p);
 }
 
 // computeAndSetEdgeFreeProbability for a set of edges — BP.cpp:464-493
@@ -584,7 +599,7 @@ void BatchingPOMP::computeFreeProbabilities(const std::vector<Edge>& edges) {
         mNumLookups++;
         result *= (1.0 - prior);
       }
-      mEdges[e].probFree = result;
+      setProbFree(mEdges[e], result);
     }
   } else {
     std::vector<uint32_t> from(edges.size()), to(edges.size()), nl(edges.size());
@@ -596,7 +611,7 @@ void BatchingPOMP::computeFreeProbabilities(const std::vector<Edge>& edges) {
     flushVertices();
     check(bpomp_belief_edge_pfree_indexed(mCtx, from.data(), to.data(), (int64_t)edges.size(), pf.data(), nl.data()));
     for (size_t i = 0; i < edges.size(); ++i) {
-      mEdges[edges[i]].probFree = pf[i];
+      setProbFree(mEdges[edges[i]], pf[i]);
       mNumLookups += nl[i];
     }
   }
@@ -663,13 +678,13 @@ bool BatchingPOMP::checkAndUpdatePathBlocked(const std::vector<Edge>& ePath) {
       mNumCollChecks += (unsigned int)first[i];  // one isValid per slot up to the invalid one, BP.cpp:516
       ep.blockedStatus = BLOCKED;                 // BP.cpp:529-531
       ep.distance = kInf;
-      ep.probFree = 0.0;
+      setProbFree(ep, 0.0);
       pathBlocked = true;
       if (mUsingSelector) break;  // BP.cpp:591-593
     } else {
       mNumCollChecks += ep.nStates - 2u;
       ep.blockedStatus = FREE;  // BP.cpp:541-542
-      ep.probFree = 1.0;
+      setProbFree(ep, 1.0);
     }
   }
   // belief inserts of the committed edges, in check order (BP.cpp:523-537), replayed on the device
@@ -705,7 +720,7 @@ double BatchingPOMP::edgeWeight(Edge e) const {
   if (ep.blockedStatus == BLOCKED) return kInf;
   double alpha = mCurrentAlpha;
   if (ep.blockedStatus == FREE) return alpha * ep.distance;
-  double w_m = -std::log(ep.probFree);
+  double w_m = ep.negLogProbFree;  // == -std::log(ep.probFree), cached when probFree is set
   double w_l = ep.distance;
   double exp_cost = alpha * w_l + (1 - alpha) * w_m;
   return exp_cost;

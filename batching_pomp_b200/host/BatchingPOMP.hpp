@@ -79,6 +79,7 @@ public:
     Vertex source, target;  // creation orientation = interpolation direction (BP.cpp:162-165, 437-438)
     double distance;
     double probFree;
+    double negLogProbFree;  // -log(probFree), kept beside it for the edge weight (BP.cpp:78)
     int blockedStatus;
     unsigned int nStates;
     bool removed;
@@ -171,6 +172,7 @@ private:
   void pruneVertices(bool withValidity);
   void expandVertex(Vertex u, double radius);
   void refreshOutEdgeProbabilities(Vertex u);
+  static void setProbFree(EProps& e, double p);
   void computeFreeProbabilities(const std::vector<Edge>& edges);
   void computeCreatedEdgeProbabilities(Vertex u, const std::vector<Edge>& created);
   bool checkAndUpdatePathBlocked(const std::vector<Edge>& ePath);
@@ -236,6 +238,7 @@ private:
   // speculative probFree values for the current search: (source<<32 | target) -> (probFree, lookups)
   std::unordered_map<uint64_t, std::pair<double, uint32_t>> mSpecCache;
   std::vector<uint32_t> mSpecStamp;
+  std::vector<uint32_t> mExpandedStamp;  // batch number in which the vertex was last expanded
 
   // ---- batching manager state ----
   unsigned int bmNumBatches;

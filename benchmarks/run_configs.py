@@ -11,6 +11,7 @@ Sections (each prints one JSON line and is also collected into --out):
   belief_knn             kNN collision-measure queries: M belief points, nq queries (k=15)
   planner_config1        time to first / best path, 2-D image, N=10^4, hybrid batching: GPU planner vs CPU oracle
   planner_config3        7-DoF boxes, vertex batching (bounded number of solve() calls): GPU planner vs CPU oracle
+  planner_full           configs 2 and 3 as planner runs on the full 10^6-vertex roadmaps (GPU planner only)
 Times are wall clock around synchronous C-ABI calls unless marked device (CUDA events)."""
 import argparse
 import json
@@ -289,7 +290,35 @@ def planner_config3(quick):
     _plan(make, "planner_config3", 400, max_solutions=(5 if quick else 9), time_cap=(30.0 if quick else 100.0))
 
 
-SECTIONS = {"config2": config2, "config3": config3, "belief": belief, "planner_config1": planner_config1,
+def planner_full_scale(quick):
+    """Configs 2 and 3 as planner runs at full roadmap size (GPU planner only: the brute-force CPU oracle
+    cannot expand vertices of a 10^6-vertex roadmap in reasonable time)."""
+    from batching_pomp_b200.planner import Planner
+    N = 10 ** 5 if quick else 10 ** 6
+    # config 2: 2-D image, edge batching, selector_type=normal
+    pix = workloads.image_world(4096, seed=2)
+    roadmap = workloads.halton(N, 2)
+
+    def make2():
+        gp = Planner(2, segment_fraction=1e-4, image=pix)
+        gp.set_roadmap_view(roadmap)
+        for k, v in (("batching_type", "edge"), ("graph_type", "halton"), ("selector_type", "normal")):
+            gp.set_param(k, v)
+        return gp, None, [0.1, 0.1], [0.9, 0.9], False
+    _plan(make2, "planner_config2_full", 400, max_solutions=4, time_cap=60.0)
+    # config 3: 7-DoF boxes, vertex batching
+    lo, hi = workloads.box_world(7, 500, seed=3)
+    roadmap7 = workloads.halton(N, 7)
+
+    def make3():
+        gp = Planner(7, boxes=(lo, hi))
+        gp.set_roadmap_view(roadmap7)
+        gp.set_param("batching_type", "vertex")
+        return gp, None, np.full(7, 0.1), np.full(7, 0.9), False
+    _plan(make3, "planner_config3_full", 400, max_solutions=6, time_cap=60.0)
+
+
+SECTIONS = {"planner_full": planner_full_scale, "config2": config2, "config3": config3, "belief": belief, "planner_config1": planner_config1,
             "planner_config3": planner_config3}
 
 if __name__ == "__main__":
