@@ -32,7 +32,9 @@ def _ctx_boxes(capi, wl, d, nboxes, seed, fraction=0.01):
 
 
 @pytest.mark.parametrize("d,nboxes,count", [(7, 500, 200000), (2, 40, 50000), (3, 100, 50000), (6, 300, 50000),
-                                            (8, 200, 30000), (1, 5, 5000), (7, 33, 20000), (7, 1, 20000)])
+                                            (8, 200, 30000), (1, 5, 5000), (7, 33, 20000), (7, 1, 20000),
+                                            # tables too large for shared memory -> global-memory path
+                                            (8, 500, 30000), (7, 1200, 30000), (4, 700, 30000)])
 def test_edge_check_boxes_parity(capi, orc, wl, d, nboxes, count):
     ctx, L, lo, hi = _ctx_boxes(capi, wl, d, nboxes, seed=3)
     frm, to = wl.random_edges(count, d, seed=4, max_len=wl.halton_radius(10 ** 6, 7))
