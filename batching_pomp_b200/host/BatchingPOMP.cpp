@@ -14,6 +14,9 @@
 #include <cmath>
 #include <cstring>
 
+#include <map>
+#include <mutex>
+
 #include "graphml.hpp"
 
 namespace batching_pomp {
@@ -41,6 +44,44 @@ inline double rvDistance(const double* a, const double* b, unsigned d) {
 }
 inline double now() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+// Device contexts are recycled between planner instances of one process: the reference is
+// one-planner-per-query, and creating a context (streams, tables, world upload) costs more than a
+// short query.  A context is only reused for the same device, dimension, segment length and world.
+struct CtxPool {
+  std::mutex mu;
+  std::map<std::string, std::vector<bpomp_ctx*>> idle;
+  // idle contexts are deliberately not destroyed at process exit: the CUDA runtime may already be
+  // unloading when static destructors run, and the driver reclaims the memory with the process
+};
+CtxPool& pool() {
+  static CtxPool p;
+  return p;
+}
+std::string ctxKey(const SpaceInformation& si, double L) {
+  uint64_t h = 1469598103934665603ull;  // FNV-1a over everything that defines the context
+  auto mix = [&](const void* data, size_t n) {
+    const unsigned char* b = static_cast<const unsigned char*>(data);
+    for (size_t i = 0; i < n; ++i) {
+      h ^= b[i];
+      h *= 1099511628211ull;
+    }
+  };
+  int w = (int)si.world;
+  mix(&si.device, sizeof(int));
+  mix(&si.dim, sizeof(unsigned));
+  mix(&L, sizeof(double));
+  mix(&w, sizeof(int));
+  if (!si.boxLo.empty()) mix(si.boxLo.data(), si.boxLo.size() * sizeof(double));
+  if (!si.boxHi.empty()) mix(si.boxHi.data(), si.boxHi.size() * sizeof(double));
+  if (!si.image.empty()) mix(si.image.data(), si.image.size());
+  mix(&si.imageWidth, sizeof(int));
+  mix(&si.imageHeight, sizeof(int));
+  mix(&si.imageThreshold, sizeof(int));
+  char buf[96];
+  snprintf(buf, sizeof(buf), "%d/%u/%016llx/%zu/%zu", si.device, si.dim, (unsigned long long)h, si.boxLo.size(),
+           si.image.size());
+  return buf;
 }
 }  // namespace
 
@@ -70,7 +111,7 @@ double SpaceInformation::getSpaceMeasure() const {
 BatchingPOMP::BatchingPOMP(const SpaceInformation& si)
     : mSi(si), mDim(si.dim), mCtx(nullptr), mCurrentAlpha(0.0), mIncrement(0.2), mStartGoalRadius(0.0),
       mPruneThreshold(1.05), mIsInitSearchBatch(true), mIsPathFound(false), mUsingSelector(false),
-      mBestPathCost(kInf), mSelType("normal"), mRoadmap(nullptr), mN(0), mFlushed(0), mStartVertex(0), mGoalVertex(0),
+      mBestPathCost(kInf), mSelType("normal"), mLaunchBase(0), mRoadmap(nullptr), mN(0), mFlushed(0), mStartVertex(0), mGoalVertex(0),
       mHaveProblem(false), mEpoch(0), mCsrValid(false), mCsrRadius(0.0), mCsrBudget(30000000ull), bmNumBatches(0),
       bmExhausted(false), bmCurrRadius(0.0), bmNumVerticesAdded(0), bmNextVertexTarget(0), bmVertInfl(2.0),
       bmRadiusInfl(1.0), bmInitRadius(0.0), bmMaxRadius(0.0), bmCurrVertex(0), bmEdgeMode(false), mNumSolutions(0),
@@ -83,17 +124,31 @@ BatchingPOMP::BatchingPOMP(const SpaceInformation& si)
   mL = si.getLongestValidSegmentLength();
   mMaxExtent = si.getMaximumExtent();
   mSpaceMeasure = si.getSpaceMeasure();
+  if (si.world == SpaceInformation::World::NONE)
+    throw Exception("the StateValidityChecker must be described as a device world (boxes or image); "
+                    "there is no CPU fallback");
+  mCtxKey = ctxKey(si, mL);
+  {
+    std::lock_guard<std::mutex> lk(pool().mu);
+    auto it = pool().idle.find(mCtxKey);
+    if (it != pool().idle.end() && !it->second.empty()) {
+      mCtx = it->second.back();
+      it->second.pop_back();
+    }
+  }
+  if (mCtx) {  // recycled: same device / dim / L / world, emptied when it was returned
+    mLaunchBase = bpomp_launch_count(mCtx);
+    check(bpomp_belief_config(mCtx, 15, 0.5, 0.25));
+    return;
+  }
   int rc = bpomp_create(si.device, (int)mDim, mL, &mCtx);
   if (rc != BPOMP_OK) throw Exception(std::string("bpomp_create: ") + bpomp_last_error(nullptr));
   try {
     if (si.world == SpaceInformation::World::BOXES) {
       int nb = (int)(si.boxLo.size() / mDim);
       check(bpomp_world_set_boxes(mCtx, si.boxLo.data(), si.boxHi.data(), nb));
-    } else if (si.world == SpaceInformation::World::IMAGE) {
-      check(bpomp_world_set_image(mCtx, si.image.data(), si.imageWidth, si.imageHeight, si.imageThreshold));
     } else {
-      throw Exception("the StateValidityChecker must be described as a device world (boxes or image); "
-                      "there is no CPU fallback");
+      check(bpomp_world_set_image(mCtx, si.image.data(), si.imageWidth, si.imageHeight, si.imageThreshold));
     }
     // default belief model: KNNModel(15, 0.5, 0.25, ...) (BP.cpp:300)
     check(bpomp_belief_config(mCtx, 15, 0.5, 0.25));
@@ -105,7 +160,17 @@ BatchingPOMP::BatchingPOMP(const SpaceInformation& si)
 }
 
 BatchingPOMP::~BatchingPOMP() {
-  if (mCtx) bpomp_destroy(mCtx);
+  if (!mCtx) return;
+  // hand the emptied context back for the next planner instance (at most 4 idle per configuration)
+  if (bpomp_vertices_clear(mCtx) == BPOMP_OK && bpomp_belief_clear(mCtx) == BPOMP_OK && bpomp_sync(mCtx) == BPOMP_OK) {
+    std::lock_guard<std::mutex> lk(pool().mu);
+    std::vector<bpomp_ctx*>& v = pool().idle[mCtxKey];
+    if (v.size() < 4) {
+      v.push_back(mCtx);
+      return;
+    }
+  }
+  bpomp_destroy(mCtx);
 }
 
 void BatchingPOMP::check(int rc) const {

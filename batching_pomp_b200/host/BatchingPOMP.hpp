@@ -150,6 +150,8 @@ public:
   size_t numEdges() const { return mEdges.size(); }
   const double* vertexState(Vertex v) const { return &mVState[(size_t)v * mDim]; }
   bpomp_ctx* context() const { return mCtx; }
+  /// Kernel launches issued on behalf of this planner instance.
+  uint64_t gpuLaunches() const { return bpomp_launch_count(mCtx) - mLaunchBase; }
 
 private:
   struct OutEdge { Vertex target; Edge eid; };
@@ -188,6 +190,7 @@ private:
   unsigned int mDim;
   double mL, mMaxExtent, mSpaceMeasure;
   bpomp_ctx* mCtx;
+  std::string mCtxKey;  // device contexts are recycled between planner instances (BatchingPOMP.cpp, CtxPool)
 
   // ---- parameters ----
   std::string mRoadmapName, mGraphType, mBatchingType, mSelectorType;
@@ -195,6 +198,7 @@ private:
   bool mIsInitSearchBatch, mIsPathFound, mUsingSelector;
   double mBestPathCost;
   std::string mSelType;
+  uint64_t mLaunchBase;
 
   // ---- roadmap file contents ----
   std::vector<double> mRoadmapOwned;

@@ -160,7 +160,7 @@ extern "C" void bpomp_planner_counters(const bpomp_planner* p, uint32_t* out4, d
 extern "C" uint64_t bpomp_planner_num_vertices(const bpomp_planner* p) { return p->planner->numVertices(); }
 extern "C" uint64_t bpomp_planner_num_edges(const bpomp_planner* p) { return p->planner->numEdges(); }
 extern "C" uint64_t bpomp_planner_gpu_launches(const bpomp_planner* p) {
-  return bpomp_launch_count(p->planner->context());
+  return p->planner->gpuLaunches();
 }
 
 extern "C" int bpomp_graphml_write(const char* filename, int dim, const double* states, uint32_t n,
