@@ -196,10 +196,12 @@ class Context:
         self._ck(self.lib.bpomp_neighbors_fetch(self.h, _ptr(row_ptr), _ptr(col), _ptr(dist)))
         return row_ptr, col[:nnz], dist[:nnz]
 
-    def neighbors_radius(self, query_ids, r):
+    def neighbors_radius(self, query_ids, r, fetch=True):
         q = _u32(query_ids)
         nnz = C.c_uint64(0)
         self._ck(self.lib.bpomp_neighbors_radius(self.h, _ptr(q), q.size, float(r), C.byref(nnz)))
+        if not fetch:  # the CSR stays on the device (bpomp_neighbors_device / a later fetch)
+            return int(nnz.value)
         return self._fetch(q.size, int(nnz.value))
 
     def neighbors_all(self, r, fetch=True):

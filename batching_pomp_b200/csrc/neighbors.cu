@@ -17,6 +17,9 @@
 #include "common.cuh"
 
 #define NB_MAXG 3
+#ifndef NB_U
+#define NB_U(D) ((D) <= 3 ? 1 : 2)  // point groups in flight per lane
+#endif
 
 struct GridView {
   int gd;                      // gridded dimensions (<= NB_MAXG)
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(256) nb_query_kernel(QueryArgs a, GridView g) 
           uint32_t p0 = __ldg(g.cell_start + first_cell), p1 = __ldg(g.cell_start + last_cell + 1);
           // U point groups per iteration: all coordinate loads are issued before the first use, so each
           // lane has U*D independent loads in flight against the (L2-resident) point table
-          constexpr int U = D <= 3 ? 1 : 2;  // measured: 7-D rows 23.6 -> 15.4 ms with 2; no gain for 2-D rows
+          constexpr int U = NB_U(D);  // measured: 7-D rows 23.6 -> 15.4 ms with 2; no gain for 2-D rows
           const uint32_t stride = (uint32_t)a.S * 32u;
           for (uint32_t pb = p0 + (uint32_t)s * 32u; pb < p1; pb += U * stride) {
             double c[U][D];
