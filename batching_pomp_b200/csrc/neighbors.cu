@@ -309,6 +309,71 @@ __global__ void __launch_bounds__(256) nb_query_kernel(QueryArgs a, GridView g) 
   }
 }
 
+// Brute-force regime (the grid has a handful of cells because r is of the order of the domain, e.g.
+// 7-D roadmaps or vertex batching's unbounded radius): every query meets most points, so the scan is
+// organised as tiled all-pairs instead — thread = query, a block of NB_TQ queries walks its chunk of the
+// cell-ordered point table in tiles staged through shared memory (coalesced tile loads, broadcast reads),
+// exactly like the belief kNN kernel.  Slice index = point chunk, so counts / offsets / fill keep the
+// (query, slice) layout of the warp kernel and the rest of the pipeline is unchanged.
+#define NB_TQ 128
+#define NB_TP 128
+template <int D, bool FILL>
+__global__ void __launch_bounds__(NB_TQ) nb_tile_kernel(QueryArgs a, GridView g, uint32_t chunk) {
+  __shared__ double s_pts[D][NB_TP];
+  __shared__ uint32_t s_ids[NB_TP];
+  const int tid = threadIdx.x;
+  const uint32_t qi = blockIdx.x * NB_TQ + tid;
+  const uint32_t c = blockIdx.y;
+  const uint32_t p_begin = c * chunk;
+  const uint32_t p_end = min(p_begin + chunk, g.nactive);
+  const bool have = qi < a.nq;
+  const uint32_t qid = have ? (a.query ? __ldg(a.query + qi) : qi) : 0u;
+  const bool skip = !have || (a.skip_inactive_query && !a.active[qid]);
+  double q[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) q[j] = have ? __ldg(a.verts + (size_t)qid * D + j) : 0.0;
+  const uint64_t w = (uint64_t)qi * a.S + c;
+  uint64_t o = (FILL && have) ? a.offs[w] : 0;
+  uint32_t cnt = 0;
+  for (uint32_t base = p_begin; base < p_end; base += NB_TP) {
+    const uint32_t tn = min((uint32_t)NB_TP, p_end - base);
+    __syncthreads();
+    if ((uint32_t)tid < tn) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) s_pts[j][tid] = __ldg(g.pts + (size_t)j * g.nactive + base + tid);
+      if (FILL) s_ids[tid] = __ldg(g.ids + base + tid);
+    }
+    __syncthreads();
+    if (skip) continue;
+    for (uint32_t t = 0; t < tn; ++t) {
+      // fused prefilter (2 FP64 operations per dimension instead of 3); survivors are recomputed with
+      // the reference's unfused arithmetic
+      double dq = 0.0;
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        const double diff = __dsub_rn(q[j], s_pts[j][t]);
+        dq = __fma_rn(diff, diff, dq);
+      }
+      if (dq > a.r2pad) continue;
+      double d2 = 0.0;
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        const double diff = __dsub_rn(q[j], s_pts[j][t]);
+        d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
+      }
+      const double dist = __dsqrt_rn(d2);
+      if (dist <= a.r) {  // inclusive, as GNAT nearestR
+        if (FILL) {
+          a.out_dist[o + cnt] = dist;
+          a.out_id[o + cnt] = s_ids[t];
+        }
+        ++cnt;
+      }
+    }
+  }
+  if (!FILL && have) a.counts[w] = cnt;
+}
+
 // row_ptr[q] = offs[q*S]
 __global__ void nb_rowptr_kernel(const uint64_t* __restrict__ offs, uint32_t nq, int S, uint64_t* __restrict__ row_ptr,
                                  unsigned long long* __restrict__ maxrow) {
@@ -492,9 +557,19 @@ template <int D>
 static int neighbors_impl(bpomp_ctx* ctx, const uint32_t* d_query, uint32_t nq, double r, bool all, uint64_t* nnz_out) {
   GridView g;
   BP_TRY(build_grid<D>(ctx, r, g));
+  // Brute-force regime with enough queries to fill thread-per-query blocks -> tiled all-pairs kernel
+  const bool tiled = g.ncells <= 8 && nq >= 4 * NB_TQ && g.nactive >= 4 * NB_TP;
   // slices per query: enough warps to fill the machine when there are few queries
   int S = 1;
-  {
+  uint32_t chunk = 0;
+  if (tiled) {
+    uint64_t qblocks = ((uint64_t)nq + NB_TQ - 1) / NB_TQ;
+    uint64_t want = (uint64_t)ctx->num_sms * 8;  // resident blocks
+    while (qblocks * S < want && (uint64_t)g.nactive / (2 * S) >= 8 * NB_TP) S *= 2;
+    chunk = (uint32_t)(((uint64_t)g.nactive + S - 1) / S);
+    chunk = (chunk + NB_TP - 1) / NB_TP * NB_TP;
+    S = (int)(((uint64_t)g.nactive + chunk - 1) / chunk);
+  } else {
     uint64_t want = (uint64_t)ctx->num_sms * 64;  // resident warps
     while ((uint64_t)nq * S < want && S < 1024 && (uint64_t)S * 32 * 4 < (uint64_t)g.nactive + 1) S *= 2;
   }
@@ -507,7 +582,7 @@ static int neighbors_impl(bpomp_ctx* ctx, const uint32_t* d_query, uint32_t nq, 
   a.nq = nq;
   a.S = S;
   a.r = r;
-  a.r2pad = (r * r) * (1.0 + 8.881784197001252e-16);  // 2^-50
+  a.r2pad = (r * r) * (1.0 + 9.094947017729282e-13);  // 2^-40: covers the sqrt rounding and the fused prefilter
   if (!(a.r2pad >= 0.0)) a.r2pad = DBL_MAX;           // NaN guard
   if (std::isinf(a.r2pad)) a.r2pad = DBL_MAX;
   a.skip_inactive_query = all ? 1 : 0;
@@ -516,7 +591,9 @@ static int neighbors_impl(bpomp_ctx* ctx, const uint32_t* d_query, uint32_t nq, 
   a.counts = ctx->s_f.as<uint32_t>();
   int grid = (int)std::min<uint64_t>((nw * 32 + 255) / 256, (uint64_t)ctx->num_sms * 8);
   if (grid < 1) grid = 1;
-  nb_query_kernel<D, false><<<grid, 256, 0, ctx->stream>>>(a, g);
+  const dim3 tgrid((unsigned)(((uint64_t)nq + NB_TQ - 1) / NB_TQ), (unsigned)S);
+  if (tiled) nb_tile_kernel<D, false><<<tgrid, NB_TQ, 0, ctx->stream>>>(a, g, chunk);
+  else nb_query_kernel<D, false><<<grid, 256, 0, ctx->stream>>>(a, g);
   ctx->launches++;
   BP_CUDA(ctx, cudaGetLastError());
   uint64_t* offs = ctx->s_g.as<uint64_t>();
@@ -542,7 +619,8 @@ static int neighbors_impl(bpomp_ctx* ctx, const uint32_t* d_query, uint32_t nq, 
   a.out_dist = ctx->d_nb_tmp.as<double>();
   a.out_id = ctx->s_f.as<uint32_t>();
   if (nnz > 0) {
-    nb_query_kernel<D, true><<<grid, 256, 0, ctx->stream>>>(a, g);
+    if (tiled) nb_tile_kernel<D, true><<<tgrid, NB_TQ, 0, ctx->stream>>>(a, g, chunk);
+    else nb_query_kernel<D, true><<<grid, 256, 0, ctx->stream>>>(a, g);
     ctx->launches++;
     BP_CUDA(ctx, cudaGetLastError());
     const uint64_t* rp = ctx->d_nb_rowptr.as<uint64_t>();
