@@ -524,6 +524,15 @@ void BatchingPOMP::prepareNeighbourCache(double radius) {
   check(bpomp_neighbors_fetch(mCtx, mCsrRowPtr.data(), mCsrCol.data(), mCsrDist.data()));
   mCsrValid = true;
   mCsrRadius = radius;
+  // the CSR bounds what this batch can create: size the host graph once instead of growing it edge by edge
+  const size_t maxNew = (size_t)(nnz / 2 + 1);
+  mEdges.reserve(mEdges.size() + maxNew);
+  mEdgeMarked.reserve(mEdgeMarked.size() + maxNew);
+  mEdgeIndex.reserve(mEdgeIndex.size() + maxNew);
+  for (uint32_t v = 0; v < nv; ++v) {
+    size_t len = (size_t)(mCsrRowPtr[v + 1] - mCsrRowPtr[v]);
+    if (len > mOut[v].capacity()) mOut[v].reserve(len);
+  }
 }
 
 const std::vector<std::pair<double, BatchingPOMP::Vertex>>& BatchingPOMP::neighbourRow(Vertex u, double radius) {
