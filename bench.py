@@ -66,7 +66,12 @@ def config_dict(edges, n_gpus, extra=None):
 # --------------------------------------------------------------------------------------------
 def cpu_baseline_run(L, lo, hi, frm, to, target_s=12.0, steps=1, warmup=0):
     from oracle import oracle
-    cores = oracle.max_threads()
+    # all host cores this process may use; torchrun exports OMP_NUM_THREADS=1, which must not throttle the
+    # CPU arm, so the thread count is passed explicitly (OpenMP num_threads clause) instead of read from it
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
     probe = min(20000, frm.shape[0])
     t0 = time.perf_counter()
     oracle.edges_check_boxes(frm[:probe], to[:probe], L, lo, hi, nthreads=cores)
