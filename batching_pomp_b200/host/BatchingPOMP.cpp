@@ -23,6 +23,7 @@ namespace batching_pomp {
 
 namespace {
 const double kInf = std::numeric_limits<double>::max();
+const uint32_t kNoEdge = 0xFFFFFFFFu;
 
 inline double closedPlus(double a, double b) {  // boost::closed_plus<double>(DBL_MAX), BP.cpp:893
   if (a == kInf) return kInf;
@@ -112,7 +113,7 @@ BatchingPOMP::BatchingPOMP(const SpaceInformation& si)
     : mSi(si), mDim(si.dim), mCtx(nullptr), mCurrentAlpha(0.0), mIncrement(0.2), mStartGoalRadius(0.0),
       mPruneThreshold(1.05), mIsInitSearchBatch(true), mIsPathFound(false), mUsingSelector(false),
       mBestPathCost(kInf), mSelType("normal"), mLaunchBase(0), mRoadmap(nullptr), mN(0), mFlushed(0), mStartVertex(0), mGoalVertex(0),
-      mHaveProblem(false), mEpoch(0), mCsrValid(false), mCsrRadius(0.0), mCsrBudget(30000000ull), bmNumBatches(0),
+      mHaveProblem(false), mHashedUpTo(0), mEpoch(0), mCsrValid(false), mCsrRadius(0.0), mCsrOlderEdges(false), mCsrBudget(30000000ull), bmNumBatches(0),
       bmExhausted(false), bmCurrRadius(0.0), bmNumVerticesAdded(0), bmNextVertexTarget(0), bmVertInfl(2.0),
       bmRadiusInfl(1.0), bmInitRadius(0.0), bmMaxRadius(0.0), bmCurrVertex(0), bmEdgeMode(false), mNumSolutions(0),
       mBeliefEmpty(true), mNumEdgeChecks(0), mNumCollChecks(0), mNumSearches(0), mNumLookups(0), mLookupTime(0.0),
@@ -233,7 +234,7 @@ BatchingPOMP::Vertex BatchingPOMP::addVertex(const double* state, bool inNN) {
   return (Vertex)mOut.size() - 1;
 }
 
-BatchingPOMP::Edge BatchingPOMP::addEdge(Vertex u, Vertex v) {
+BatchingPOMP::Edge BatchingPOMP::addEdge(Vertex u, Vertex v, bool index) {
   EProps e;
   e.source = u;
   e.target = v;
@@ -247,24 +248,41 @@ BatchingPOMP::Edge BatchingPOMP::addEdge(Vertex u, Vertex v) {
   Edge id = (Edge)mEdges.size() - 1;
   mOut[u].push_back({v, id});
   mOut[v].push_back({u, id});
-  mEdgeIndex.emplace(edgeKey(u, v), id);  // first edge wins, as boost::edge's scan returns the first
+  // The pair index is only maintained while rows are fetched on demand; with a cached CSR the edge
+  // ids live in the CSR slots (mCsrEdge) and the hash is brought up to date when it is needed again.
+  if (index && mHashedUpTo == id) {
+    mEdgeIndex.emplace(edgeKey(u, v), id);  // first edge wins, as boost::edge's scan returns the first
+    mHashedUpTo = id + 1;
+  }
   mEdgeMarked.push_back(0);
   return id;
 }
 
-bool BatchingPOMP::hasEdge(Vertex u, Vertex v) const { return mEdgeIndex.find(edgeKey(u, v)) != mEdgeIndex.end(); }
+void BatchingPOMP::completeEdgeIndex() {
+  for (Edge e = mHashedUpTo; e < mEdges.size(); ++e)
+    if (!mEdges[e].removed) mEdgeIndex.emplace(edgeKey(mEdges[e].source, mEdges[e].target), e);
+  mHashedUpTo = (Edge)mEdges.size();
+}
 
+bool BatchingPOMP::hasEdge(Vertex u, Vertex v) {
+  if (mHashedUpTo != mEdges.size()) completeEdgeIndex();
+  return mEdgeIndex.find(edgeKey(u, v)) != nullptr;
+}
+
+// boost::edge(u, v, g): the first out-edge of u whose target is v (BP.cpp:960)
 BatchingPOMP::Edge BatchingPOMP::findEdge(Vertex u, Vertex v) const {
-  auto it = mEdgeIndex.find(edgeKey(u, v));
-  if (it == mEdgeIndex.end()) return (Edge)-1;
-  return it->second;
+  for (const OutEdge& oe : mOut[u])
+    if (oe.target == v) return oe.eid;
+  return (Edge)-1;
 }
 
 void BatchingPOMP::clearVertex(Vertex v) {  // boost::clear_vertex, BatchingManager.hpp:163
   for (const OutEdge& oe : mOut[v]) {
     mEdges[oe.eid].removed = true;
-    auto it = mEdgeIndex.find(edgeKey(v, oe.target));
-    if (it != mEdgeIndex.end() && it->second == oe.eid) mEdgeIndex.erase(it);
+    if (oe.eid < mHashedUpTo) {
+      const Edge* it = mEdgeIndex.find(edgeKey(v, oe.target));
+      if (it && *it == oe.eid) mEdgeIndex.erase(edgeKey(v, oe.target));
+    }
     if (oe.target == v) continue;
     std::vector<OutEdge>& o = mOut[oe.target];
     o.erase(std::remove_if(o.begin(), o.end(), [&](const OutEdge& x) { return x.eid == oe.eid; }), o.end());
@@ -524,11 +542,12 @@ void BatchingPOMP::prepareNeighbourCache(double radius) {
   check(bpomp_neighbors_fetch(mCtx, mCsrRowPtr.data(), mCsrCol.data(), mCsrDist.data()));
   mCsrValid = true;
   mCsrRadius = radius;
+  mCsrEdge.assign(nnz ? nnz : 1, kNoEdge);
+  mCsrOlderEdges = !mEdges.empty();
   // the CSR bounds what this batch can create: size the host graph once instead of growing it edge by edge
   const size_t maxNew = (size_t)(nnz / 2 + 1);
   mEdges.reserve(mEdges.size() + maxNew);
   mEdgeMarked.reserve(mEdgeMarked.size() + maxNew);
-  mEdgeIndex.reserve(mEdgeIndex.size() + maxNew);
   for (uint32_t v = 0; v < nv; ++v) {
     size_t len = (size_t)(mCsrRowPtr[v + 1] - mCsrRowPtr[v]);
     if (len > mOut[v].capacity()) mOut[v].reserve(len);
@@ -565,18 +584,38 @@ void BatchingPOMP::expandVertex(Vertex u, double radius) {
   if (mExpandedStamp.size() < mOut.size()) mExpandedStamp.resize(mOut.size(), 0);
   if (mExpandedStamp[u] == bmNumBatches) return;
   mExpandedStamp[u] = bmNumBatches;
-  const auto& row = neighbourRow(u, radius);
   std::vector<Edge> created;
-  for (const auto& pr : row) {
-    Vertex nbr = pr.second;
-    if (nbr == u) continue;
-    if (!hasEdge(u, nbr)) {
-      Edge e = addEdge(u, nbr);
-      mEdges[e].distance = pr.first;  // bit-equal to vertexDistFun(source, target)
-      mEdges[e].blockedStatus = UNKNOWN;
-      unsigned int n = static_cast<unsigned int>(std::floor(pr.first / mL));  // BP.cpp:440-445
-      mEdges[e].nStates = n < 2u ? 2u : n;
-      created.push_back(e);
+  auto create = [&](Vertex nbr, double dist, bool index) -> Edge {
+    Edge e = addEdge(u, nbr, index);
+    mEdges[e].distance = dist;  // bit-equal to vertexDistFun(source, target)
+    mEdges[e].blockedStatus = UNKNOWN;
+    unsigned int n = static_cast<unsigned int>(std::floor(dist / mL));  // BP.cpp:440-445
+    mEdges[e].nStates = n < 2u ? 2u : n;
+    created.push_back(e);
+    return e;
+  };
+  if (mCsrValid && radius == mCsrRadius && (size_t)u + 1 < mCsrRowPtr.size() && mNNActive[u]) {
+    // Cached CSR: the edge id of every (u, neighbour) pair lives in the CSR slot itself, so the existence
+    // test is a sequential read instead of a hash probe; the mirror slot (neighbour's row) is set too.
+    for (uint64_t k = mCsrRowPtr[u]; k < mCsrRowPtr[u + 1]; ++k) {
+      const Vertex nbr = mCsrCol[k];
+      if (nbr == u || !mNNActive[nbr]) continue;  // pruned since the CSR was built
+      if (mCsrEdge[k] != kNoEdge) continue;
+      Edge e = mCsrOlderEdges ? findEdge(u, nbr) : kNoEdge;  // created before this CSR existed?
+      if (e == kNoEdge) e = create(nbr, mCsrDist[k], false);
+      mCsrEdge[k] = e;
+      for (uint64_t k2 = mCsrRowPtr[nbr]; k2 < mCsrRowPtr[nbr + 1]; ++k2)
+        if (mCsrCol[k2] == u) {
+          mCsrEdge[k2] = e;
+          break;
+        }
+    }
+  } else {
+    const auto& row = neighbourRow(u, radius);
+    for (const auto& pr : row) {
+      Vertex nbr = pr.second;
+      if (nbr == u) continue;
+      if (!hasEdge(u, nbr)) create(nbr, pr.first, true);
     }
   }
   computeCreatedEdgeProbabilities(u, created);  // BP.cpp:166
@@ -598,10 +637,10 @@ void BatchingPOMP::computeCreatedEdgeProbabilities(Vertex u, const std::vector<E
   double t0 = now();
   std::vector<Edge> miss;
   for (Edge e : created) {
-    auto it = mSpecCache.find(((uint64_t)mEdges[e].source << 32) | mEdges[e].target);
-    if (it != mSpecCache.end()) {
-      setProbFree(mEdges[e], it->second.first);
-      mNumLookups += it->second.second;
+    const std::pair<double, uint32_t>* it = mSpecCache.find(((uint64_t)mEdges[e].source << 32) | mEdges[e].target);
+    if (it) {
+      setProbFree(mEdges[e], it->first);
+      mNumLookups += it->second;
     } else {
       miss.push_back(e);
     }
@@ -626,7 +665,14 @@ void BatchingPOMP::computeCreatedEdgeProbabilities(Vertex u, const std::vector<E
       ++taken;
       for (uint64_t k = mCsrRowPtr[v]; k < mCsrRowPtr[v + 1]; ++k) {
         Vertex w2 = mCsrCol[k];
-        if (w2 == v || !mNNActive[w2] || hasEdge(v, w2)) continue;
+        if (w2 == v || !mNNActive[w2] || mCsrEdge[k] != kNoEdge) continue;
+        if (mCsrOlderEdges) {  // an edge from an earlier batch: remember it in the slot, nothing to evaluate
+          Edge old = findEdge(v, w2);
+          if (old != kNoEdge) {
+            mCsrEdge[k] = old;
+            continue;
+          }
+        }
         from.push_back(v);
         to.push_back(w2);
       }

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "bpomp_cuda.h"
+#include "flat_map.hpp"
 
 namespace batching_pomp {
 
@@ -158,8 +159,9 @@ private:
 
   // ---- graph (adjacency_list<vecS,vecS,undirectedS> semantics, flat storage) ----
   Vertex addVertex(const double* state, bool inNN);
-  Edge addEdge(Vertex u, Vertex v);
-  bool hasEdge(Vertex u, Vertex v) const;
+  Edge addEdge(Vertex u, Vertex v, bool index = true);
+  bool hasEdge(Vertex u, Vertex v);
+  void completeEdgeIndex();
   Edge findEdge(Vertex u, Vertex v) const;
   void clearVertex(Vertex v);
 
@@ -211,11 +213,12 @@ private:
   std::vector<std::vector<OutEdge>> mOut;
   std::vector<EProps> mEdges;
   std::vector<uint8_t> mNNActive;              // membership in mVertexNN
-  std::unordered_map<uint64_t, Edge> mEdgeIndex;  // (min,max) -> edge id, replaces boost::edge's linear scan
+  util::FlatMap64<Edge> mEdgeIndex;  // (min,max) -> edge id, replaces boost::edge's linear scan
   uint32_t mFlushed;                           // vertices already resident in the device table
   std::vector<uint32_t> mPendingDeactivate;
   Vertex mStartVertex, mGoalVertex;
   bool mHaveProblem;
+  Edge mHashedUpTo;                            // edges [0, mHashedUpTo) are in mEdgeIndex
 
   // ---- search state: flat arrays + epoch stamps instead of four std::map (BP.cpp:860-863) ----
   std::vector<double> mDist, mCost;
@@ -237,10 +240,12 @@ private:
   std::vector<uint64_t> mCsrRowPtr;
   std::vector<uint32_t> mCsrCol;
   std::vector<double> mCsrDist;
+  std::vector<Edge> mCsrEdge;                  // edge id per CSR slot (kNoEdge: not created / not looked up yet)
+  bool mCsrOlderEdges;                         // edges existed before this CSR was built
   std::vector<std::pair<double, Vertex>> mRowScratch;
   uint64_t mCsrBudget;
   // speculative probFree values for the current search: (source<<32 | target) -> (probFree, lookups)
-  std::unordered_map<uint64_t, std::pair<double, uint32_t>> mSpecCache;
+  util::FlatMap64<std::pair<double, uint32_t>> mSpecCache;
   std::vector<uint32_t> mSpecStamp;
   std::vector<uint32_t> mExpandedStamp;  // batch number in which the vertex was last expanded
 

@@ -80,3 +80,13 @@ def test_planner_needs_gpu(planner_mod):
     with pytest.raises(planner_mod.PlannerError) as ei:
         planner_mod.Planner(2, boxes=(np.zeros((1, 2)), np.ones((1, 2))))
     assert "CUDA" in str(ei.value)
+
+
+def test_flat_map_against_std_unordered_map(tmp_path):
+    """The planner's open-addressing edge index (host/flat_map.hpp) fuzzed against std::unordered_map."""
+    import subprocess
+    exe = str(tmp_path / "fm")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "batching_pomp_b200", "host"),
+                           os.path.join(ROOT, "tests", "cpp", "flat_map_fuzz.cpp"), "-o", exe])
+    out = subprocess.check_output([exe], timeout=120).decode()
+    assert "flat map ok" in out
