@@ -113,7 +113,7 @@ BatchingPOMP::BatchingPOMP(const SpaceInformation& si)
     : mSi(si), mDim(si.dim), mCtx(nullptr), mCurrentAlpha(0.0), mIncrement(0.2), mStartGoalRadius(0.0),
       mPruneThreshold(1.05), mIsInitSearchBatch(true), mIsPathFound(false), mUsingSelector(false),
       mBestPathCost(kInf), mSelType("normal"), mLaunchBase(0), mRoadmap(nullptr), mN(0), mFlushed(0), mStartVertex(0), mGoalVertex(0),
-      mHaveProblem(false), mHashedUpTo(0), mEpoch(0), mCsrValid(false), mCsrRadius(0.0), mCsrOlderEdges(false), mCsrBudget(30000000ull), bmNumBatches(0),
+      mHaveProblem(false), mHashedUpTo(0), mEpoch(0), mSearchEdgesNeeded(0), mCsrValid(false), mCsrRadius(0.0), mCsrOlderEdges(false), mCsrBudget(30000000ull), bmNumBatches(0),
       bmExhausted(false), bmCurrRadius(0.0), bmNumVerticesAdded(0), bmNextVertexTarget(0), bmVertInfl(2.0),
       bmRadiusInfl(1.0), bmInitRadius(0.0), bmMaxRadius(0.0), bmCurrVertex(0), bmEdgeMode(false), mNumSolutions(0),
       mBeliefEmpty(true), mNumEdgeChecks(0), mNumCollChecks(0), mNumSearches(0), mNumLookups(0), mLookupTime(0.0),
@@ -653,10 +653,13 @@ void BatchingPOMP::computeCreatedEdgeProbabilities(Vertex u, const std::vector<E
     }
     const size_t nreal = from.size();
     // speculative part: potential edges of the first vertices of the open list (smallest f first-ish)
-    // a device call costs about the same up to ~10^5 queries, so the speculative part grows with the
-    // open list (large frontiers = first search of a batch on a big roadmap)
-    const size_t kSpecVertices = std::min<size_t>(4096, std::max<size_t>(48, mHeap.size() / 8));
-    const size_t kSpecEdges = kSpecVertices * 24;
+    // Speculation budget: half of what this search has really needed so far (geometric growth), so
+    // the wasted work is bounded by that fraction when the goal is popped early (vertex batching pops
+    // it after a few expansions of a complete graph) and the number of device calls stays logarithmic-ish
+    // in the size of a search that sweeps a large roadmap.
+    mSearchEdgesNeeded += nreal;
+    const size_t kSpecVertices = mHeap.size();
+    const size_t kSpecEdges = std::min<size_t>(262144, std::max<size_t>(512, mSearchEdgesNeeded / 2));
     size_t taken = 0;
     for (size_t h = 0; h < mHeap.size() && taken < kSpecVertices && from.size() < nreal + kSpecEdges; ++h) {
       Vertex v = mHeap[h];
@@ -955,6 +958,7 @@ bool BatchingPOMP::astar(bool zeroHeuristic, bool single) {
   }
   mHeap.clear();
   mSpecCache.clear();  // speculative probFree values are valid for one search (one belief-model state)
+  mSearchEdgesNeeded = 0;
   if (mSpecStamp.size() < nv) mSpecStamp.resize(nv, 0);
   const double alpha = mCurrentAlpha;
   const double* goalState = vertexState(mGoalVertex);

@@ -227,6 +227,7 @@ private:
   std::vector<int64_t> mHeapIndex;
   std::vector<uint32_t> mStamp;
   uint32_t mEpoch;
+  size_t mSearchEdgesNeeded;  // created edges of the current search whose probFree had to be computed
   std::vector<Vertex> mHeap;
   void touch(Vertex v);
   void heapPush(Vertex v);
