@@ -527,8 +527,12 @@ static int edges_check_pipelined(bpomp_ctx* ctx, const double* from, const doubl
     if (c < EC_PIPE_LANES) cudaStreamWaitEvent(s, ev, 0);
     const char* hf = indexed ? (const char*)(fi + c0) : (const char*)(from + c0 * ctx->dim);
     const char* ht = indexed ? (const char*)(ti + c0) : (const char*)(to + c0 * ctx->dim);
-    cudaMemcpyAsync(ctx->lane_a[l].p, hf, (size_t)m * in_elem, cudaMemcpyHostToDevice, s);
-    cudaMemcpyAsync(ctx->lane_b[l].p, ht, (size_t)m * in_elem, cudaMemcpyHostToDevice, s);
+    cudaError_t ce = cudaMemcpyAsync(ctx->lane_a[l].p, hf, (size_t)m * in_elem, cudaMemcpyHostToDevice, s);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(ctx->lane_b[l].p, ht, (size_t)m * in_elem, cudaMemcpyHostToDevice, s);
+    if (ce != cudaSuccess) {
+      rc = bp_fail(ctx, BPOMP_ERR_CUDA, "pipelined edge check: H2D copy failed: %s", cudaGetErrorString(ce));
+      break;
+    }
     uint8_t* dv = ctx->lane_o[l].as<uint8_t>();
     int32_t* dfirst = reinterpret_cast<int32_t*>(dv + EC_PIPE_CHUNK);
     uint32_t* dn = reinterpret_cast<uint32_t*>(dv + (size_t)EC_PIPE_CHUNK * 5);
@@ -540,9 +544,15 @@ static int edges_check_pipelined(bpomp_ctx* ctx, const double* from, const doubl
                               indexed ? ctx->lane_b[l].as<uint32_t>() : nullptr, m, dv, dfirst, dn, false);
     ctx->stream = saved;
     ctx->work_slot = 0;
-    cudaMemcpyAsync(valid + c0, dv, (size_t)m, cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(first + c0, dfirst, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
-    if (nstates) cudaMemcpyAsync(nstates + c0, dn, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
+    if (rc != BPOMP_OK) break;
+    ce = cudaMemcpyAsync(valid + c0, dv, (size_t)m, cudaMemcpyDeviceToHost, s);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(first + c0, dfirst, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+    if (ce == cudaSuccess && nstates)
+      ce = cudaMemcpyAsync(nstates + c0, dn, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
+    if (ce != cudaSuccess) {
+      rc = bp_fail(ctx, BPOMP_ERR_CUDA, "pipelined edge check: D2H copy failed: %s", cudaGetErrorString(ce));
+      break;
+    }
   }
   for (int l = 0; l < EC_PIPE_LANES; ++l) {
     cudaError_t e2 = cudaStreamSynchronize(ctx->lane_stream[l]);

@@ -110,7 +110,7 @@ double SpaceInformation::getSpaceMeasure() const {
 // construction
 // ---------------------------------------------------------------------------
 BatchingPOMP::BatchingPOMP(const SpaceInformation& si)
-    : mSi(si), mDim(si.dim), mCtx(nullptr), mCurrentAlpha(0.0), mIncrement(0.2), mStartGoalRadius(0.0),
+    : mDim(si.dim), mCtx(nullptr), mCurrentAlpha(0.0), mIncrement(0.2), mStartGoalRadius(0.0),
       mPruneThreshold(1.05), mIsInitSearchBatch(true), mIsPathFound(false), mUsingSelector(false),
       mBestPathCost(kInf), mSelType("normal"), mLaunchBase(0), mRoadmap(nullptr), mN(0), mFlushed(0), mStartVertex(0), mGoalVertex(0),
       mHaveProblem(false), mHashedUpTo(0), mEpoch(0), mSearchEdgesNeeded(0), mCsrValid(false), mCsrRadius(0.0), mCsrOlderEdges(false), mCsrBudget(30000000ull), bmNumBatches(0),

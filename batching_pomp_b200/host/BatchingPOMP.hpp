@@ -188,7 +188,6 @@ private:
   void prepareNeighbourCache(double radius);
 
   // ---- space ----
-  SpaceInformation mSi;
   unsigned int mDim;
   double mL, mMaxExtent, mSpaceMeasure;
   bpomp_ctx* mCtx;
