@@ -318,7 +318,8 @@ def run_gpu(args):
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        cb = cpu_baseline_run(L, lo, hi, frm, to, target_s=12.0) if not args.no_cpu else None
+        # the CPU baseline is timed on rank 0 of the single-GPU run only (multi-GPU runs stay short)
+        cb = cpu_baseline_run(L, lo, hi, frm, to, target_s=12.0) if (not args.no_cpu and world == 1) else None
         value = world * E * args.steps / (elapsed_ms * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
