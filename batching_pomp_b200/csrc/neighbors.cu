@@ -481,6 +481,109 @@ __global__ void nb_bitonic_step(double* __restrict__ d, uint32_t* __restrict__ i
 }
 
 // ---------------------------------------------------------------------------
+// Whole-roadmap densification when the grid covers every dimension (D <= 3) and rows are short: one
+// THREAD per vertex, taken in cell order, so that the threads of a warp are spatial neighbours and walk
+// (nearly) the same candidate runs out of L1.  Count pass, scan over the vertex ids, fill pass, then the
+// warp-per-row rank sort by (distance, id).
+// ---------------------------------------------------------------------------
+#define NB_DENSE_CAP NB_SMALL  // rows longer than the warp rank sort handles take the general path
+
+template <int D, bool FILL>
+__global__ void __launch_bounds__(128) nb_dense_kernel(GridView g, double r, double r2pad,
+                                                       uint32_t* __restrict__ counts,
+                                                       const uint64_t* __restrict__ row_ptr,
+                                                       uint32_t* __restrict__ col, double* __restrict__ dist_out) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g.nactive) return;
+  double q[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) q[j] = __ldg(g.pts + (size_t)j * g.nactive + p);
+  int c0[D], c1[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    double pad = (fabs(q[j]) + r) * 9.094947017729282e-13;
+    c0[j] = nb_cell(q[j] - r - pad, g.lo[j], g.inv[j], g.G[j]);
+    c1[j] = nb_cell(q[j] + r + pad, g.lo[j], g.inv[j], g.G[j]);
+  }
+  uint32_t cnt = 0;
+  const uint32_t vid = __ldg(g.ids + p);
+  const uint64_t o = FILL ? row_ptr[vid] : 0;
+  const int A0 = D >= 2 ? c0[0] : 0, A1 = D >= 2 ? c1[0] : 0;
+  const int B0 = D >= 3 ? c0[1] : 0, B1 = D >= 3 ? c1[1] : 0;
+  const int GL = g.G[D - 1];
+  for (int a0 = A0; a0 <= A1; ++a0)
+    for (int b0 = B0; b0 <= B1; ++b0) {
+      const int prefix = D == 1 ? 0 : (D == 2 ? a0 : a0 * g.G[1] + b0);
+      const uint32_t i0 = __ldg(g.cell_start + (uint32_t)(prefix * GL + c0[D - 1]));
+      const uint32_t i1 = __ldg(g.cell_start + (uint32_t)(prefix * GL + c1[D - 1]) + 1);
+      for (uint32_t i = i0; i < i1; ++i) {
+        double d2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          const double diff = __dsub_rn(q[j], __ldg(g.pts + (size_t)j * g.nactive + i));
+          d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
+        }
+        if (d2 > r2pad) continue;
+        const double dd = __dsqrt_rn(d2);
+        if (!(dd <= r)) continue;  // inclusive, as GNAT nearestR
+        if (FILL) {  // unsorted; the row sort kernel orders it by (distance, id)
+          col[o + cnt] = __ldg(g.ids + i);
+          dist_out[o + cnt] = dd;
+        }
+        ++cnt;
+      }
+    }
+  if (!FILL) counts[vid] = cnt;
+}
+
+template <int D>
+static int neighbors_all_dense(bpomp_ctx* ctx, const GridView& g, double r, double r2pad, uint64_t* nnz_out, bool* done) {
+  *done = false;
+  const uint32_t nv = ctx->nverts;
+  BP_TRY(bp_reserve(ctx, ctx->s_f, ((size_t)nv + 2) * sizeof(uint32_t), false));
+  BP_TRY(bp_reserve(ctx, ctx->d_nb_rowptr, ((size_t)nv + 2) * sizeof(uint64_t), false));
+  uint32_t* counts = ctx->s_f.as<uint32_t>();
+  uint64_t* rp = ctx->d_nb_rowptr.as<uint64_t>();
+  BP_CUDA(ctx, cudaMemsetAsync(counts, 0, ((size_t)nv + 1) * sizeof(uint32_t), ctx->stream));  // inactive: empty rows
+  const int grid = (int)((g.nactive + 127) / 128);
+  if (grid > 0) nb_dense_kernel<D, false><<<grid, 128, 0, ctx->stream>>>(g, r, r2pad, counts, nullptr, nullptr, nullptr);
+  ctx->launches++;
+  BP_TRY(bp_exclusive_scan_u32(ctx, counts, nv, rp, ctx->d_nb_tmp2));
+  // longest row: reuse the row-pointer kernel's reduction (S = 1 maps offsets onto themselves)
+  BP_TRY(bp_reserve(ctx, ctx->s_g, 2 * sizeof(uint64_t), false));
+  unsigned long long* d_max = ctx->s_g.as<unsigned long long>();
+  BP_CUDA(ctx, cudaMemsetAsync(d_max, 0, sizeof(unsigned long long), ctx->stream));
+  BP_TRY(bp_reserve(ctx, ctx->d_nb_query, ((size_t)nv + 2) * sizeof(uint64_t), false));
+  nb_rowptr_kernel<<<(int)std::min<uint32_t>((nv + 256) / 256, 1024u), 256, 0, ctx->stream>>>(
+      rp, nv, 1, ctx->d_nb_query.as<uint64_t>(), d_max);
+  ctx->launches++;
+  uint64_t hostv[2];
+  BP_CUDA(ctx, cudaMemcpyAsync(&hostv[0], rp + nv, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA(ctx, cudaMemcpyAsync(&hostv[1], d_max, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (hostv[1] > NB_DENSE_CAP) return BPOMP_OK;  // some row is too long for the warp rank sort: general path
+  const uint64_t nnz = hostv[0];
+  BP_TRY(bp_reserve(ctx, ctx->d_nb_dist, (nnz + 1) * sizeof(double), false));
+  BP_TRY(bp_reserve(ctx, ctx->d_nb_col, (nnz + 1) * sizeof(uint32_t), false));
+  BP_TRY(bp_reserve(ctx, ctx->d_nb_tmp, (nnz + 1) * sizeof(double), false));
+  BP_TRY(bp_reserve(ctx, ctx->s_e, (nnz + 1) * sizeof(uint32_t), false));
+  if (nnz > 0 && grid > 0) {
+    nb_dense_kernel<D, true><<<grid, 128, 0, ctx->stream>>>(g, r, r2pad, nullptr, rp, ctx->s_e.as<uint32_t>(),
+                                                           ctx->d_nb_tmp.as<double>());
+    int gs = (int)std::min<uint64_t>(((uint64_t)nv * 32 + 255) / 256, (uint64_t)ctx->num_sms * 16);
+    nb_sort_small<<<std::max(gs, 1), 256, 0, ctx->stream>>>(rp, nv, ctx->d_nb_tmp.as<double>(), ctx->s_e.as<uint32_t>(),
+                                                           ctx->d_nb_dist.as<double>(), ctx->d_nb_col.as<uint32_t>());
+    ctx->launches += 2;
+    BP_CUDA(ctx, cudaGetLastError());
+  }
+  ctx->nb_nnz = nnz;
+  ctx->nb_nq = nv;
+  if (nnz_out) *nnz_out = nnz;
+  *done = true;
+  return BPOMP_OK;
+}
+
+// ---------------------------------------------------------------------------
 // Host driver
 // ---------------------------------------------------------------------------
 template <int D>
@@ -557,6 +660,13 @@ template <int D>
 static int neighbors_impl(bpomp_ctx* ctx, const uint32_t* d_query, uint32_t nq, double r, bool all, uint64_t* nnz_out) {
   GridView g;
   BP_TRY(build_grid<D>(ctx, r, g));
+  if (all && D <= NB_MAXG && g.gd == D && g.ncells >= 64 && std::isfinite(r)) {
+    // whole-roadmap densification on a grid that covers every dimension: thread-per-vertex path
+    double r2p = (r * r) * (1.0 + 9.094947017729282e-13);
+    bool done = false;
+    BP_TRY((neighbors_all_dense<(D <= NB_MAXG ? D : 1)>(ctx, g, r, r2p, nnz_out, &done)));
+    if (done) return BPOMP_OK;
+  }
   // Brute-force regime with enough queries to fill thread-per-query blocks -> tiled all-pairs kernel
   const bool tiled = g.ncells <= 8 && nq >= 4 * NB_TQ && g.nactive >= 4 * NB_TP;
   // slices per query: enough warps to fill the machine when there are few queries
