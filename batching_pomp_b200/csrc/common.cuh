@@ -190,8 +190,14 @@ __host__ __device__ __forceinline__ int bp_cell(double x, double g0, double gs) 
   return (int)v;
 }
 
-// Row of the range-mask table for cells [c0, c0+span] of dimension j (span < BP_SPAN).
+// Row of the range-mask table for cells [c0, c0+span] of dimension j (span < BP_SPAN).  c0 is the minor
+// index: a row is 16 B per group, so the shared-memory bank group of a lookup is (row mod 8) = (c0 mod 8),
+// which is spread evenly over the lanes of a warp (span is not: most segments stay within 1-2 cells).
+#ifdef BP_RROW_SPAN_MINOR  // tuning builds only: the layout before the bank-spread fix
 __host__ __device__ __forceinline__ int bp_rrow(int j, int c0, int span) { return (j * BP_GRID_C + c0) * BP_SPAN + span; }
+#else
+__host__ __device__ __forceinline__ int bp_rrow(int j, int c0, int span) { return (j * BP_SPAN + span) * BP_GRID_C + c0; }
+#endif
 // Row of the prefix-mask table: which = 0 -> "lowest cell <= c", which = 1 -> "highest cell >= c".
 __host__ __device__ __forceinline__ int bp_row(int j, int which, int c) { return (j * 2 + which) * BP_GRID_C + c; }
 

@@ -129,6 +129,16 @@ BatchingPOMP::BatchingPOMP(const SpaceInformation& si)
     throw Exception("the StateValidityChecker must be described as a device world (boxes or image); "
                     "there is no CPU fallback");
   mCtxKey = ctxKey(si, mL);
+  // The device context is acquired at the first call that needs the GPU (setProblemDefinition, solve):
+  // parameters, setup() and roadmap files are host work.  There is still no CPU fallback — that first
+  // call throws when CUDA or the device library is unavailable.
+  mSpace.reset(new SpaceInformation(si));
+}
+
+bpomp_ctx* BatchingPOMP::dev() {
+  if (mCtx) return mCtx;
+  if (!mSpace) throw Exception("device context was released");
+  const SpaceInformation& si = *mSpace;
   {
     std::lock_guard<std::mutex> lk(pool().mu);
     auto it = pool().idle.find(mCtxKey);
@@ -140,10 +150,14 @@ BatchingPOMP::BatchingPOMP(const SpaceInformation& si)
   if (mCtx) {  // recycled: same device / dim / L / world, emptied when it was returned
     mLaunchBase = bpomp_launch_count(mCtx);
     check(bpomp_belief_config(mCtx, 15, 0.5, 0.25));
-    return;
+    mSpace.reset();
+    return mCtx;
   }
   int rc = bpomp_create(si.device, (int)mDim, mL, &mCtx);
-  if (rc != BPOMP_OK) throw Exception(std::string("bpomp_create: ") + bpomp_last_error(nullptr));
+  if (rc != BPOMP_OK) {
+    mCtx = nullptr;
+    throw Exception(std::string("bpomp_create: ") + bpomp_last_error(nullptr));
+  }
   try {
     if (si.world == SpaceInformation::World::BOXES) {
       int nb = (int)(si.boxLo.size() / mDim);
@@ -158,6 +172,8 @@ BatchingPOMP::BatchingPOMP(const SpaceInformation& si)
     mCtx = nullptr;
     throw;
   }
+  mSpace.reset();
+  return mCtx;
 }
 
 BatchingPOMP::~BatchingPOMP() {
@@ -295,16 +311,16 @@ void BatchingPOMP::flushVertices() {
   uint32_t nv = (uint32_t)mOut.size();
   if (mFlushed < nv) {
     uint32_t first = 0;
-    check(bpomp_vertices_append(mCtx, &mVState[(size_t)mFlushed * mDim], nv - mFlushed, &first));
+    check(bpomp_vertices_append(dev(), &mVState[(size_t)mFlushed * mDim], nv - mFlushed, &first));
     if (first != mFlushed) throw Exception("internal: device vertex ids out of step with the roadmap");
     std::vector<uint32_t> off;
     for (uint32_t v = mFlushed; v < nv; ++v)
       if (!mNNActive[v]) off.push_back(v);
-    if (!off.empty()) check(bpomp_vertices_set_active(mCtx, off.data(), (uint32_t)off.size(), 0));
+    if (!off.empty()) check(bpomp_vertices_set_active(dev(), off.data(), (uint32_t)off.size(), 0));
     mFlushed = nv;
   }
   if (!mPendingDeactivate.empty()) {
-    check(bpomp_vertices_set_active(mCtx, mPendingDeactivate.data(), (uint32_t)mPendingDeactivate.size(), 0));
+    check(bpomp_vertices_set_active(dev(), mPendingDeactivate.data(), (uint32_t)mPendingDeactivate.size(), 0));
     mPendingDeactivate.clear();
   }
 }
@@ -406,7 +422,7 @@ void BatchingPOMP::setProblemDefinition(const std::vector<double>& start, const 
   std::vector<double> sg(start);
   sg.insert(sg.end(), goal.begin(), goal.end());
   uint8_t ok[2] = {0, 0};
-  check(bpomp_states_valid(mCtx, sg.data(), 2, ok));
+  check(bpomp_states_valid(dev(), sg.data(), 2, ok));
   if (!ok[0]) throw Exception("Start configuration is in collision!");
   mStartVertex = addVertex(start.data(), true);
   if (!ok[1]) throw Exception("Goal configuration is in collision!");
@@ -447,7 +463,7 @@ void BatchingPOMP::nextBatch() {
   auto admitRange = [&](uint32_t first, uint32_t count) {
     if (count == 0) return;
     std::vector<uint8_t> prune(count);
-    check(bpomp_states_prune(mCtx, &mRoadmap[(size_t)first * mDim], count, vertexState(mStartVertex),
+    check(bpomp_states_prune(dev(), &mRoadmap[(size_t)first * mDim], count, vertexState(mStartVertex),
                              vertexState(mGoalVertex), mBestPathCost, 1, prune.data()));
     for (uint32_t i = 0; i < count; ++i)
       if (!prune[i]) addVertex(&mRoadmap[(size_t)(first + i) * mDim], true);
@@ -500,7 +516,7 @@ void BatchingPOMP::pruneVertices(bool withValidity) {
   uint32_t nv = (uint32_t)mOut.size();
   if (nv == 0) return;
   std::vector<uint8_t> prune(nv);
-  check(bpomp_vertices_prune(mCtx, mStartVertex, mGoalVertex, mBestPathCost, withValidity ? 1 : 0, prune.data()));
+  check(bpomp_vertices_prune(dev(), mStartVertex, mGoalVertex, mBestPathCost, withValidity ? 1 : 0, prune.data()));
   for (Vertex v = 0; v < nv; ++v) {
     if (!prune[v]) continue;
     if (mNNActive[v]) {
@@ -530,16 +546,16 @@ void BatchingPOMP::prepareNeighbourCache(double radius) {
     uint32_t stride = nv / 64 ? nv / 64 : 1;
     for (uint32_t v = 0; v < nv && q.size() < 64; v += stride) q.push_back(v);
     uint64_t nnz = 0;
-    check(bpomp_neighbors_radius(mCtx, q.data(), (uint32_t)q.size(), radius, &nnz));
+    check(bpomp_neighbors_radius(dev(), q.data(), (uint32_t)q.size(), radius, &nnz));
     est = (double)nnz / (double)q.size() * (double)nactive;
   }
   if (est > (double)mCsrBudget) return;  // rows are fetched on demand instead
   uint64_t nnz = 0;
-  check(bpomp_neighbors_all(mCtx, radius, &nnz));
+  check(bpomp_neighbors_all(dev(), radius, &nnz));
   mCsrRowPtr.resize((size_t)nv + 1);
   mCsrCol.resize(nnz ? nnz : 1);
   mCsrDist.resize(nnz ? nnz : 1);
-  check(bpomp_neighbors_fetch(mCtx, mCsrRowPtr.data(), mCsrCol.data(), mCsrDist.data()));
+  check(bpomp_neighbors_fetch(dev(), mCsrRowPtr.data(), mCsrCol.data(), mCsrDist.data()));
   mCsrValid = true;
   mCsrRadius = radius;
   mCsrEdge.assign(nnz ? nnz : 1, kNoEdge);
@@ -567,11 +583,11 @@ const std::vector<std::pair<double, BatchingPOMP::Vertex>>& BatchingPOMP::neighb
   }
   flushVertices();
   uint64_t nnz = 0;
-  check(bpomp_neighbors_radius(mCtx, &u, 1, radius, &nnz));
+  check(bpomp_neighbors_radius(dev(), &u, 1, radius, &nnz));
   std::vector<uint64_t> rp(2);
   std::vector<uint32_t> col(nnz ? nnz : 1);
   std::vector<double> dist(nnz ? nnz : 1);
-  check(bpomp_neighbors_fetch(mCtx, rp.data(), col.data(), dist.data()));
+  check(bpomp_neighbors_fetch(dev(), rp.data(), col.data(), dist.data()));
   for (uint64_t k = 0; k < nnz; ++k) mRowScratch.emplace_back(dist[k], col[k]);
   return mRowScratch;
 }
@@ -683,7 +699,7 @@ void BatchingPOMP::computeCreatedEdgeProbabilities(Vertex u, const std::vector<E
     std::vector<uint32_t> nl(from.size());
     std::vector<double> pf(from.size());
     flushVertices();
-    check(bpomp_belief_edge_pfree_indexed(mCtx, from.data(), to.data(), (int64_t)from.size(), pf.data(), nl.data()));
+    check(bpomp_belief_edge_pfree_indexed(dev(), from.data(), to.data(), (int64_t)from.size(), pf.data(), nl.data()));
     for (size_t i = 0; i < nreal; ++i) {
       setProbFree(mEdges[miss[i]], pf[i]);
       mNumLookups += nl[i];
@@ -732,7 +748,7 @@ void BatchingPOMP::computeFreeProbabilities(const std::vector<Edge>& edges) {
       to[i] = mEdges[edges[i]].target;
     }
     flushVertices();
-    check(bpomp_belief_edge_pfree_indexed(mCtx, from.data(), to.data(), (int64_t)edges.size(), pf.data(), nl.data()));
+    check(bpomp_belief_edge_pfree_indexed(dev(), from.data(), to.data(), (int64_t)edges.size(), pf.data(), nl.data()));
     for (size_t i = 0; i < edges.size(); ++i) {
       setProbFree(mEdges[edges[i]], pf[i]);
       mNumLookups += nl[i];
@@ -781,7 +797,7 @@ bool BatchingPOMP::checkAndUpdatePathBlocked(const std::vector<Edge>& ePath) {
     to[i] = mEdges[unknown[i]].target;
   }
   flushVertices();
-  check(bpomp_edges_check_indexed(mCtx, from.data(), to.data(), (int64_t)m, valid.data(), first.data(), ns.data()));
+  check(bpomp_edges_check_indexed(dev(), from.data(), to.data(), (int64_t)m, valid.data(), first.data(), ns.data()));
   bool pathBlocked = false;
   size_t committed = 0;
   for (size_t i = 0; i < m; ++i) {
@@ -819,7 +835,7 @@ bool BatchingPOMP::checkAndUpdatePathBlocked(const std::vector<Edge>& ePath) {
     added += valid[i] ? ns[i] - 2u : (uint32_t)first[i];
   }
   if (added > 0) {
-    check(bpomp_belief_append_checked(mCtx, fs.data(), ts.data(), first.data(), (int64_t)committed));
+    check(bpomp_belief_append_checked(dev(), fs.data(), ts.data(), first.data(), (int64_t)committed));
     mBeliefEmpty = false;
   }
   mCollCheckTime += now() - t0;

@@ -150,9 +150,10 @@ public:
   size_t numVertices() const { return mOut.size(); }
   size_t numEdges() const { return mEdges.size(); }
   const double* vertexState(Vertex v) const { return &mVState[(size_t)v * mDim]; }
+  /// The device context; null until the first call that needed the GPU (setProblemDefinition / solve).
   bpomp_ctx* context() const { return mCtx; }
   /// Kernel launches issued on behalf of this planner instance.
-  uint64_t gpuLaunches() const { return bpomp_launch_count(mCtx) - mLaunchBase; }
+  uint64_t gpuLaunches() const { return mCtx ? bpomp_launch_count(mCtx) - mLaunchBase : 0; }
 
 private:
   struct OutEdge { Vertex target; Edge eid; };
@@ -191,6 +192,8 @@ private:
   unsigned int mDim;
   double mL, mMaxExtent, mSpaceMeasure;
   bpomp_ctx* mCtx;
+  bpomp_ctx* dev();                         // acquires the context on first use; throws without CUDA
+  std::unique_ptr<SpaceInformation> mSpace; // world description, held until the context exists
   std::string mCtxKey;  // device contexts are recycled between planner instances (BatchingPOMP.cpp, CtxPool)
 
   // ---- parameters ----

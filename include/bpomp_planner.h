@@ -28,7 +28,9 @@ typedef struct bpomp_planner bpomp_planner;
 
 /* Space description (RealVectorStateSpace bounds low/high[dim], longestValidSegmentFraction) and
  * the collision world.  world_kind: 1 = boxes (lo, hi, count), 2 = image (pix, width, height,
- * threshold).  Returns NULL on failure (message from bpomp_planner_error(NULL)). */
+ * threshold).  Returns NULL on failure (message from bpomp_planner_error(NULL)).  The device context
+ * is acquired by the first call that needs the GPU (set_problem / solve); parameters, setup and
+ * roadmap files are host work.  There is no CPU fallback: that first call fails without CUDA. */
 BPOMP_PAPI bpomp_planner* bpomp_planner_create_boxes(int device, int dim, const double* low, const double* high,
                                                      double segment_fraction, const double* box_lo,
                                                      const double* box_hi, int nboxes);

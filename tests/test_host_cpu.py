@@ -74,12 +74,70 @@ def test_graphml_errors(planner_mod, tmp_path):
 
 
 def test_planner_needs_gpu(planner_mod):
+    """No CPU fallback: parameters, setup() and roadmap files are host work, the first call that needs the
+    device (setProblemDefinition validates start/goal there, BP.cpp:772-780) fails loudly without CUDA."""
     import torch
     if torch.cuda.is_available():
         pytest.skip("GPU present")
+    p = planner_mod.Planner(2, boxes=(np.zeros((1, 2)), np.full((1, 2), 0.1)))
+    assert p.gpu_launches == 0
     with pytest.raises(planner_mod.PlannerError) as ei:
-        planner_mod.Planner(2, boxes=(np.zeros((1, 2)), np.ones((1, 2))))
+        p.set_problem([0.5, 0.5], [0.9, 0.9])
     assert "CUDA" in str(ei.value)
+    with pytest.raises(planner_mod.PlannerError):
+        p.solve(max_iterations=1)
+
+
+def test_planner_setup_errors_mirror_reference(planner_mod, tmp_path):
+    """setup() parameter validation in the reference's order and wording (BP.cpp:676-750, Selector.hpp:74)."""
+    from batching_pomp_b200 import workloads as wl
+    P, E = planner_mod.Planner, planner_mod.PlannerError
+    lo, hi = wl.box_world(2, 10, seed=3)
+    p = P(2, boxes=(lo, hi))
+    p.set_roadmap(wl.halton(100, 2))
+    p.set_param("batching_type", "edge")
+    with pytest.raises(E) as ei:
+        p.setup()  # BP.cpp:681-683
+    assert "Graph type needed" in str(ei.value)
+    p.set_param("graph_type", "halton")
+    p.set_param("batching_type", "bogus")
+    with pytest.raises(E) as ei:
+        p.setup()  # BP.cpp:745-747
+    assert "Invalid batching type" in str(ei.value)
+    p.set_param("batching_type", "vertex")
+    p.set_param("selector_type", "bogus")
+    with pytest.raises(E) as ei:
+        p.setup()  # Selector.hpp:74
+    assert ei.value.code == -2
+    r = P(2, boxes=(lo, hi))
+    r.set_param("batching_type", "vertex")
+    with pytest.raises(E) as ei:
+        r.setup()  # BP.cpp:686-688
+    assert "Roadmap name must be set" in str(ei.value)
+    r.set_param("roadmap_filename", str(tmp_path / "missing.graphml"))
+    with pytest.raises(E):
+        r.setup()
+
+
+@pytest.mark.parametrize("batching", ["vertex", "edge", "hybrid", "single"])
+def test_planner_setup_from_graphml_on_cpu(planner_mod, tmp_path, batching):
+    """setup() with roadmap_filename reads the GraphML roadmap and builds the batching manager on the host."""
+    from batching_pomp_b200 import workloads as wl
+    d, N = 3, 400
+    roadmap = wl.halton(N, d)
+    edges = np.stack([np.arange(N - 1), np.arange(1, N)], 1).astype(np.uint32)
+    f = str(tmp_path / "roadmap.graphml")
+    planner_mod.write_graphml(f, roadmap, edges)
+    lo, hi = wl.box_world(d, 10, seed=3)
+    p = planner_mod.Planner(d, boxes=(lo, hi))
+    p.set_param("roadmap_filename", f)
+    p.set_param("batching_type", batching)
+    p.set_param("graph_type", "halton")
+    p.set_param("start_goal_radius", 0.3)
+    p.setup()
+    assert p.num_batches == 0 and not p.exhausted
+    assert p.best_cost == np.finfo(np.float64).max  # std::numeric_limits<double>::max() (BP.cpp:242,279)
+    assert p.gpu_launches == 0
 
 
 def test_flat_map_against_std_unordered_map(tmp_path):
