@@ -180,14 +180,16 @@ __device__ __forceinline__ uint32_t bp_nstates(double dist, double L) {
 // Monotone cell index used by the broad phase; the host builds the masks with the same function.
 __host__ __device__ __forceinline__ int bp_cell(double x, double g0, double gs) {
 #ifdef __CUDA_ARCH__
-  double v = __dmul_rn(__dsub_rn(x, g0), gs);
+  // the conversion saturates and maps NaN to 0, so clamping the integer gives the same cells as the
+  // comparisons of the host branch
+  return min(max(__double2int_rz(__dmul_rn(__dsub_rn(x, g0), gs)), 0), BP_GRID_C - 1);
 #else
   volatile double t = x - g0;
   double v = t * gs;
-#endif
   if (!(v > 0.0)) return 0;
   if (v >= (double)BP_GRID_C) return BP_GRID_C - 1;
   return (int)v;
+#endif
 }
 
 // Row of the range-mask table for cells [c0, c0+span] of dimension j (span < BP_SPAN).  c0 is the minor

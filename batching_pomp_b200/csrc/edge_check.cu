@@ -143,6 +143,7 @@ __device__ __forceinline__ bool edge_prologue(const EdgeArgs& a, const PermView&
 struct WarpScratch {
   int32_t first[32];                         // first invalid slot found so far, per edge of the tile
   unsigned short list[EC_MAXCAND * 32];      // candidate boxes [c][lane]
+  unsigned char nzlane[32];                  // lanes of the edges that have slots to test, in lane order
 };
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -225,8 +226,9 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
       bool longspan = false;
 #pragma unroll
       for (int j = 0; j < D; ++j) {
-        const int c0 = bp_cell(fmin(f[j], t[j]), w.g0[j], w.gs[j]);
-        const int c1 = bp_cell(fmax(f[j], t[j]), w.g0[j], w.gs[j]);
+        // bp_cell is monotone: the cells of the two endpoints bound the cells of every sample between them
+        const int cf = bp_cell(f[j], w.g0[j], w.gs[j]), ct = bp_cell(t[j], w.g0[j], w.gs[j]);
+        const int c0 = min(cf, ct), c1 = max(cf, ct);
         rr[j] = (c1 - c0 < BP_SPAN) ? bp_rrow(j, c0, c1 - c0) : -(1 + c0 * BP_GRID_C + c1);
         longspan = longspan || rr[j] < 0;
       }
@@ -301,20 +303,23 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
     }
     const uint32_t start = incl - cnt;  // exclusive prefix of the slots to test per edge
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    {
+      const uint32_t nz = __ballot_sync(0xffffffffu, cnt > 0);
+      if (cnt > 0) ws->nzlane[__popc(nz & ((1u << lane) - 1u))] = (unsigned char)lane;
+    }
+    uint32_t before = 0;  // edges with slots whose first item lies before the current window
     __syncwarp();
 
     // ---- C. flattened (edge, slot) pairs (lane = sample).  The edge data stays in the owner lane's
     // registers and is fetched with warp shuffles; every lane executes the shuffles of every round. ----
     for (uint32_t ib = 0; ib < total; ib += 32) {
       const uint32_t it = ib + lane;
-      int lo_i = 0, hi_i = 32;  // last edge whose first item is <= it
-#pragma unroll
-      for (int s = 0; s < 5; ++s) {
-        const int mid = (lo_i + hi_i) >> 1;
-        const uint32_t sm = __shfl_sync(0xffffffffu, start, mid);
-        if (sm <= it) lo_i = mid; else hi_i = mid;
-      }
-      const int el = lo_i;
+      // edge of item `it`: the window's edge heads as a bit mask (one warp OR-reduction), then the rank of
+      // the last head at or before this lane indexes the list of edges that have slots
+      const uint32_t rel = start - ib;
+      const uint32_t heads = __reduce_or_sync(0xffffffffu, (cnt > 0 && rel < 32u) ? (1u << rel) : 0u);
+      const int el = ws->nzlane[(before + __popc(heads & (0xffffffffu >> (31 - lane))) - 1u) & 31u];
+      before += __popc(heads);
       const int32_t slot = (int32_t)(1u + it - __shfl_sync(0xffffffffu, start, el));
       const uint32_t off_el = __shfl_sync(0xffffffffu, off, el);
       const int ncl_el = __shfl_sync(0xffffffffu, ncl, el);
@@ -331,9 +336,11 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
       if (act) {
         bool inside = false;
         if (ncl_el >= 0) {
+          int b = ws->list[el];  // the next candidate id is read while the current box is tested
           for (int c = 0; c < ncl_el; ++c) {
-            const int b = ws->list[c * 32 + el];
+            const int bn = ws->list[min(c + 1, EC_MAXCAND - 1) * 32 + el];
             if (bp_inside_box_grouped<D>(x, lohi + (size_t)b * w.lohi_stride)) { inside = true; break; }
+            b = bn;
           }
         } else {  // more candidates than the list holds: test every box (rare)
           for (int b = 0; b < w.nboxes; ++b)
