@@ -15,7 +15,10 @@
 
 #include "common.cuh"
 
-#define BK_QB 128    // queries (threads) per block
+#define BK_QB 128    // threads per block
+#ifndef BK_QT
+#define BK_QT 2      // queries per thread
+#endif
 #define BK_TILE 256  // belief points staged per tile
 #define BK_KMAX 32   // largest supported k
 
@@ -146,74 +149,166 @@ __global__ void __launch_bounds__(256) bk_expand_kernel(EdgeSrc src, int64_t cou
 // ---------------------------------------------------------------------------
 // kNN: partial top-k per (query, point chunk)
 // ---------------------------------------------------------------------------
+// Tile layout: bk_ds(D) doubles per point = the D coordinates, |p|^2 / 2 at index D, padded to an even
+// count so a point is read with 16-byte broadcast loads.
+__host__ __device__ constexpr int bk_ds(int D) { return (D + 2) & ~1; }
+
+// One (query, point) candidate in the reference's arithmetic (unfused sum of squares, sqrt) and the ordered
+// insertion into the query's list kd/ki (entries BK_QT*BK_QB apart).  nq = -query (negation is exact).
 template <int D>
-__global__ void __launch_bounds__(BK_QB) bk_knn_partial(const double* __restrict__ queries, int64_t nq,
+__device__ __forceinline__ void bk_consider(const double* nq, const double* pt, uint32_t idx, int K, double* kd,
+                                            uint32_t* ki, int& cnt, double& worst, double& thr) {
+  constexpr int LS = BK_QT * BK_QB;
+  double d2 = 0.0;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    double diff = __dsub_rn(-nq[j], pt[j]);
+    d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
+  }
+  if (cnt == K && d2 > thr) return;
+  double dist = __dsqrt_rn(d2);
+  if (cnt == K && !(dist < worst)) return;  // an equidistant later point never displaces (GNAT)
+  // insert after every entry with distance <= dist (indices ascend within the scan)
+  int pos = cnt < K ? cnt : K - 1;
+  while (pos > 0 && kd[(pos - 1) * LS] > dist) {
+    kd[pos * LS] = kd[(pos - 1) * LS];
+    ki[pos * LS] = ki[(pos - 1) * LS];
+    --pos;
+  }
+  kd[pos * LS] = dist;
+  ki[pos * LS] = idx;
+  if (cnt < K) ++cnt;
+  if (cnt == K) {
+    worst = kd[(K - 1) * LS];
+    thr = __dmul_rn(__dmul_rn(worst, worst), 1.0 + 9.094947017729282e-13);  // conservative (2^-40)
+  }
+}
+
+// Each thread owns BK_QT queries (tid, tid + BK_QB, ...) of the block's BK_QT*BK_QB, so a point read from the
+// tile (a shared-memory broadcast, the scarce resource of this kernel) serves BK_QT distance evaluations.
+template <int D>
+__global__ void __launch_bounds__(BK_QB) bk_knn_partial(const double* __restrict__ queries, int64_t nq_total,
                                                         const double* __restrict__ pts, uint64_t M, uint64_t chunk,
                                                         int K, double* __restrict__ part_d,
                                                         uint32_t* __restrict__ part_i) {
+  constexpr int DS = bk_ds(D);
+  constexpr int LS = BK_QT * BK_QB;
   extern __shared__ __align__(16) unsigned char smem[];
-  double* s_pts = reinterpret_cast<double*>(smem);                                  // [BK_TILE][D]
-  double* s_kd = s_pts + BK_TILE * D;                                               // [K][BK_QB]
-  uint32_t* s_ki = reinterpret_cast<uint32_t*>(s_kd + (size_t)K * BK_QB);           // [K][BK_QB]
+  double* s_pts = reinterpret_cast<double*>(smem);                                  // [BK_TILE][DS]
+  double* s_kd = s_pts + BK_TILE * DS;                                              // [K][BK_QT][BK_QB]
+  uint32_t* s_ki = reinterpret_cast<uint32_t*>(s_kd + (size_t)K * LS);              // [K][BK_QT][BK_QB]
+  __shared__ unsigned long long s_pnmax;  // bits of the tile's largest |p|^2 (non-negative doubles order as integers)
   const int tid = threadIdx.x;
-  const int64_t qi = (int64_t)blockIdx.x * BK_QB + tid;
   const uint64_t p_begin = (uint64_t)blockIdx.y * chunk;
   const uint64_t p_end = p_begin + chunk < M ? p_begin + chunk : M;
-  double q[D];
+  double nq[BK_QT][D];   // -query
+  double qn[BK_QT];      // |q|^2 (approximate: prefilter only)
+  double worst[BK_QT], thr[BK_QT], thrp[BK_QT];
+  int cnt[BK_QT];
 #pragma unroll
-  for (int j = 0; j < D; ++j) q[j] = qi < nq ? queries[qi * D + j] : 0.0;
-  int cnt = 0;
-  double worst = DBL_MAX, thr = DBL_MAX;  // worst distance in a full list; d2 prefilter threshold
+  for (int s = 0; s < BK_QT; ++s) {
+    const int64_t qi = (int64_t)blockIdx.x * LS + s * BK_QB + tid;
+    qn[s] = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      const double v = qi < nq_total ? queries[qi * D + j] : 0.0;  // out-of-range slots scan as query 0, unwritten
+      nq[s][j] = -v;
+      qn[s] = fma(v, v, qn[s]);
+    }
+    cnt[s] = 0;
+    worst[s] = DBL_MAX;  // worst distance of a full list
+    thr[s] = DBL_MAX;    // its square, padded: bound on the unfused d2
+    thrp[s] = DBL_MAX;   // bound on the prefilter value
+  }
+
+  // Prefilter: |q-p|^2 / 2 = |p|^2/2 - q.p + |q|^2/2 as D fused multiply-adds on top of the stored |p|^2/2 (a
+  // third of the FP64 work of the unfused difference form).  Its absolute error is below 2^-49 (|q|^2 + |p|^2);
+  // the bound is padded by 2^-46 (|q|^2 + max |p|^2 of the tile), so a point it rejects is beyond thr in the
+  // reference's arithmetic too.  Survivors go through bk_consider().  A NaN makes the comparison false.
+  auto approx = [&](const double2* pp, int s) {
+    double acc = (D & 1) ? pp[D / 2].y : pp[D / 2].x;
+#pragma unroll
+    for (int h = 0; h < D / 2; ++h) {
+      const double2 v = pp[h];
+      acc = fma(nq[s][2 * h], v.x, acc);
+      acc = fma(nq[s][2 * h + 1], v.y, acc);
+    }
+    if (D & 1) acc = fma(nq[s][D - 1], pp[D / 2].x, acc);
+    return acc;
+  };
+
   for (uint64_t base = p_begin; base < p_end; base += BK_TILE) {
     uint32_t tn = (uint32_t)((p_end - base) < BK_TILE ? (p_end - base) : BK_TILE);
     __syncthreads();
-    for (uint32_t i = tid; i < tn * D; i += BK_QB) s_pts[i] = pts[base * D + i];
+    if (tid == 0) s_pnmax = 0ull;
+    for (uint32_t i = tid; i < tn * D; i += BK_QB) s_pts[(i / D) * DS + (i % D)] = pts[base * D + i];
     __syncthreads();
-    if (qi >= nq) continue;
-    for (uint32_t p = 0; p < tn; ++p) {
-      // Prefilter with fused multiply-adds (14 FP64 operations instead of 21): the fused sum differs from
-      // the reference's unfused one by a few ulp at most, so anything above thr*(1+2^-40) cannot enter the
-      // list; survivors are recomputed with the reference's exact unfused arithmetic.
-      if (cnt == K) {
-        double dq = 0.0;
+    for (uint32_t p = tid; p < tn; p += BK_QB) {
+      double pn = 0.0;
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-          double diff = __dsub_rn(q[j], s_pts[p * D + j]);
-          dq = __fma_rn(diff, diff, dq);
+      for (int j = 0; j < D; ++j) pn = fma(s_pts[p * DS + j], s_pts[p * DS + j], pn);
+      s_pts[p * DS + D] = 0.5 * pn;
+      atomicMax(&s_pnmax, (unsigned long long)__double_as_longlong(pn));  // NaN bits exceed +inf: stays NaN
+    }
+    __syncthreads();
+    const double pnmax = __longlong_as_double((long long)s_pnmax);
+    double pad[BK_QT];
+#pragma unroll
+    for (int s = 0; s < BK_QT; ++s) {
+      pad[s] = 2.842170943040401e-14 * (qn[s] + pnmax);  // 2^-45, halved with the bound below
+      thrp[s] = 0.5 * ((thr[s] - qn[s]) + pad[s]);
+    }
+    uint32_t p = 0;
+    while (p < tn) {  // cnt[] is the same in every thread: min(points scanned, K)
+      if (cnt[0] == K && !(p & 3u) && p + 4 <= tn) {
+        double acc[4][BK_QT];
+        bool far = true;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double2* pp = reinterpret_cast<const double2*>(s_pts + (p + u) * DS);
+#pragma unroll
+          for (int s = 0; s < BK_QT; ++s) {
+            acc[u][s] = approx(pp, s);
+            far = far && acc[u][s] > thrp[s];
+          }
         }
-        if (dq > thr) continue;
-      }
-      double d2 = 0.0;
+        if (!far) {
 #pragma unroll
-      for (int j = 0; j < D; ++j) {
-        double diff = __dsub_rn(q[j], s_pts[p * D + j]);
-        d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
-      }
-      if (cnt == K && d2 > thr) continue;
-      double dist = __dsqrt_rn(d2);
-      if (cnt == K && !(dist < worst)) continue;  // an equidistant later point never displaces (GNAT)
-      // insert after every entry with distance <= dist (indices ascend within the scan)
-      int pos = cnt < K ? cnt : K - 1;
-      while (pos > 0 && s_kd[(pos - 1) * BK_QB + tid] > dist) {
-        s_kd[pos * BK_QB + tid] = s_kd[(pos - 1) * BK_QB + tid];
-        s_ki[pos * BK_QB + tid] = s_ki[(pos - 1) * BK_QB + tid];
-        --pos;
-      }
-      s_kd[pos * BK_QB + tid] = dist;
-      s_ki[pos * BK_QB + tid] = (uint32_t)(base + p);
-      if (cnt < K) ++cnt;
-      if (cnt == K) {
-        worst = s_kd[(K - 1) * BK_QB + tid];
-        thr = __dmul_rn(__dmul_rn(worst, worst), 1.0 + 9.094947017729282e-13);  // conservative (2^-40)
+          for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int s = 0; s < BK_QT; ++s) {
+              if (!(acc[u][s] > thrp[s])) {  // a stale (looser) bound after an insertion stays conservative
+                bk_consider<D>(nq[s], s_pts + (p + u) * DS, (uint32_t)(base + p + u), K, s_kd + s * BK_QB + tid,
+                               s_ki + s * BK_QB + tid, cnt[s], worst[s], thr[s]);
+                thrp[s] = 0.5 * ((thr[s] - qn[s]) + pad[s]);
+              }
+            }
+          }
+        }
+        p += 4;
+      } else {
+        const double2* pp = reinterpret_cast<const double2*>(s_pts + p * DS);
+#pragma unroll
+        for (int s = 0; s < BK_QT; ++s) {
+          if (cnt[s] < K || !(approx(pp, s) > thrp[s])) {
+            bk_consider<D>(nq[s], s_pts + p * DS, (uint32_t)(base + p), K, s_kd + s * BK_QB + tid,
+                           s_ki + s * BK_QB + tid, cnt[s], worst[s], thr[s]);
+            thrp[s] = 0.5 * ((thr[s] - qn[s]) + pad[s]);
+          }
+        }
+        ++p;
       }
     }
   }
-  if (qi < nq) {
-    double* od = part_d + ((size_t)blockIdx.y * nq + qi) * K;
-    uint32_t* oi = part_i + ((size_t)blockIdx.y * nq + qi) * K;
+#pragma unroll
+  for (int s = 0; s < BK_QT; ++s) {
+    const int64_t qi = (int64_t)blockIdx.x * LS + s * BK_QB + tid;
+    if (qi >= nq_total) continue;
+    double* od = part_d + ((size_t)blockIdx.y * nq_total + qi) * K;
+    uint32_t* oi = part_i + ((size_t)blockIdx.y * nq_total + qi) * K;
     for (int k = 0; k < K; ++k) {
-      od[k] = k < cnt ? s_kd[k * BK_QB + tid] : DBL_MAX;
-      oi[k] = k < cnt ? s_ki[k * BK_QB + tid] : 0xFFFFFFFFu;
+      od[k] = k < cnt[s] ? s_kd[k * LS + s * BK_QB + tid] : DBL_MAX;
+      oi[k] = k < cnt[s] ? s_ki[k * LS + s * BK_QB + tid] : 0xFFFFFFFFu;
     }
   }
 }
@@ -283,7 +378,7 @@ static int knn_estimate_dev(bpomp_ctx* ctx, const double* d_queries, int64_t nq,
   int P = 1;
   uint64_t chunk = M ? M : 1;
   if (M > 0) {
-    int64_t qblocks = (nq + BK_QB - 1) / BK_QB;
+    int64_t qblocks = (nq + BK_QB * BK_QT - 1) / (BK_QB * BK_QT);
     int64_t want = 2 * (int64_t)ctx->num_sms;
     while (qblocks * P < want && P < 64 && (M + (2 * P) - 1) / (2 * P) >= 1024) P *= 2;
     chunk = (M + P - 1) / P;
@@ -291,10 +386,10 @@ static int knn_estimate_dev(bpomp_ctx* ctx, const double* d_queries, int64_t nq,
     P = (int)((M + chunk - 1) / chunk);
     BP_TRY(bp_reserve(ctx, bd, (size_t)P * nq * K * sizeof(double), false));
     BP_TRY(bp_reserve(ctx, bi, (size_t)P * nq * K * sizeof(uint32_t), false));
-    size_t sm = (size_t)BK_TILE * D * sizeof(double) + (size_t)K * BK_QB * (sizeof(double) + sizeof(uint32_t));
+    size_t sm = (size_t)BK_TILE * bk_ds(D) * sizeof(double) + (size_t)K * BK_QT * BK_QB * (sizeof(double) + sizeof(uint32_t));
     auto kern = bk_knn_partial<D>;
     BP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    dim3 grid((unsigned)((nq + BK_QB - 1) / BK_QB), (unsigned)P);
+    dim3 grid((unsigned)qblocks, (unsigned)P);
     kern<<<grid, BK_QB, sm, ctx->stream>>>(d_queries, nq, ctx->d_bel_pts.as<double>(), M, chunk, K, bd.as<double>(),
                                            bi.as<uint32_t>());
     ctx->launches++;
