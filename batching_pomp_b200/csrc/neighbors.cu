@@ -315,63 +315,136 @@ __global__ void __launch_bounds__(256) nb_query_kernel(QueryArgs a, GridView g) 
 // cell-ordered point table in tiles staged through shared memory (coalesced tile loads, broadcast reads),
 // exactly like the belief kNN kernel.  Slice index = point chunk, so counts / offsets / fill keep the
 // (query, slice) layout of the warp kernel and the rest of the pipeline is unchanged.
-#define NB_TQ 128
-#define NB_TP 128
+#define NB_TQ 128   // threads per block
+#define NB_TP 128   // points per tile
+#define NB_QT 2     // queries per thread: a point read from the tile (shared-memory broadcast) serves both
+__host__ __device__ constexpr int nb_ds(int D) { return (D + 2) & ~1; }  // coordinates, |p|^2/2, pad to 16 B
+
 template <int D, bool FILL>
-__global__ void __launch_bounds__(NB_TQ) nb_tile_kernel(QueryArgs a, GridView g, uint32_t chunk) {
-  __shared__ double s_pts[D][NB_TP];
+__global__ void __launch_bounds__(NB_TQ, 4) nb_tile_kernel(QueryArgs a, GridView g, uint32_t chunk) {
+  constexpr int DS = nb_ds(D);
+  __shared__ __align__(16) double s_pts[NB_TP * DS];
   __shared__ uint32_t s_ids[NB_TP];
+  __shared__ unsigned int s_pnhi;  // high word of the tile's largest |p|^2 (non-negative doubles order as integers)
   const int tid = threadIdx.x;
-  const uint32_t qi = blockIdx.x * NB_TQ + tid;
   const uint32_t c = blockIdx.y;
   const uint32_t p_begin = c * chunk;
   const uint32_t p_end = min(p_begin + chunk, g.nactive);
-  const bool have = qi < a.nq;
-  const uint32_t qid = have ? (a.query ? __ldg(a.query + qi) : qi) : 0u;
-  const bool skip = !have || (a.skip_inactive_query && !a.active[qid]);
-  double q[D];
+  bool have[NB_QT], skip[NB_QT];
+  double nq[NB_QT][D];  // -query (negation is exact)
+  double qn[NB_QT];     // |q|^2, prefilter only
+  uint64_t w[NB_QT], o[NB_QT];
+  uint32_t cnt[NB_QT];
+  bool skip_all = true;
 #pragma unroll
-  for (int j = 0; j < D; ++j) q[j] = have ? __ldg(a.verts + (size_t)qid * D + j) : 0.0;
-  const uint64_t w = (uint64_t)qi * a.S + c;
-  uint64_t o = (FILL && have) ? a.offs[w] : 0;
-  uint32_t cnt = 0;
+  for (int s = 0; s < NB_QT; ++s) {
+    const uint32_t qi = (blockIdx.x * NB_QT + s) * NB_TQ + tid;
+    have[s] = qi < a.nq;
+    const uint32_t qid = have[s] ? (a.query ? __ldg(a.query + qi) : qi) : 0u;
+    skip[s] = !have[s] || (a.skip_inactive_query && !a.active[qid]);
+    skip_all = skip_all && skip[s];
+    qn[s] = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      const double v = have[s] ? __ldg(a.verts + (size_t)qid * D + j) : 0.0;
+      nq[s][j] = -v;
+      qn[s] = fma(v, v, qn[s]);
+    }
+    w[s] = (uint64_t)qi * a.S + c;
+    o[s] = (FILL && have[s]) ? a.offs[w[s]] : 0;
+    cnt[s] = 0;
+  }
+  // Prefilter: |q-p|^2/2 = |p|^2/2 - q.p + |q|^2/2 as D fused multiply-adds on the stored |p|^2/2; absolute
+  // error below 2^-49 (|q|^2 + |p|^2), bound padded by 2^-46 (|q|^2 + an upper bound of the tile's max |p|^2).
+  // Survivors are recomputed with the reference's unfused arithmetic.  NaN compares false -> recomputed.
+  auto approx = [&](const double2* pp, int s) {
+    double acc = (D & 1) ? pp[D / 2].y : pp[D / 2].x;
+#pragma unroll
+    for (int h = 0; h < D / 2; ++h) {
+      const double2 v = pp[h];
+      acc = fma(nq[s][2 * h], v.x, acc);
+      acc = fma(nq[s][2 * h + 1], v.y, acc);
+    }
+    if (D & 1) acc = fma(nq[s][D - 1], pp[D / 2].x, acc);
+    return acc;
+  };
+  auto exact = [&](int s, uint32_t t) {
+    double d2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      const double diff = __dsub_rn(-nq[s][j], s_pts[t * DS + j]);
+      d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
+    }
+    const double dist = __dsqrt_rn(d2);
+    if (dist <= a.r) {  // inclusive, as GNAT nearestR
+      if (FILL) {
+        a.out_dist[o[s] + cnt[s]] = dist;
+        a.out_id[o[s] + cnt[s]] = s_ids[t];
+      }
+      ++cnt[s];
+    }
+  };
   for (uint32_t base = p_begin; base < p_end; base += NB_TP) {
     const uint32_t tn = min((uint32_t)NB_TP, p_end - base);
     __syncthreads();
-    if ((uint32_t)tid < tn) {
+    if (tid == 0) s_pnhi = 0u;
+    __syncthreads();
+    {
+      double pn = 0.0;
+      if ((uint32_t)tid < tn) {
 #pragma unroll
-      for (int j = 0; j < D; ++j) s_pts[j][tid] = __ldg(g.pts + (size_t)j * g.nactive + base + tid);
-      if (FILL) s_ids[tid] = __ldg(g.ids + base + tid);
+        for (int j = 0; j < D; ++j) {
+          const double v = __ldg(g.pts + (size_t)j * g.nactive + base + tid);
+          s_pts[tid * DS + j] = v;
+          pn = fma(v, v, pn);
+        }
+        s_pts[tid * DS + D] = 0.5 * pn;
+        if (FILL) s_ids[tid] = __ldg(g.ids + base + tid);
+      }
+      const unsigned int hi = __reduce_max_sync(0xffffffffu, (unsigned int)__double2hiint(pn));
+      if ((tid & 31) == 0) atomicMax(&s_pnhi, hi);
     }
     __syncthreads();
-    if (skip) continue;
-    for (uint32_t t = 0; t < tn; ++t) {
-      // fused prefilter (2 FP64 operations per dimension instead of 3); survivors are recomputed with
-      // the reference's unfused arithmetic
-      double dq = 0.0;
+    if (skip_all) continue;
+    // upper bound of max |p|^2: next high word (inf / NaN high words stay non-finite -> every point is recomputed)
+    const double pnmax = __hiloint2double((int)(s_pnhi < 0x7ff00000u ? s_pnhi + 1u : 0x7ff80000u), 0);
+    double bound[NB_QT];
 #pragma unroll
-      for (int j = 0; j < D; ++j) {
-        const double diff = __dsub_rn(q[j], s_pts[j][t]);
-        dq = __fma_rn(diff, diff, dq);
-      }
-      if (dq > a.r2pad) continue;
-      double d2 = 0.0;
+    for (int s = 0; s < NB_QT; ++s)
+      bound[s] = skip[s] ? -DBL_MAX : 0.5 * ((a.r2pad - qn[s]) + 2.842170943040401e-14 * (qn[s] + pnmax));
+    uint32_t t = 0;
+    for (; t + 4 <= tn; t += 4) {
+      double acc[4][NB_QT];
+      bool far = true;
 #pragma unroll
-      for (int j = 0; j < D; ++j) {
-        const double diff = __dsub_rn(q[j], s_pts[j][t]);
-        d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
-      }
-      const double dist = __dsqrt_rn(d2);
-      if (dist <= a.r) {  // inclusive, as GNAT nearestR
-        if (FILL) {
-          a.out_dist[o + cnt] = dist;
-          a.out_id[o + cnt] = s_ids[t];
+      for (int u = 0; u < 4; ++u) {
+        const double2* pp = reinterpret_cast<const double2*>(s_pts + (t + u) * DS);
+#pragma unroll
+        for (int s = 0; s < NB_QT; ++s) {
+          acc[u][s] = approx(pp, s);
+          far = far && acc[u][s] > bound[s];
         }
-        ++cnt;
+      }
+      if (far) continue;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int s = 0; s < NB_QT; ++s)
+          if (!skip[s] && !(acc[u][s] > bound[s])) exact(s, t + u);
       }
     }
+    for (; t < tn; ++t) {
+      const double2* pp = reinterpret_cast<const double2*>(s_pts + t * DS);
+#pragma unroll
+      for (int s = 0; s < NB_QT; ++s)
+        if (!skip[s] && !(approx(pp, s) > bound[s])) exact(s, t);
+    }
   }
-  if (!FILL && have) a.counts[w] = cnt;
+  if (!FILL) {
+#pragma unroll
+    for (int s = 0; s < NB_QT; ++s)
+      if (have[s]) a.counts[w[s]] = cnt[s];
+  }
 }
 
 // row_ptr[q] = offs[q*S]
@@ -673,7 +746,7 @@ static int neighbors_impl(bpomp_ctx* ctx, const uint32_t* d_query, uint32_t nq, 
   int S = 1;
   uint32_t chunk = 0;
   if (tiled) {
-    uint64_t qblocks = ((uint64_t)nq + NB_TQ - 1) / NB_TQ;
+    uint64_t qblocks = ((uint64_t)nq + NB_TQ * NB_QT - 1) / (NB_TQ * NB_QT);
     uint64_t want = (uint64_t)ctx->num_sms * 8;  // resident blocks
     while (qblocks * S < want && (uint64_t)g.nactive / (2 * S) >= 8 * NB_TP) S *= 2;
     chunk = (uint32_t)(((uint64_t)g.nactive + S - 1) / S);
@@ -701,7 +774,7 @@ static int neighbors_impl(bpomp_ctx* ctx, const uint32_t* d_query, uint32_t nq, 
   a.counts = ctx->s_f.as<uint32_t>();
   int grid = (int)std::min<uint64_t>((nw * 32 + 255) / 256, (uint64_t)ctx->num_sms * 8);
   if (grid < 1) grid = 1;
-  const dim3 tgrid((unsigned)(((uint64_t)nq + NB_TQ - 1) / NB_TQ), (unsigned)S);
+  const dim3 tgrid((unsigned)(((uint64_t)nq + NB_TQ * NB_QT - 1) / (NB_TQ * NB_QT)), (unsigned)S);
   if (tiled) nb_tile_kernel<D, false><<<tgrid, NB_TQ, 0, ctx->stream>>>(a, g, chunk);
   else nb_query_kernel<D, false><<<grid, 256, 0, ctx->stream>>>(a, g);
   ctx->launches++;
