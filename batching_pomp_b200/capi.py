@@ -48,6 +48,8 @@ SIGNATURES = {
     "bpomp_edges_check_indexed": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp, vp]),
     "bpomp_edges_check_dev": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp, vp]),
     "bpomp_edges_check_indexed_dev": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp, vp]),
+    "bpomp_edge_status_pack_dev": (C.c_int, [vp, vp, C.c_int64, vp]),
+    "bpomp_edge_status_unpack_dev": (C.c_int, [vp, vp, C.c_int64, vp]),
     "bpomp_edge_states": (C.c_int, [vp, vp, vp, vp, C.c_uint32, c_u32p]),
     "bpomp_belief_config": (C.c_int, [vp, C.c_int, C.c_double, C.c_double]),
     "bpomp_belief_append": (C.c_int, [vp, vp, vp, C.c_int64]),
@@ -244,6 +246,13 @@ class Context:
         self._ck(self.lib.bpomp_edges_check_indexed_dev(self.h, _ptr(d_from_ids), _ptr(d_to_ids), int(count),
                                                         _ptr(d_valid), _ptr(d_first),
                                                         _ptr(d_nstates) if d_nstates else None))
+
+    def edge_status_pack_dev(self, d_valid, count, d_packed):
+        """Status bytes -> 2 bits per edge ((count+15)//16 uint32 words); device pointers, ctx stream."""
+        self._ck(self.lib.bpomp_edge_status_pack_dev(self.h, _ptr(d_valid), int(count), _ptr(d_packed)))
+
+    def edge_status_unpack_dev(self, d_packed, count, d_valid):
+        self._ck(self.lib.bpomp_edge_status_unpack_dev(self.h, _ptr(d_packed), int(count), _ptr(d_valid)))
 
     def edge_states(self, frm, to):
         f, t = _f64(frm), _f64(to)

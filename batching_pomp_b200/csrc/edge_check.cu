@@ -646,6 +646,77 @@ __global__ void edge_states_kernel(const double* f, const double* t, int D, cons
     for (int j = 0; j < D; ++j) out[(size_t)i * D + j] = __dadd_rn(f[j], __dmul_rn(__dsub_rn(t[j], f[j]), tt));
   }
 }
+// ---------------------------------------------------------------------------
+// Status packing for the multi-GPU merge: 2 bits per edge, 16 edges per word.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) status_pack_kernel(const uint8_t* __restrict__ valid, int64_t count,
+                                                          uint32_t* __restrict__ packed) {
+  const int64_t words = (count + 15) / 16;
+  for (int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < words; wi += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = wi * 16;
+    uint32_t out = 0;
+    if (e0 + 16 <= count && (reinterpret_cast<uintptr_t>(valid) & 15) == 0) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(valid + e0));
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) out |= ((w4[q] >> (8 * b)) & 3u) << (2 * (4 * q + b));
+      }
+    } else {
+      for (int i = 0; i < 16 && e0 + i < count; ++i) out |= ((uint32_t)valid[e0 + i] & 3u) << (2 * i);
+    }
+    packed[wi] = out;
+  }
+}
+
+__global__ void __launch_bounds__(256) status_unpack_kernel(const uint32_t* __restrict__ packed, int64_t count,
+                                                            uint8_t* __restrict__ valid) {
+  const int64_t words = (count + 15) / 16;
+  for (int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < words; wi += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = wi * 16;
+    const uint32_t in = __ldg(packed + wi);
+    if (e0 + 16 <= count && (reinterpret_cast<uintptr_t>(valid) & 15) == 0) {
+      uint32_t w4[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        w4[q] = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) w4[q] |= ((in >> (2 * (4 * q + b))) & 3u) << (8 * b);
+      }
+      *reinterpret_cast<uint4*>(valid + e0) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+    } else {
+      for (int i = 0; i < 16 && e0 + i < count; ++i) valid[e0 + i] = (uint8_t)((in >> (2 * i)) & 3u);
+    }
+  }
+}
+
+static int status_grid(bpomp_ctx* ctx, int64_t count) {
+  const int64_t words = (count + 15) / 16;
+  return (int)std::max<int64_t>(1, std::min<int64_t>((words + 255) / 256, (int64_t)ctx->num_sms * 8));
+}
+
+extern "C" int bpomp_edge_status_pack_dev(bpomp_ctx* ctx, const uint8_t* d_valid, int64_t count, uint32_t* d_packed) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (count < 0 || (count > 0 && (!d_valid || !d_packed))) return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
+  if (count == 0) return BPOMP_OK;
+  status_pack_kernel<<<status_grid(ctx, count), 256, 0, ctx->stream>>>(d_valid, count, d_packed);
+  ctx->launches++;
+  BP_CUDA(ctx, cudaGetLastError());
+  return BPOMP_OK;
+}
+
+extern "C" int bpomp_edge_status_unpack_dev(bpomp_ctx* ctx, const uint32_t* d_packed, int64_t count,
+                                            uint8_t* d_valid) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (count < 0 || (count > 0 && (!d_valid || !d_packed))) return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
+  if (count == 0) return BPOMP_OK;
+  status_unpack_kernel<<<status_grid(ctx, count), 256, 0, ctx->stream>>>(d_packed, count, d_valid);
+  ctx->launches++;
+  BP_CUDA(ctx, cudaGetLastError());
+  return BPOMP_OK;
+}
+
 __global__ void edge_nstates_kernel(const double* f, const double* t, int D, double L, uint32_t* n) {
   double s = 0.0;
   for (int j = 0; j < D; ++j) {

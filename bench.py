@@ -211,6 +211,9 @@ def run_gpu(args):
     d_valid = [d_valid] + [torch.empty_like(d_valid) for _ in range(nbuf - 1)]
     d_first = [d_first] + [torch.empty_like(d_first) for _ in range(nbuf - 1)]
     gathered = [torch.empty(world * E, dtype=torch.uint8, device=dev) for _ in range(nbuf)] if world > 1 else None
+    words = (E + 15) // 16  # status flags travel packed, 2 bits per edge (bpomp_edge_status_pack_dev)
+    packed = [torch.empty(words, dtype=torch.int32, device=dev) for _ in range(nbuf)] if world > 1 else None
+    packed_all = [torch.empty(world * words, dtype=torch.int32, device=dev) for _ in range(nbuf)] if world > 1 else None
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
     kernel_ms = []
     pending = [None] * nbuf
@@ -220,8 +223,7 @@ def run_gpu(args):
         k = step_no[0] % nbuf
         step_no[0] += 1
         if pending[k] is not None:  # the gather that last read this buffer set must be done
-            pending[k].wait()
-            pending[k] = None
+            finish(k)
         if timed:
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
@@ -232,17 +234,27 @@ def run_gpu(args):
             e1.record(stream)
             kernel_ms.append((e0, e1, E))
         if world > 1:
+            ctx.edge_status_pack_dev(d_valid[k].data_ptr(), E, packed[k].data_ptr())
             ev = torch.cuda.Event()
             ev.record(stream)
             with torch.cuda.stream(comm_stream):
                 comm_stream.wait_event(ev)
-                pending[k] = sharding.allgather_equal(d_valid[k], gathered[k], async_op=True)[1]
+                pending[k] = sharding.allgather_equal(packed[k], packed_all[k], async_op=True)[1]
+
+    def finish(k):
+        """Buffer set k: wait for its gather and expand every rank's packed flags to the merged byte array."""
+        pending[k].wait()  # the kernel stream waits for the collective
+        pending[k] = None
+        if E % 16 == 0:
+            ctx.edge_status_unpack_dev(packed_all[k].data_ptr(), world * E, gathered[k].data_ptr())
+        else:
+            for g in range(world):
+                ctx.edge_status_unpack_dev(packed_all[k][g * words:].data_ptr(), E, gathered[k][g * E:].data_ptr())
 
     def drain():
         for k in range(nbuf):
             if pending[k] is not None:
-                pending[k].wait()
-                pending[k] = None
+                finish(k)
         if world > 1:
             stream.wait_stream(comm_stream)
 
@@ -326,7 +338,8 @@ def run_gpu(args):
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(E, world, {
-                "merge": ("nccl all_gather of the edge status flags (1 B/edge) per step, overlapped with the next "
+                "merge": ("nccl all_gather of the edge status flags (packed to 2 bits/edge, unpacked to 1 B/edge on "
+                          "every rank) per step, overlapped with the next "
                           "step's kernel (double-buffered results); first-invalid slots stay with the shard "
                           "owner, which replays the belief inserts") if world > 1 else "none (single GPU)"}),
             "kernel_ms_per_step": kern_ms_per_step,

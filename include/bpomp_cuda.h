@@ -161,6 +161,14 @@ BPOMP_API int bpomp_edges_check_dev(bpomp_ctx* ctx, const double* d_from, const 
 BPOMP_API int bpomp_edges_check_indexed_dev(bpomp_ctx* ctx, const uint32_t* d_from_ids, const uint32_t* d_to_ids,
                                             int64_t count, uint8_t* d_valid, int32_t* d_first_invalid_slot,
                                             uint32_t* d_nstates);
+/* Multi-GPU merge helpers (no counterpart in the reference, which is single-process: BASELINE north_star,
+ * "NCCL all-gather ... only for merging edge-status").  The status bytes of bpomp_edges_check*_dev packed
+ * to 2 bits per edge, 16 edges per word (edge e -> word e/16, bits 2*(e%16)..+1, unused bits 0), so the
+ * all-gather moves a quarter of the bytes; unpack restores the byte flags.  d_packed holds (count+15)/16
+ * words.  Asynchronous on the ctx stream. */
+BPOMP_API int bpomp_edge_status_pack_dev(bpomp_ctx* ctx, const uint8_t* d_valid, int64_t count, uint32_t* d_packed);
+BPOMP_API int bpomp_edge_status_unpack_dev(bpomp_ctx* ctx, const uint32_t* d_packed, int64_t count,
+                                           uint8_t* d_valid);
 /* The states of one edge in slot order (debug / belief replay helper): out[n][dim]. */
 BPOMP_API int bpomp_edge_states(bpomp_ctx* ctx, const double* from, const double* to, double* out,
                                 uint32_t cap, uint32_t* nstates);

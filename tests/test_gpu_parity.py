@@ -430,6 +430,40 @@ def test_device_pointer_api_with_torch(capi, orc, wl):
     ctx.close()
 
 
+def _pack_status_numpy(valid):
+    """The layout include/bpomp_cuda.h states: edge e -> word e//16, bits 2*(e%16)..+1, unused bits 0."""
+    n = valid.size
+    pad = np.zeros((n + 15) // 16 * 16, dtype=np.uint32)
+    pad[:n] = valid & 3
+    return (pad.reshape(-1, 16) << (2 * np.arange(16, dtype=np.uint32))).sum(axis=1, dtype=np.uint64).astype(np.uint32)
+
+
+@pytest.mark.parametrize("count,shift", [(1, 0), (15, 0), (16, 0), (17, 0), (4096, 0), (1000003, 0), (100001, 1), (64, 3)])
+def test_edge_status_pack_unpack(capi, count, shift):
+    """Multi-GPU merge helpers: 2-bit packing of the status bytes and its inverse, aligned and unaligned."""
+    import torch
+    ctx = capi.Context(2, 0.01)
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(count)
+    valid = rng.integers(0, 3, size=count, dtype=np.uint8)  # BLOCKED / FREE / DEFERRED
+    buf = torch.zeros(count + 16, dtype=torch.uint8, device=dev)
+    tv = buf[shift:shift + count]
+    tv.copy_(torch.from_numpy(valid))
+    words = (count + 15) // 16
+    tp = torch.full((words,), -1, dtype=torch.int32, device=dev)
+    out = torch.full((count + 16,), 7, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    ctx.edge_status_pack_dev(tv.data_ptr(), count, tp.data_ptr())
+    ctx.edge_status_unpack_dev(tp.data_ptr(), count, out[shift:].data_ptr())
+    ctx.sync()
+    np.testing.assert_array_equal(tp.cpu().numpy().view(np.uint32), _pack_status_numpy(valid))
+    o = out.cpu().numpy()
+    np.testing.assert_array_equal(o[shift:shift + count], valid)
+    assert (o[:shift] == 7).all() and (o[shift + count:] == 7).all()  # nothing written outside [0, count)
+    ctx.edge_status_pack_dev(0, 0, 0)  # empty input is a no-op
+    ctx.close()
+
+
 def test_full_size_properties_config4(capi, wl):
     """BASELINE config 4 at full size (10^7 edges, 7-DoF, 500 boxes): size-independent properties.
     (a) a chunked evaluation equals the one-shot evaluation; (b) an edge is BLOCKED iff its first

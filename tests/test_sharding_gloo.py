@@ -45,6 +45,57 @@ def _worker(rank, world, port, count, q):
     dist.destroy_process_group()
 
 
+def _pack2(valid):
+    """2 bits per status, 16 per word: the layout of bpomp_edge_status_pack_dev (include/bpomp_cuda.h)."""
+    n = valid.size
+    pad = np.zeros((n + 15) // 16 * 16, dtype=np.uint32)
+    pad[:n] = valid & 3
+    return (pad.reshape(-1, 16) << (2 * np.arange(16, dtype=np.uint32))).sum(axis=1, dtype=np.uint64).astype(np.uint32)
+
+
+def _unpack2(words, n):
+    return ((words[:, None] >> (2 * np.arange(16, dtype=np.uint32))) & 3).astype(np.uint8).reshape(-1)[:n]
+
+
+def _packed_worker(rank, world, port, per_rank, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from batching_pomp_b200 import sharding
+    valid = np.random.default_rng(100 + rank).integers(0, 3, size=per_rank, dtype=np.uint8)
+    words = (per_rank + 15) // 16
+    merged, _ = sharding.allgather_equal(torch.from_numpy(_pack2(valid).view(np.int32).copy()))
+    merged = merged.numpy().view(np.uint32)
+    # bench.py's finish(): one unpack over world*E when E % 16 == 0, else one per rank
+    if per_rank % 16 == 0:
+        out = _unpack2(merged, world * per_rank)
+    else:
+        out = np.concatenate([_unpack2(merged[g * words:(g + 1) * words], per_rank) for g in range(world)])
+    if rank == 0:
+        q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("per_rank", [4096, 4099])
+def test_packed_status_merge_layout(per_rank):
+    """The N>1 merge of bench.py on gloo: every rank's 2-bit packed flags gathered and expanded back to the
+    concatenation of the ranks' status bytes (the CUDA pack/unpack kernels are checked in test_gpu_parity)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_packed_worker, args=(r, 2, port, per_rank, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    want = np.concatenate([np.random.default_rng(100 + r).integers(0, 3, size=per_rank, dtype=np.uint8) for r in range(2)])
+    np.testing.assert_array_equal(out, want)
+
+
 @pytest.mark.parametrize("count", [4000, 4001])
 def test_sharded_edge_check_merges_to_unsharded(orc, count):
     from batching_pomp_b200 import workloads
