@@ -19,7 +19,12 @@
 #ifndef BK_QT
 #define BK_QT 2      // queries per thread
 #endif
+#ifndef BK_TILE
 #define BK_TILE 256  // belief points staged per tile
+#endif
+#ifndef BK_G
+#define BK_G 8       // points per prefilter group (independent accumulation chains per query)
+#endif
 #define BK_KMAX 32   // largest supported k
 
 extern "C" int bpomp_belief_config(bpomp_ctx* ctx, int k, double prior, double prior_weight) {
@@ -260,11 +265,11 @@ __global__ void __launch_bounds__(BK_QB) bk_knn_partial(const double* __restrict
     }
     uint32_t p = 0;
     while (p < tn) {  // cnt[] is the same in every thread: min(points scanned, K)
-      if (cnt[0] == K && !(p & 3u) && p + 4 <= tn) {
-        double acc[4][BK_QT];
+      if (cnt[0] == K && !(p & (BK_G - 1u)) && p + BK_G <= tn) {
+        double acc[BK_G][BK_QT];
         bool far = true;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < BK_G; ++u) {
           const double2* pp = reinterpret_cast<const double2*>(s_pts + (p + u) * DS);
 #pragma unroll
           for (int s = 0; s < BK_QT; ++s) {
@@ -274,7 +279,7 @@ __global__ void __launch_bounds__(BK_QB) bk_knn_partial(const double* __restrict
         }
         if (!far) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < BK_G; ++u) {
 #pragma unroll
             for (int s = 0; s < BK_QT; ++s) {
               if (!(acc[u][s] > thrp[s])) {  // a stale (looser) bound after an insertion stays conservative
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(BK_QB) bk_knn_partial(const double* __restrict
             }
           }
         }
-        p += 4;
+        p += BK_G;
       } else {
         const double2* pp = reinterpret_cast<const double2*>(s_pts + p * DS);
 #pragma unroll

@@ -347,7 +347,7 @@ def run_gpu(args):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_edge": ALGO_BYTES_PER_EDGE,
                          "kernel": "edge_check_boxes_kernel<7,false,true,4>", "avg_launch_ms": avg_launch_ms,
-                         "note": "shared-memory / issue bound well before HBM (DESIGN.md 4.1): smem wavefronts 74% of peak, issue 62%"},
+                         "note": "shared-memory / latency bound well before HBM (DESIGN.md 4.1): smem wavefronts 74% of peak, issue slots 56%"},
             "e2e": {"value": world * E * e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(2 * E * DIM * 8), "d2h_bytes_per_step": int(E * 5),
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
