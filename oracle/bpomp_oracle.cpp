@@ -12,6 +12,10 @@
 // (OMPL RealVectorStateSpace, GNAT result semantics) is restated from its
 // published behaviour.  It is pinned only against the
 // hand-derived known-answer values of SURVEY.md §4 (tests/test_oracle_kat.py).
+// One exception: util/BisectPerm.hpp is header-only standard C++, so it IS
+// compiled from where it lies (oracle/ref_shim.cpp -> oracle/_ref/libbpomp_ref.so)
+// and orc_bisect_perm is pinned to it, live and through tests/golden/
+// bisect_perm_ref.npz.  Everything else in this file stays unpinned.
 //
 // Compile: g++ -O2 -std=c++17 -fPIC -shared -fopenmp -ffp-contract=off   (no
 // -march, no -ffast-math: the reference sets only -std=c++11, CMakeLists.txt:4,

@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the cpu_baseline /
 ``--impl reference`` legs of bench.py.  The product package (batching_pomp_b200) never imports it.
-PARITY UNPINNED — see the header of bpomp_oracle.cpp.
+PARITY UNPINNED (except BisectPerm, pinned to the reference's own header through oracle/_ref) — see the
+header of bpomp_oracle.cpp.
 """
 import ctypes as C
 import os
@@ -74,6 +75,26 @@ def _p(a, t):
 
 def max_threads():
     return int(lib().orc_max_threads())
+
+
+_REF_PATH = os.path.join(_HERE, "_ref", "libbpomp_ref.so")
+_ref = None
+
+
+def ref_available():
+    """True when the reference's own BisectPerm.hpp was compiled here (oracle/Makefile target `ref`)."""
+    return os.path.exists(_REF_PATH)
+
+
+def ref_bisect_perm(n):
+    """BisectPerm::get(n) of the reference itself (oracle/ref_shim.cpp includes the header from /root/reference)."""
+    global _ref
+    if _ref is None:
+        _ref = C.CDLL(_REF_PATH)
+    first = np.zeros(max(n, 1), dtype=np.int32)
+    second = np.zeros(max(n, 1), dtype=np.int32)
+    m = _ref.ref_bisect_perm(C.c_int(n), _p(first, c_i32p), _p(second, c_i32p))
+    return first[:m].copy(), second[:m].copy()
 
 
 def bisect_perm(n):

@@ -54,6 +54,15 @@ def test_create_argument_errors(capi):
     assert b"segment_length" in lib.bpomp_last_error(None)
 
 
+def test_gap_bisect_perm_equals_reference_golden(capi):
+    """The product's sample order (bpomp_bisect_perm, host side of ctx.cu) against vectors produced by the
+    reference's own BisectPerm.hpp (tests/golden/bisect_perm_ref.npz, tests/golden/make_golden_ref.py)."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bisect_perm_ref.npz"))
+    ns, offs, gf = z["n"], z["offsets"], z["first"]
+    for i, n in enumerate(ns.tolist()):
+        np.testing.assert_array_equal(capi.bisect_perm(n), gf[offs[i]:offs[i + 1]], err_msg="n=%d" % n)
+
+
 @pytest.mark.parametrize("n", list(range(0, 70)) + [100, 127, 128, 129, 255, 300, 1000])
 def test_gap_bisect_perm_equals_reference_algorithm(capi, orc, n):
     """The O(n log n) gap formulation (ctx.cu) against the literal O(n^2) restatement of

@@ -30,6 +30,35 @@ def test_bisect_perm_is_permutation(orc, n):
     assert sorted(first.tolist()) == list(range(n))
 
 
+def _golden_perm():
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bisect_perm_ref.npz"))
+    return z["n"], z["offsets"], z["first"], z["second"]
+
+
+def test_bisect_perm_matches_reference_golden(orc):
+    """Pinned to the reference itself: tests/golden/bisect_perm_ref.npz holds BisectPerm::get(n) of the
+    reference's own header compiled in the build container (tests/golden/make_golden_ref.py)."""
+    ns, offs, gf, gs = _golden_perm()
+    assert len(ns) > 250
+    for i, n in enumerate(ns.tolist()):
+        first, second = orc.bisect_perm(n)
+        np.testing.assert_array_equal(first, gf[offs[i]:offs[i + 1]], err_msg="n=%d" % n)
+        np.testing.assert_array_equal(second, gs[offs[i]:offs[i + 1]], err_msg="n=%d" % n)
+
+
+def test_bisect_perm_matches_reference_build(orc):
+    """Live check against oracle/_ref (the reference's BisectPerm.hpp compiled from where it lies); the
+    library is built where /root/reference exists and travels to the GPU box with the snapshot."""
+    if not orc.ref_available():
+        pytest.skip("oracle/_ref/libbpomp_ref.so not built (no /root/reference at build time)")
+    for n in list(range(0, 400)) + [777, 1024, 2049, 5000]:
+        rf, rs = orc.ref_bisect_perm(n)
+        first, second = orc.bisect_perm(n)
+        np.testing.assert_array_equal(first, rf, err_msg="n=%d" % n)
+        np.testing.assert_array_equal(second, rs, err_msg="n=%d" % n)
+
+
 def test_nstates_floor_and_minimum(orc):
     L = 0.0264575
     assert orc.nstates(0.0, L) == 2
