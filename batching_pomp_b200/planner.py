@@ -11,7 +11,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbpomp_host.so")
+# env override: tuning builds, and the CPU test-suite's copy of the library that sits next to a test double of
+# libbpomp_cuda.so (tests/mock) — the product never sets it
+LIB_PATH = os.environ.get("BPOMP_HOST_LIB") or os.path.join(_HERE, "libbpomp_host.so")
 vp = C.c_void_p
 
 SIGNATURES = {
