@@ -1,6 +1,8 @@
 // ompl_adapter.hpp — drop-in ompl::base::Planner named batching_pomp::BatchingPOMP on top of the B200
-// host planner.  Compiled only where OMPL is installed (it is NOT in this image, so this header has
-// never been compiled here; it is the binding shown in INTEGRATION.md, kept next to the code it wraps).
+// host planner.  Compiled only where OMPL is installed.  OMPL is NOT in this image: the CPU test-suite
+// compiles this header against stand-ins of the OMPL API (tests/stubs) and drives it like an OMPL application
+// (tests/cpp/ompl_adapter_check.cpp); it has not been built against a real OMPL tree.  It is the binding shown
+// in INTEGRATION.md, kept next to the code it wraps.
 //
 // Keeps the outer contract of /root/reference/include/batching_pomp/BatchingPOMP.hpp:68-280:
 //   BatchingPOMP(const ompl::base::SpaceInformationPtr&), the seven ParamSet entries
@@ -11,6 +13,7 @@
 #if __has_include(<ompl/base/Planner.h>)
 
 #include <ompl/base/Planner.h>
+#include <ompl/base/ScopedState.h>
 #include <ompl/base/goals/GoalState.h>
 #include <ompl/base/spaces/RealVectorStateSpace.h>
 #include <ompl/geometric/PathGeometric.h>

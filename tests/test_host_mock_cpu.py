@@ -40,3 +40,22 @@ def test_host_planner_matches_oracle_planner_on_cpu(mock_dir, case):
                        env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
     assert "mock parity ok" in r.stdout
+
+
+def test_ompl_adapter_compiles_and_plans(tmp_path):
+    """batching_pomp_b200/host/ompl_adapter.hpp (the drop-in ompl::base::Planner) compiled against the OMPL API
+    stand-ins of tests/stubs and driven like an OMPL application: ParamSet by name, GraphML roadmap file,
+    ProblemDefinition + GoalState, solve(ptc), anytime solutions through addSolutionPath, ompl::Exception on a
+    bad parameter (tests/cpp/ompl_adapter_check.cpp).  Device side = the test double."""
+    exe = str(tmp_path / "ompl_adapter_check")
+    host = os.path.join(ROOT, "batching_pomp_b200", "host")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fopenmp", "-ffp-contract=off",
+                           "-I", os.path.join(ROOT, "tests", "stubs"), "-I", os.path.join(ROOT, "include"), "-I", host,
+                           os.path.join(ROOT, "tests", "cpp", "ompl_adapter_check.cpp"),
+                           os.path.join(host, "BatchingPOMP.cpp"), os.path.join(host, "graphml.cpp"),
+                           os.path.join(ROOT, "tests", "mock", "mock_cuda.cpp"),
+                           os.path.join(ROOT, "oracle", "bpomp_oracle.cpp"), "-o", exe])
+    out = subprocess.run([exe, str(tmp_path / "roadmap.graphml")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:]
+    assert "ompl adapter ok" in out.stdout
