@@ -46,6 +46,15 @@ inline double rvDistance(const double* a, const double* b, unsigned d) {
 inline double now() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
+// Every call into the device library goes through this: its wall time (launch + wait for the results) is
+// accumulated so that a run can be split into host and device shares (getDeviceTime()).
+#define BP_DEV(expr)                 \
+  do {                               \
+    const double t0_ = now();        \
+    const int rc_ = (expr);          \
+    mDeviceTime += now() - t0_;      \
+    check(rc_);                      \
+  } while (0)
 // Device contexts are recycled between planner instances of one process: the reference is
 // one-planner-per-query, and creating a context (streams, tables, world upload) costs more than a
 // short query.  A context is only reused for the same device, dimension, segment length and world.
@@ -117,7 +126,7 @@ BatchingPOMP::BatchingPOMP(const SpaceInformation& si)
       bmExhausted(false), bmCurrRadius(0.0), bmNumVerticesAdded(0), bmNextVertexTarget(0), bmVertInfl(2.0),
       bmRadiusInfl(1.0), bmInitRadius(0.0), bmMaxRadius(0.0), bmCurrVertex(0), bmEdgeMode(false), mNumSolutions(0),
       mBeliefEmpty(true), mNumEdgeChecks(0), mNumCollChecks(0), mNumSearches(0), mNumLookups(0), mLookupTime(0.0),
-      mCollCheckTime(0.0), mSearchTime(0.0) {
+      mCollCheckTime(0.0), mSearchTime(0.0), mDeviceTime(0.0), mSearchHostTime(0.0) {
   if (mDim == 0 || si.low.size() != mDim || si.high.size() != mDim)
     throw Exception("SpaceInformation: bounds must have `dim` entries");
   // mCheckRadius = 0.5*getLongestValidSegmentLength() is captured at construction (BP.cpp:241,278);
@@ -311,16 +320,16 @@ void BatchingPOMP::flushVertices() {
   uint32_t nv = (uint32_t)mOut.size();
   if (mFlushed < nv) {
     uint32_t first = 0;
-    check(bpomp_vertices_append(dev(), &mVState[(size_t)mFlushed * mDim], nv - mFlushed, &first));
+    BP_DEV(bpomp_vertices_append(dev(), &mVState[(size_t)mFlushed * mDim], nv - mFlushed, &first));
     if (first != mFlushed) throw Exception("internal: device vertex ids out of step with the roadmap");
     std::vector<uint32_t> off;
     for (uint32_t v = mFlushed; v < nv; ++v)
       if (!mNNActive[v]) off.push_back(v);
-    if (!off.empty()) check(bpomp_vertices_set_active(dev(), off.data(), (uint32_t)off.size(), 0));
+    if (!off.empty()) BP_DEV(bpomp_vertices_set_active(dev(), off.data(), (uint32_t)off.size(), 0));
     mFlushed = nv;
   }
   if (!mPendingDeactivate.empty()) {
-    check(bpomp_vertices_set_active(dev(), mPendingDeactivate.data(), (uint32_t)mPendingDeactivate.size(), 0));
+    BP_DEV(bpomp_vertices_set_active(dev(), mPendingDeactivate.data(), (uint32_t)mPendingDeactivate.size(), 0));
     mPendingDeactivate.clear();
   }
 }
@@ -422,7 +431,7 @@ void BatchingPOMP::setProblemDefinition(const std::vector<double>& start, const 
   std::vector<double> sg(start);
   sg.insert(sg.end(), goal.begin(), goal.end());
   uint8_t ok[2] = {0, 0};
-  check(bpomp_states_valid(dev(), sg.data(), 2, ok));
+  BP_DEV(bpomp_states_valid(dev(), sg.data(), 2, ok));
   if (!ok[0]) throw Exception("Start configuration is in collision!");
   mStartVertex = addVertex(start.data(), true);
   if (!ok[1]) throw Exception("Goal configuration is in collision!");
@@ -463,7 +472,7 @@ void BatchingPOMP::nextBatch() {
   auto admitRange = [&](uint32_t first, uint32_t count) {
     if (count == 0) return;
     std::vector<uint8_t> prune(count);
-    check(bpomp_states_prune(dev(), &mRoadmap[(size_t)first * mDim], count, vertexState(mStartVertex),
+    BP_DEV(bpomp_states_prune(dev(), &mRoadmap[(size_t)first * mDim], count, vertexState(mStartVertex),
                              vertexState(mGoalVertex), mBestPathCost, 1, prune.data()));
     for (uint32_t i = 0; i < count; ++i)
       if (!prune[i]) addVertex(&mRoadmap[(size_t)(first + i) * mDim], true);
@@ -516,7 +525,7 @@ void BatchingPOMP::pruneVertices(bool withValidity) {
   uint32_t nv = (uint32_t)mOut.size();
   if (nv == 0) return;
   std::vector<uint8_t> prune(nv);
-  check(bpomp_vertices_prune(dev(), mStartVertex, mGoalVertex, mBestPathCost, withValidity ? 1 : 0, prune.data()));
+  BP_DEV(bpomp_vertices_prune(dev(), mStartVertex, mGoalVertex, mBestPathCost, withValidity ? 1 : 0, prune.data()));
   for (Vertex v = 0; v < nv; ++v) {
     if (!prune[v]) continue;
     if (mNNActive[v]) {
@@ -546,16 +555,16 @@ void BatchingPOMP::prepareNeighbourCache(double radius) {
     uint32_t stride = nv / 64 ? nv / 64 : 1;
     for (uint32_t v = 0; v < nv && q.size() < 64; v += stride) q.push_back(v);
     uint64_t nnz = 0;
-    check(bpomp_neighbors_radius(dev(), q.data(), (uint32_t)q.size(), radius, &nnz));
+    BP_DEV(bpomp_neighbors_radius(dev(), q.data(), (uint32_t)q.size(), radius, &nnz));
     est = (double)nnz / (double)q.size() * (double)nactive;
   }
   if (est > (double)mCsrBudget) return;  // rows are fetched on demand instead
   uint64_t nnz = 0;
-  check(bpomp_neighbors_all(dev(), radius, &nnz));
+  BP_DEV(bpomp_neighbors_all(dev(), radius, &nnz));
   mCsrRowPtr.resize((size_t)nv + 1);
   mCsrCol.resize(nnz ? nnz : 1);
   mCsrDist.resize(nnz ? nnz : 1);
-  check(bpomp_neighbors_fetch(dev(), mCsrRowPtr.data(), mCsrCol.data(), mCsrDist.data()));
+  BP_DEV(bpomp_neighbors_fetch(dev(), mCsrRowPtr.data(), mCsrCol.data(), mCsrDist.data()));
   mCsrValid = true;
   mCsrRadius = radius;
   mCsrEdge.assign(nnz ? nnz : 1, kNoEdge);
@@ -583,11 +592,11 @@ const std::vector<std::pair<double, BatchingPOMP::Vertex>>& BatchingPOMP::neighb
   }
   flushVertices();
   uint64_t nnz = 0;
-  check(bpomp_neighbors_radius(dev(), &u, 1, radius, &nnz));
+  BP_DEV(bpomp_neighbors_radius(dev(), &u, 1, radius, &nnz));
   std::vector<uint64_t> rp(2);
   std::vector<uint32_t> col(nnz ? nnz : 1);
   std::vector<double> dist(nnz ? nnz : 1);
-  check(bpomp_neighbors_fetch(dev(), rp.data(), col.data(), dist.data()));
+  BP_DEV(bpomp_neighbors_fetch(dev(), rp.data(), col.data(), dist.data()));
   for (uint64_t k = 0; k < nnz; ++k) mRowScratch.emplace_back(dist[k], col[k]);
   return mRowScratch;
 }
@@ -600,7 +609,8 @@ void BatchingPOMP::expandVertex(Vertex u, double radius) {
   if (mExpandedStamp.size() < mOut.size()) mExpandedStamp.resize(mOut.size(), 0);
   if (mExpandedStamp[u] == bmNumBatches) return;
   mExpandedStamp[u] = bmNumBatches;
-  std::vector<Edge> created;
+  std::vector<Edge>& created = mCreatedScratch;
+  created.clear();
   auto create = [&](Vertex nbr, double dist, bool index) -> Edge {
     Edge e = addEdge(u, nbr, index);
     mEdges[e].distance = dist;  // bit-equal to vertexDistFun(source, target)
@@ -613,18 +623,37 @@ void BatchingPOMP::expandVertex(Vertex u, double radius) {
   if (mCsrValid && radius == mCsrRadius && (size_t)u + 1 < mCsrRowPtr.size() && mNNActive[u]) {
     // Cached CSR: the edge id of every (u, neighbour) pair lives in the CSR slot itself, so the existence
     // test is a sequential read instead of a hash probe; the mirror slot (neighbour's row) is set too.
-    for (uint64_t k = mCsrRowPtr[u]; k < mCsrRowPtr[u + 1]; ++k) {
+    const uint64_t rb = mCsrRowPtr[u], re = mCsrRowPtr[u + 1];
+    if (mOut[u].capacity() == 0) mOut[u].reserve((size_t)(re - rb));  // one allocation per adjacency list
+    for (uint64_t k = rb; k < re; ++k) {
       const Vertex nbr = mCsrCol[k];
       if (nbr == u || !mNNActive[nbr]) continue;  // pruned since the CSR was built
       if (mCsrEdge[k] != kNoEdge) continue;
       Edge e = mCsrOlderEdges ? findEdge(u, nbr) : kNoEdge;  // created before this CSR existed?
-      if (e == kNoEdge) e = create(nbr, mCsrDist[k], false);
+      if (e == kNoEdge) {
+        if (mOut[nbr].capacity() == 0) mOut[nbr].reserve((size_t)(mCsrRowPtr[nbr + 1] - mCsrRowPtr[nbr]));
+        e = create(nbr, mCsrDist[k], false);
+      }
       mCsrEdge[k] = e;
-      for (uint64_t k2 = mCsrRowPtr[nbr]; k2 < mCsrRowPtr[nbr + 1]; ++k2)
+      // mirror slot: rows are sorted by (distance, id) and distance(u, nbr) == distance(nbr, u) bit for bit,
+      // so u sits in nbr's row at the first entry with this distance (then among the ties)
+      const double* db = mCsrDist.data() + mCsrRowPtr[nbr];
+      const double* de = mCsrDist.data() + mCsrRowPtr[nbr + 1];
+      bool mirrored = false;
+      for (uint64_t k2 = (uint64_t)(std::lower_bound(db, de, mCsrDist[k]) - mCsrDist.data());
+           k2 < mCsrRowPtr[nbr + 1] && mCsrDist[k2] == mCsrDist[k]; ++k2)
         if (mCsrCol[k2] == u) {
           mCsrEdge[k2] = e;
+          mirrored = true;
           break;
         }
+      if (!mirrored) {  // not reached for rows in (distance, id) order; kept so that a slot is never missed
+        for (uint64_t k2 = mCsrRowPtr[nbr]; k2 < mCsrRowPtr[nbr + 1]; ++k2)
+          if (mCsrCol[k2] == u) {
+            mCsrEdge[k2] = e;
+            break;
+          }
+      }
     }
   } else {
     const auto& row = neighbourRow(u, radius);
@@ -678,7 +707,7 @@ void BatchingPOMP::computeCreatedEdgeProbabilities(Vertex u, const std::vector<E
     const size_t kSpecEdges = std::min<size_t>(262144, std::max<size_t>(512, mSearchEdgesNeeded / 2));
     size_t taken = 0;
     for (size_t h = 0; h < mHeap.size() && taken < kSpecVertices && from.size() < nreal + kSpecEdges; ++h) {
-      Vertex v = mHeap[h];
+      Vertex v = mHeap[h].v;
       if (v == u || mSpecStamp[v] == mEpoch || !mNNActive[v] || v + 1 >= mCsrRowPtr.size()) continue;
       mSpecStamp[v] = mEpoch;
       ++taken;
@@ -699,7 +728,7 @@ void BatchingPOMP::computeCreatedEdgeProbabilities(Vertex u, const std::vector<E
     std::vector<uint32_t> nl(from.size());
     std::vector<double> pf(from.size());
     flushVertices();
-    check(bpomp_belief_edge_pfree_indexed(dev(), from.data(), to.data(), (int64_t)from.size(), pf.data(), nl.data()));
+    BP_DEV(bpomp_belief_edge_pfree_indexed(dev(), from.data(), to.data(), (int64_t)from.size(), pf.data(), nl.data()));
     for (size_t i = 0; i < nreal; ++i) {
       setProbFree(mEdges[miss[i]], pf[i]);
       mNumLookups += nl[i];
@@ -748,7 +777,7 @@ void BatchingPOMP::computeFreeProbabilities(const std::vector<Edge>& edges) {
       to[i] = mEdges[edges[i]].target;
     }
     flushVertices();
-    check(bpomp_belief_edge_pfree_indexed(dev(), from.data(), to.data(), (int64_t)edges.size(), pf.data(), nl.data()));
+    BP_DEV(bpomp_belief_edge_pfree_indexed(dev(), from.data(), to.data(), (int64_t)edges.size(), pf.data(), nl.data()));
     for (size_t i = 0; i < edges.size(); ++i) {
       setProbFree(mEdges[edges[i]], pf[i]);
       mNumLookups += nl[i];
@@ -797,7 +826,7 @@ bool BatchingPOMP::checkAndUpdatePathBlocked(const std::vector<Edge>& ePath) {
     to[i] = mEdges[unknown[i]].target;
   }
   flushVertices();
-  check(bpomp_edges_check_indexed(dev(), from.data(), to.data(), (int64_t)m, valid.data(), first.data(), ns.data()));
+  BP_DEV(bpomp_edges_check_indexed(dev(), from.data(), to.data(), (int64_t)m, valid.data(), first.data(), ns.data()));
   bool pathBlocked = false;
   size_t committed = 0;
   for (size_t i = 0; i < m; ++i) {
@@ -835,7 +864,7 @@ bool BatchingPOMP::checkAndUpdatePathBlocked(const std::vector<Edge>& ePath) {
     added += valid[i] ? ns[i] - 2u : (uint32_t)first[i];
   }
   if (added > 0) {
-    check(bpomp_belief_append_checked(dev(), fs.data(), ts.data(), first.data(), (int64_t)committed));
+    BP_DEV(bpomp_belief_append_checked(dev(), fs.data(), ts.data(), first.data(), (int64_t)committed));
     mBeliefEmpty = false;
   }
   mCollCheckTime += now() - t0;
@@ -871,25 +900,26 @@ double BatchingPOMP::edgeWeight(Edge e) const {
 // sifts down choosing the first strictly-smallest child.
 // ---------------------------------------------------------------------------
 void BatchingPOMP::touch(Vertex v) {
-  if (mStamp[v] != mEpoch) {  // lazily applies astar_search's initialisation loop to v
-    mStamp[v] = mEpoch;
-    mDist[v] = kInf;
-    mCost[v] = kInf;
-    mPred[v] = v;
-    mColor[v] = 0;
-    mHeapIndex[v] = -1;
+  SearchNode& n = mNode[v];
+  if (n.stamp != mEpoch) {  // lazily applies astar_search's initialisation loop to v
+    n.stamp = mEpoch;
+    n.dist = kInf;
+    n.cost = kInf;
+    n.pred = v;
+    n.color = 0;
+    n.heapIndex = 0xffffffffu;
   }
 }
 
 void BatchingPOMP::heapUp(size_t index) {
+  const HeapEntry moving{mNode[mHeap[index].v].cost, mHeap[index].v};  // refreshes the key after a decrease
+  mHeap[index].key = moving.key;
   if (index == 0) return;
   size_t orig = index, moved = 0;
-  Vertex moving = mHeap[index];
-  double key = mCost[moving];
   for (;;) {
     if (index == 0) break;
     size_t parent = (index - 1) / 4;
-    if (key < mCost[mHeap[parent]]) {
+    if (moving.key < mHeap[parent].key) {
       ++moved;
       index = parent;
       continue;
@@ -899,33 +929,32 @@ void BatchingPOMP::heapUp(size_t index) {
   index = orig;
   for (size_t i = 0; i < moved; ++i) {
     size_t parent = (index - 1) / 4;
-    Vertex pv = mHeap[parent];
-    mHeapIndex[pv] = (int64_t)index;
-    mHeap[index] = pv;
+    mHeap[index] = mHeap[parent];
+    mNode[mHeap[index].v].heapIndex = (uint32_t)index;
     index = parent;
   }
   mHeap[index] = moving;
-  mHeapIndex[moving] = (int64_t)index;
+  mNode[moving.v].heapIndex = (uint32_t)index;
 }
 
 void BatchingPOMP::heapPush(Vertex v) {
-  mHeap.push_back(v);
-  mHeapIndex[v] = (int64_t)mHeap.size() - 1;
+  mHeap.push_back(HeapEntry{mNode[v].cost, v});
+  mNode[v].heapIndex = (uint32_t)(mHeap.size() - 1);
   heapUp(mHeap.size() - 1);
 }
 
 void BatchingPOMP::heapDown() {
   if (mHeap.empty()) return;
   size_t index = 0, size = mHeap.size();
-  double key = mCost[mHeap[0]];
+  const double key = mHeap[0].key;
   for (;;) {
     size_t firstChild = 4 * index + 1;
     if (firstChild >= size) break;
     size_t nchild = std::min<size_t>(4, size - firstChild);
     size_t best = 0;
-    double bestKey = mCost[mHeap[firstChild]];
+    double bestKey = mHeap[firstChild].key;
     for (size_t i = 1; i < nchild; ++i) {
-      double k = mCost[mHeap[firstChild + i]];
+      double k = mHeap[firstChild + i].key;
       if (k < bestKey) {
         best = i;
         bestKey = k;
@@ -934,8 +963,8 @@ void BatchingPOMP::heapDown() {
     if (bestKey < key) {
       size_t c = firstChild + best;
       std::swap(mHeap[c], mHeap[index]);
-      mHeapIndex[mHeap[c]] = (int64_t)c;
-      mHeapIndex[mHeap[index]] = (int64_t)index;
+      mNode[mHeap[c].v].heapIndex = (uint32_t)c;
+      mNode[mHeap[index].v].heapIndex = (uint32_t)index;
       index = c;
       continue;
     }
@@ -944,10 +973,10 @@ void BatchingPOMP::heapDown() {
 }
 
 void BatchingPOMP::heapPop() {
-  mHeapIndex[mHeap[0]] = -1;
+  mNode[mHeap[0].v].heapIndex = 0xffffffffu;
   if (mHeap.size() != 1) {
     mHeap[0] = mHeap.back();
-    mHeapIndex[mHeap[0]] = 0;
+    mNode[mHeap[0].v].heapIndex = 0;
     mHeap.pop_back();
     heapDown();
   } else {
@@ -959,16 +988,9 @@ void BatchingPOMP::heapPop() {
 // BP.cpp:860-924, 88-175; semantics in SURVEY.md A.4.  Returns true when the goal is popped.
 bool BatchingPOMP::astar(bool zeroHeuristic, bool single) {
   size_t nv = mOut.size();
-  if (mStamp.size() < nv) {
-    mStamp.resize(nv, 0);
-    mDist.resize(nv);
-    mCost.resize(nv);
-    mPred.resize(nv);
-    mColor.resize(nv);
-    mHeapIndex.resize(nv);
-  }
+  if (mNode.size() < nv) mNode.resize(nv, SearchNode{0.0, 0.0, 0u, 0u, 0u, 0});
   if (++mEpoch == 0) {  // stamp wrap-around
-    std::fill(mStamp.begin(), mStamp.end(), 0);
+    for (SearchNode& n : mNode) n.stamp = 0;
     std::fill(mSpecStamp.begin(), mSpecStamp.end(), 0);
     mEpoch = 1;
   }
@@ -985,12 +1007,12 @@ bool BatchingPOMP::astar(bool zeroHeuristic, bool single) {
   const double radius = bmCurrRadius;  // captured when the visitor is built, BP.cpp:904
   Vertex s = mStartVertex;
   touch(s);
-  mDist[s] = 0.0;
-  mCost[s] = h(s);
-  mColor[s] = 1;
+  mNode[s].dist = 0.0;
+  mNode[s].cost = h(s);
+  mNode[s].color = 1;
   heapPush(s);
   while (!mHeap.empty()) {
-    Vertex u = mHeap[0];
+    Vertex u = mHeap[0].v;
     heapPop();
     if (u == mGoalVertex) return true;  // examine_vertex throws, BP.cpp:104-106 / 145-147
     if (single) refreshOutEdgeProbabilities(u);
@@ -1002,32 +1024,33 @@ bool BatchingPOMP::astar(bool zeroHeuristic, bool single) {
       double w_e = edgeWeight(eid);
       if (w_e < 0.0) throw Exception("negative edge weight");  // boost::negative_edge
       touch(v);
-      double d_u = mDist[u], d_v = mDist[v];
+      SearchNode& nv_ = mNode[v];
+      double d_u = mNode[u].dist, d_v = nv_.dist;
       bool decreased = false;
       double cand = closedPlus(d_u, w_e);
       if (cand < d_v) {  // relax_target
-        mDist[v] = cand;
-        mPred[v] = u;
+        nv_.dist = cand;
+        nv_.pred = u;
         decreased = true;
       }
-      if (mColor[v] == 0) {  // tree_edge: pushed even if the relaxation failed
-        if (decreased) mCost[v] = closedPlus(mDist[v], h(v));
-        mColor[v] = 1;
+      if (nv_.color == 0) {  // tree_edge: pushed even if the relaxation failed
+        if (decreased) nv_.cost = closedPlus(nv_.dist, h(v));
+        nv_.color = 1;
         heapPush(v);
-      } else if (mColor[v] == 1) {  // gray_target
+      } else if (nv_.color == 1) {  // gray_target
         if (decreased) {
-          mCost[v] = closedPlus(mDist[v], h(v));
-          heapUp((size_t)mHeapIndex[v]);
+          nv_.cost = closedPlus(nv_.dist, h(v));
+          heapUp((size_t)nv_.heapIndex);
         }
       } else {  // black_target: re-open
         if (decreased) {
-          mCost[v] = closedPlus(mDist[v], h(v));
+          nv_.cost = closedPlus(nv_.dist, h(v));
           heapPush(v);
-          mColor[v] = 1;
+          nv_.color = 1;
         }
       }
     }
-    mColor[u] = 2;
+    mNode[u].color = 2;
   }
   return false;
 }
@@ -1060,11 +1083,14 @@ PlannerStatus BatchingPOMP::solve(const PlannerTerminationCondition& ptc) {
     bool zeroH = mIsInitSearchBatch;
     mIsInitSearchBatch = false;
     double t0 = now();
+    const double dev0 = mDeviceTime;
     astar(zeroH, mBatchingType == "single");
-    if (mBatchingType != "single") mSearchTime += now() - t0;
+    const double dt = now() - t0;
+    if (mBatchingType != "single") mSearchTime += dt;
+    mSearchHostTime += dt - (mDeviceTime - dev0);
 
     touch(mGoalVertex);
-    if (mDist[mGoalVertex] == kInf) {
+    if (mNode[mGoalVertex].dist == kInf) {
       if (bmExhausted) {
         if (mBestPathCost < kInf) return PlannerStatus::EXACT_SOLUTION;
         return PlannerStatus::TIMEOUT;
@@ -1078,7 +1104,7 @@ PlannerStatus BatchingPOMP::solve(const PlannerTerminationCondition& ptc) {
     ePath.clear();
     vPath.clear();
     while (vWalk != mStartVertex) {
-      Vertex vPred = mPred[vWalk];
+      Vertex vPred = mNode[vWalk].pred;
       Edge e = findEdge(vPred, vWalk);
       if (e == (Edge)-1) throw Exception("Error! Edge present during search no longer exists in graph!");
       ePath.push_back(e);

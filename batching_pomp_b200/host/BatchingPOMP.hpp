@@ -123,6 +123,11 @@ public:
   double getLookupTime() const { return mLookupTime; }
   double getSearchTime() const { return mSearchTime; }
   double getCollCheckTime() const { return mCollCheckTime; }
+  /// Wall time spent inside calls of the device library (not in the reference; the three times above
+  /// include it where those calls are made from).
+  double getDeviceTime() const { return mDeviceTime; }
+  /// Wall time of the searches (astar, including edge creation) outside the device library.
+  double getSearchHostTime() const { return mSearchHostTime; }
 
   // ---- OMPL required methods, BatchingPOMP.hpp:203-205 ----
   void setup();
@@ -223,14 +228,26 @@ private:
   Edge mHashedUpTo;                            // edges [0, mHashedUpTo) are in mEdgeIndex
 
   // ---- search state: flat arrays + epoch stamps instead of four std::map (BP.cpp:860-863) ----
-  std::vector<double> mDist, mCost;
-  std::vector<Vertex> mPred;
-  std::vector<uint8_t> mColor;
-  std::vector<int64_t> mHeapIndex;
-  std::vector<uint32_t> mStamp;
+  // One 32-byte record per vertex (distance, f-cost, predecessor, colour, heap position, epoch stamp): a
+  // relaxation touches one cache line of search state instead of six arrays.
+  struct SearchNode {
+    double dist, cost;
+    uint32_t stamp;
+    Vertex pred;
+    uint32_t heapIndex;
+    uint8_t color;  // 0 white, 1 gray, 2 black
+  };
+  std::vector<SearchNode> mNode;
+  std::vector<Edge> mCreatedScratch;  // edges created by the current expansion
   uint32_t mEpoch;
   size_t mSearchEdgesNeeded;  // created edges of the current search whose probFree had to be computed
-  std::vector<Vertex> mHeap;
+  // The heap stores the key beside the vertex (always equal to mNode[v].cost: keys only change through
+  // heapUp after a decrease), so sifting compares within the heap array instead of chasing mNode[...].cost.
+  struct HeapEntry {
+    double key;
+    Vertex v;
+  };
+  std::vector<HeapEntry> mHeap;
   void touch(Vertex v);
   void heapPush(Vertex v);
   void heapUp(size_t index);
@@ -270,6 +287,7 @@ private:
   bool mBeliefEmpty;
   unsigned int mNumEdgeChecks, mNumCollChecks, mNumSearches, mNumLookups;
   double mLookupTime, mCollCheckTime, mSearchTime;
+  double mDeviceTime, mSearchHostTime;
 };
 
 }  // namespace batching_pomp

@@ -157,6 +157,8 @@ extern "C" void bpomp_planner_counters(const bpomp_planner* p, uint32_t* out4, d
   }
 }
 
+extern "C" double bpomp_planner_device_seconds(const bpomp_planner* p) { return p->planner->getDeviceTime(); }
+
 extern "C" uint64_t bpomp_planner_num_vertices(const bpomp_planner* p) { return p->planner->numVertices(); }
 extern "C" uint64_t bpomp_planner_num_edges(const bpomp_planner* p) { return p->planner->numEdges(); }
 extern "C" uint64_t bpomp_planner_gpu_launches(const bpomp_planner* p) {

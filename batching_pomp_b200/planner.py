@@ -35,6 +35,7 @@ SIGNATURES = {
     "bpomp_planner_path": (C.c_int, [vp, vp, C.c_int]),
     "bpomp_planner_vertex_state": (C.c_int, [vp, C.c_uint32, vp]),
     "bpomp_planner_counters": (None, [vp, vp, vp]),
+    "bpomp_planner_device_seconds": (C.c_double, [vp]),
     "bpomp_planner_num_vertices": (C.c_uint64, [vp]),
     "bpomp_planner_num_edges": (C.c_uint64, [vp]),
     "bpomp_planner_gpu_launches": (C.c_uint64, [vp]),
@@ -184,7 +185,8 @@ class Planner:
         c = np.zeros(4, dtype=np.uint32)
         t = np.zeros(3, dtype=np.float64)
         self.lib.bpomp_planner_counters(self.h, _p(c), _p(t))
-        return {"lookup_s": float(t[0]), "search_s": float(t[1]), "collcheck_s": float(t[2])}
+        return {"lookup_s": float(t[0]), "search_s": float(t[1]), "collcheck_s": float(t[2]),
+                "device_s": float(self.lib.bpomp_planner_device_seconds(self.h))}
 
     @property
     def num_vertices(self):

@@ -61,6 +61,9 @@ BPOMP_PAPI int bpomp_planner_vertex_state(const bpomp_planner* p, uint32_t v, do
 /* out[0..3] = numEdgeChecks, numCollChecks, numSearches, numLookups; times[0..2] = lookup, search,
  * collision-check seconds */
 BPOMP_PAPI void bpomp_planner_counters(const bpomp_planner* p, uint32_t* out4, double* times3);
+/* Wall seconds spent inside calls of the device library (launch + wait); the host share of a run is its
+ * wall time minus this. */
+BPOMP_PAPI double bpomp_planner_device_seconds(const bpomp_planner* p);
 BPOMP_PAPI uint64_t bpomp_planner_num_vertices(const bpomp_planner* p);
 BPOMP_PAPI uint64_t bpomp_planner_num_edges(const bpomp_planner* p);
 BPOMP_PAPI uint64_t bpomp_planner_gpu_launches(const bpomp_planner* p);

@@ -65,5 +65,7 @@ int main(int argc, char** argv) {
   double total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   printf("total %.2fs, searches %u, search_s %.2f lookup_s %.2f collcheck_s %.2f, vertices %zu edges %zu\n", total,
          p.getNumSearches(), p.getSearchTime(), p.getLookupTime(), p.getCollCheckTime(), p.numVertices(), p.numEdges());
+  printf("device(double)_s %.3f  host_s %.3f  search_host_s %.3f = %.2f ms per search\n", p.getDeviceTime(),
+         total - p.getDeviceTime(), p.getSearchHostTime(), 1e3 * p.getSearchHostTime() / p.getNumSearches());
   return 0;
 }
