@@ -42,6 +42,18 @@ def test_host_planner_matches_oracle_planner_on_cpu(mock_dir, case):
     assert "mock parity ok" in r.stdout
 
 
+def test_host_planner_fuzz_against_oracle_planner(mock_dir):
+    """40 random configurations (dimension, roadmap size, world, batching / graph / selector types, increment,
+    prune threshold, search budget) — tests/mock/planner_fuzz_worker.py; 200 seeds pass when run by hand."""
+    env = dict(os.environ)
+    env["BPOMP_HOST_LIB"] = os.path.join(mock_dir, "libbpomp_host.so")
+    env.pop("BPOMP_CUDA_LIB", None)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock", "planner_fuzz_worker.py"), "1", "40"],
+                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "mock fuzz ok" in r.stdout
+
+
 def test_ompl_adapter_compiles_and_plans(tmp_path):
     """batching_pomp_b200/host/ompl_adapter.hpp (the drop-in ompl::base::Planner) compiled against the OMPL API
     stand-ins of tests/stubs and driven like an OMPL application: ParamSet by name, GraphML roadmap file,
