@@ -50,6 +50,8 @@ extern "C" int bpomp_belief_clear(bpomp_ctx* ctx) {
 
 static int belief_grow(bpomp_ctx* ctx, uint64_t extra) {
   uint64_t need = ctx->bel_count + extra;
+  // insertion indices are 32-bit in the kNN lists (0xFFFFFFFF marks an empty entry)
+  if (need >= 0xFFFFFFFFull) return bp_fail(ctx, BPOMP_ERR_RANGE, "belief model is limited to 2^32-2 points");
   BP_TRY(bp_reserve(ctx, ctx->d_bel_pts, (size_t)need * ctx->dim * sizeof(double), true));
   BP_TRY(bp_reserve(ctx, ctx->d_bel_vals, (size_t)need * sizeof(double), true));
   return BPOMP_OK;
