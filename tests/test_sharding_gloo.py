@@ -96,6 +96,84 @@ def test_packed_status_merge_layout(per_rank):
     np.testing.assert_array_equal(out, want)
 
 
+class _OracleCtx:
+    """Stand-in for capi.Context in the gloo tests: the same method names and return shapes, answered by the
+    CPU oracle (there is no GPU here; on a GPU box the sharded helpers are given a real Context)."""
+
+    def __init__(self, orc, d, L, lo, hi, verts, bel_pts, bel_vals):
+        self.orc, self.d, self.L, self.lo, self.hi = orc, d, L, lo, hi
+        self.verts, self.bel_pts, self.bel_vals = verts, bel_pts, bel_vals
+
+    def neighbors_radius(self, query_ids, r):
+        return self.orc.neighbors_radius(self.verts, np.asarray(query_ids, dtype=np.uint32), r)
+
+    def belief_estimate(self, queries):
+        return self.orc.belief_estimate(self.bel_pts, self.bel_vals, queries)
+
+    def edges_check(self, frm, to):
+        return self.orc.edges_check_boxes(frm, to, self.L, self.lo, self.hi)
+
+
+def _sharded_ops_inputs():
+    from batching_pomp_b200 import workloads
+    d = 3
+    L = workloads.segment_length(d)
+    lo, hi = workloads.box_world(d, 40, seed=3)
+    verts = workloads.halton(700, d)
+    bel_pts = workloads.uniform(21, (900, d))
+    bel_vals = (workloads.uniform(22, (900,)) < 0.3).astype(np.float64)
+    queries = workloads.uniform(23, (333, d))
+    qids = np.arange(0, 700, 3, dtype=np.uint32)  # 234 queries: not divisible by 4
+    frm, to = workloads.random_edges(1001, d, seed=24, max_len=0.4)
+    return d, L, lo, hi, verts, bel_pts, bel_vals, queries, qids, frm, to
+
+
+def _sharded_ops_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from batching_pomp_b200 import sharding
+    from oracle import oracle
+    d, L, lo, hi, verts, bel_pts, bel_vals, queries, qids, frm, to = _sharded_ops_inputs()
+    ctx = _OracleCtx(oracle, d, L, lo, hi, verts, bel_pts, bel_vals)
+    rp, col, dst = sharding.neighbors_radius_sharded(ctx, qids, 0.2)
+    est = sharding.belief_estimate_sharded(ctx, queries)
+    v, fi, ns = sharding.edges_check_sharded(ctx, frm, to)
+    empty = sharding.belief_estimate_sharded(ctx, queries[:1])  # fewer units than ranks: empty shards
+    if rank == world - 1:  # any rank holds the complete result
+        q.put((rp, col, dst, est, v, fi, ns, empty))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_neighbours_belief_edges_equal_unsharded(orc, world):
+    """SURVEY §8e: query vertices, belief queries and edges sharded over the ranks, results all-gathered;
+    every rank must end with exactly the unsharded result (world sizes 2 and 3, ragged shards)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_ops_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    rp, col, dst, est, v, fi, ns, empty = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    d, L, lo, hi, verts, bel_pts, bel_vals, queries, qids, frm, to = _sharded_ops_inputs()
+    rp0, col0, dst0 = orc.neighbors_radius(verts, qids, 0.2)
+    np.testing.assert_array_equal(rp, rp0)
+    np.testing.assert_array_equal(col, col0)
+    np.testing.assert_array_equal(dst, dst0)
+    np.testing.assert_array_equal(est, orc.belief_estimate(bel_pts, bel_vals, queries))
+    v0, fi0, ns0 = orc.edges_check_boxes(frm, to, L, lo, hi)
+    np.testing.assert_array_equal(v, v0)
+    np.testing.assert_array_equal(fi, fi0)
+    np.testing.assert_array_equal(ns, ns0)
+    np.testing.assert_array_equal(empty, orc.belief_estimate(bel_pts, bel_vals, queries[:1]))
+
+
 @pytest.mark.parametrize("count", [4000, 4001])
 def test_sharded_edge_check_merges_to_unsharded(orc, count):
     from batching_pomp_b200 import workloads
