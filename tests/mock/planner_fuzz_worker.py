@@ -39,11 +39,27 @@ def one(seed):
         fraction = float(rng.choice([5e-3, 1e-2, 2e-2]))
     start = np.full(d, 0.1)
     goal = np.full(d, 0.9)
-    op, gp = _make(orc, wl, d, N, world, params, fraction, None, None)
+    single = d <= 3 and rng.random() < 0.2
+    edges = graphml = None
+    tmp = None
+    if single:  # the roadmap file carries the edges (SingleBatching.hpp:55-91); start/goal linked within a radius
+        import tempfile
+        roadmap = wl.halton(N, d)
+        r = float(rng.choice([1.5, 2.0, 3.0])) * wl.halton_radius(N, d)
+        diff = roadmap[:, None, :] - roadmap[None, :, :]
+        iu, ju = np.nonzero(np.triu(np.sqrt((diff ** 2).sum(-1)) <= r, 1))
+        edges = np.stack([iu, ju], 1).astype(np.uint32)
+        params = {"batching_type": "single", "start_goal_radius": r, "increment": params["increment"]}
+        tmp = tempfile.TemporaryDirectory()
+        graphml = os.path.join(tmp.name, "roadmap.graphml")
+    op, gp = _make(orc, wl, d, N, world, params, fraction, None, None, edges=edges, graphml=graphml)
     try:
-        nsol = _run_both(op, gp, start, goal, False, max_calls=25, budget=int(rng.integers(20, 90)))
+        nsol = _run_both(op, gp, start, goal, single, max_calls=25, budget=int(rng.integers(20, 90)))
     except AssertionError as e:
         raise AssertionError("seed %d (%s, d=%d, N=%d): %s" % (seed, params, d, N, e))
+    finally:
+        if tmp is not None:
+            tmp.cleanup()
     return nsol
 
 
