@@ -293,7 +293,9 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
 #pragma unroll
     for (int j = 0; j < D; ++j) t[j] = __dsub_rn(t[j], f[j]);  // interpolate: (to - from); t now holds it
     const uint32_t cnt = need ? n - 2u : 0u;                    // slots 1..n-2, BP.cpp:510
-    const int ncl = nc > EC_MAXCAND ? -1 : nc;                  // -1: list overflow -> test every box
+    // -1: list overflow -> test every box; the list holds 16-bit ids, so worlds with more boxes than that
+    // always take the every-box path
+    const int ncl = (nc > EC_MAXCAND || w.nboxes > 65536) ? -1 : nc;
     ws->first[lane] = 0x7fffffff;
     uint32_t incl = cnt;
 #pragma unroll

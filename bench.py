@@ -38,6 +38,7 @@ NBOXES = 500
 ALGO_BYTES_PER_EDGE = 2 * DIM * 8 + 1 + 4
 METRIC = "edge_checks_per_s"
 UNIT = "edges/s"
+KERNEL_TAG = "r2-fast-v7"  # must match profiles/edge_check_traffic.json (re-captured whenever the kernel changes)
 
 
 def make_workload(edges, seed=4):
@@ -79,9 +80,10 @@ def cpu_baseline_run(L, lo, hi, frm, to, target_s=12.0, steps=1, warmup=0):
     per_step = target_s / max(steps + warmup, 1)
     sample = int(min(frm.shape[0], max(probe, probe * per_step / dt)))
     times = []
+    outputs = None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        oracle.edges_check_boxes(frm[:sample], to[:sample], L, lo, hi, nthreads=cores)
+        outputs = oracle.edges_check_boxes(frm[:sample], to[:sample], L, lo, hi, nthreads=cores)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     total = sum(times)
@@ -93,7 +95,25 @@ def cpu_baseline_run(L, lo, hi, frm, to, target_s=12.0, steps=1, warmup=0):
     return {"value": sample * len(times) / total, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "first %d edges of the same batch, %d timed pass(es), OpenMP over edges; "
                       "single-thread: %.4g edges/s" % (sample, len(times), v1),
-            "single_thread_value": v1, "ms_per_step": 1e3 * total / len(times)}
+            "single_thread_value": v1, "ms_per_step": 1e3 * total / len(times),
+            "outputs": outputs, "sample_edges": sample}
+
+
+def parity_check(tag, got, want):
+    """In-run parity gate: the GPU's (valid, first_invalid_slot, nstates) of the first len(want[0]) edges must be
+    bit-equal to the oracle's.  A mismatch aborts the run (exit code 3) before any number is printed."""
+    names = ("valid", "first_invalid_slot", "nstates")
+    m = len(want[0])
+    for name, g, w in zip(names, got, want):
+        g = np.asarray(g[:m]).astype(np.int64)
+        w = np.asarray(w).astype(np.int64)
+        if not np.array_equal(g, w):
+            bad = int(np.nonzero(g != w)[0][0])
+            sys.stderr.write("PARITY FAILURE (%s): %s differs from the CPU oracle at edge %d: gpu %d, oracle %d "
+                             "(%d of %d differ)\n" % (tag, name, bad, g[bad], w[bad], int((g != w).sum()), m))
+            sys.stderr.flush()
+            os._exit(3)
+    return m
 
 
 def run_reference(args):
@@ -323,15 +343,34 @@ def run_gpu(args):
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         achieved = ALGO_BYTES_PER_EDGE * edges_per_launch / (avg_launch_ms * 1e-3) / 1e9
-        traffic = None
+        # DRAM bytes per launch of the timed kernel come from the committed `ncu --set full` capture of this
+        # same kernel (a profiler cannot run inside a timed bench); the record names the kernel and capture it
+        # belongs to, and is ignored (traffic = null) if it was taken for a different kernel build.
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "edge_check_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+                rec = json.load(open(tpath))
+                if rec.get("kernel_tag") == KERNEL_TAG and int(rec.get("edges_per_launch", 0)) == int(edges_per_launch):
+                    traffic = rec.get("dram_bytes_per_launch")
+                    traffic_src = "profiles/%s (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)" % rec.get("source", "?")
+                else:
+                    traffic_src = "no ncu capture of kernel build '%s' at %d edges/launch committed" % (KERNEL_TAG, int(edges_per_launch))
             except Exception:
                 traffic = None
         # the CPU baseline is timed on rank 0 of the single-GPU run only (multi-GPU runs stay short)
         cb = cpu_baseline_run(L, lo, hi, frm, to, target_s=12.0) if (not args.no_cpu and world == 1) else None
+        # parity gate: the oracle outputs of the cpu_baseline sample (or, without that leg, of a short oracle
+        # pass) against what the device-resident step and the end-to-end call produced in this very run
+        if cb:
+            want = cb["outputs"]
+        else:
+            from oracle import oracle
+            m = min(E, 200000)
+            want = oracle.edges_check_boxes(frm[:m], to[:m], L, lo, hi, nthreads=len(os.sched_getaffinity(0)))
+        ns_dev = d_ns.cpu().numpy().view(np.uint32)
+        checked = parity_check("device-resident step", (d_valid[0].cpu().numpy(), d_first[0].cpu().numpy(), ns_dev), want)
+        parity_check("end-to-end call", (v_np, fi_np, ns_dev), want)
         value = world * E * args.steps / (elapsed_ms * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -344,7 +383,7 @@ def run_gpu(args):
                           "owner, which replays the belief inserts") if world > 1 else "none (single GPU)"}),
             "kernel_ms_per_step": kern_ms_per_step,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_edge": ALGO_BYTES_PER_EDGE,
                          "kernel": "edge_check_boxes_kernel<7,false,true,4>", "avg_launch_ms": avg_launch_ms,
                          "note": "shared-memory / latency bound well before HBM (DESIGN.md 4.1): smem wavefronts 74% of peak, issue slots 56%"},
@@ -355,6 +394,9 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "blocked_fraction": float((fi_np >= 1).mean()),
+            "parity_checked_edges": int(checked),
+            "parity": "valid, first_invalid_slot and nstates of the first %d edges bit-equal to the CPU oracle, "
+                      "device-resident step and end-to-end call, checked in this run before printing" % checked,
         }
         if cb:
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -464,8 +464,10 @@ def test_edge_status_pack_unpack(capi, count, shift):
     ctx.close()
 
 
-def test_full_size_properties_config4(capi, wl):
-    """BASELINE config 4 at full size (10^7 edges, 7-DoF, 500 boxes): size-independent properties.
+def test_full_size_config4_against_oracle(capi, orc, wl):
+    """BASELINE config 4 at full size (10^7 edges, 7-DoF, 500 boxes), the workload bench.py times:
+    every edge's nStates, validity flag and first-invalid slot bit-equal to the CPU oracle (the oracle needs a
+    few seconds on all host cores), plus size-independent properties:
     (a) a chunked evaluation equals the one-shot evaluation; (b) an edge is BLOCKED iff its first
     invalid slot is in 1..n-2; (c) the state at the reported slot is invalid and every earlier slot
     state is valid (checked through the independent batched isValid kernel on a sample)."""
@@ -474,6 +476,24 @@ def test_full_size_properties_config4(capi, wl):
     ctx, L, lo, hi = _ctx_boxes(capi, wl, d, 500, seed=3)
     frm, to = wl.random_edges(count, d, seed=4, max_len=wl.halton_radius(10 ** 6, d))
     v, f, n = ctx.edges_check(frm, to)
+    ov, of, on = orc.edges_check_boxes(frm, to, L, lo, hi, nthreads=orc.max_threads())
+    np.testing.assert_array_equal(n, on)
+    np.testing.assert_array_equal(v, ov)
+    np.testing.assert_array_equal(f, of)
+    # the device-pointer entry point bench.py's `value` times, on the same batch
+    import torch
+    dev = torch.device("cuda:0")
+    tf, tt = torch.from_numpy(frm).to(dev), torch.from_numpy(to).to(dev)
+    tv = torch.empty(count, dtype=torch.uint8, device=dev)
+    tfi = torch.empty(count, dtype=torch.int32, device=dev)
+    tn = torch.empty(count, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    ctx.edges_check_dev(tf.data_ptr(), tt.data_ptr(), count, tv.data_ptr(), tfi.data_ptr(), tn.data_ptr())
+    ctx.sync()
+    np.testing.assert_array_equal(tv.cpu().numpy(), ov)
+    np.testing.assert_array_equal(tfi.cpu().numpy(), of)
+    np.testing.assert_array_equal(tn.cpu().numpy().view(np.uint32), on)
+    del tf, tt, tv, tfi, tn
     assert np.all((v == 0) == (f >= 1))
     assert np.all(f[v == 0] <= n[v == 0].astype(np.int64) - 2)
     assert np.all(n >= 2) and n.max() <= 13
@@ -491,4 +511,63 @@ def test_full_size_properties_config4(capi, wl):
     assert ctx.states_valid(np.array(slot_states)).sum() == 0
     if prev_states:
         assert ctx.states_valid(np.array(prev_states)).all()
+    ctx.close()
+
+
+def test_full_size_config3_csr_edges_indexed_against_oracle(capi, orc, wl):
+    """The planner's real edge path at BASELINE config 3 size: r-disk rows of the 10^6-vertex 7-D Halton
+    roadmap (r = haltonRadius) turned into indexed edges (source = the expanded vertex, BP.cpp:162-165),
+    checked against the 500-box world through the indexed entry point, bit-equal to the oracle on the
+    gathered endpoints."""
+    d, N = 7, 10 ** 6
+    verts = wl.halton(N, d)
+    r = wl.halton_radius(N, d)
+    ctx, L, lo, hi = _ctx_boxes(capi, wl, d, 500, seed=3)
+    ctx.vertices_append(verts)
+    nq = 1024
+    q = (np.arange(nq, dtype=np.uint64) * (N // nq)).astype(np.uint32)
+    rp, col, dist = ctx.neighbors_radius(q, r)
+    lens = np.diff(rp.astype(np.int64))
+    fi = np.repeat(q, lens)
+    keep = fi != col
+    fi, ti = fi[keep], col[keep]
+    assert fi.size > 10 ** 6
+    v, f, n = ctx.edges_check_indexed(fi, ti)
+    ov, of, on = orc.edges_check_boxes(verts[fi], verts[ti], L, lo, hi, nthreads=orc.max_threads())
+    np.testing.assert_array_equal(n, on)
+    np.testing.assert_array_equal(v, ov)
+    np.testing.assert_array_equal(f, of)
+    # reversed orientation is a different edge (interpolate is not symmetric in floating point)
+    v2, f2, n2 = ctx.edges_check_indexed(ti[:300000], fi[:300000])
+    ov2, of2, on2 = orc.edges_check_boxes(verts[ti[:300000]], verts[fi[:300000]], L, lo, hi, nthreads=orc.max_threads())
+    np.testing.assert_array_equal(v2, ov2)
+    np.testing.assert_array_equal(f2, of2)
+    ctx.close()
+
+
+def test_more_than_65536_boxes(capi, orc, wl):
+    """Box ids beyond 16 bits: candidates must not wrap."""
+    d = 2
+    rng = np.random.default_rng(7)
+    nb = 70000
+    c = rng.random((nb, d))
+    h = rng.random((nb, d)) * 0.002 + 0.0005
+    lo, hi = c - h, c + h
+    L = wl.segment_length(d, 0.002)
+    ctx = capi.Context(d, L)
+    ctx.set_world_boxes(lo, hi)
+    frm, to = wl.random_edges(4000, d, seed=12, max_len=0.05)
+    v, f, n = ctx.edges_check(frm, to)
+    ov, of, on = orc.edges_check_boxes(frm, to, L, lo, hi, nthreads=orc.max_threads())
+    np.testing.assert_array_equal(n, on)
+    np.testing.assert_array_equal(v, ov)
+    np.testing.assert_array_equal(f, of)
+    # a box that only a high id can explain: one isolated obstacle appended last
+    lo2 = np.concatenate([np.full((nb, d), 5.0), [[0.45, 0.45]]])
+    hi2 = np.concatenate([np.full((nb, d), 5.001), [[0.55, 0.55]]])
+    ctx.set_world_boxes(lo2, hi2)
+    v, f, n = ctx.edges_check(np.array([[0.3, 0.5]]), np.array([[0.7, 0.5]]))
+    assert v[0] == 0 and f[0] >= 1
+    st = wl.uniform(5, (20000, d))
+    np.testing.assert_array_equal(ctx.states_valid(st), orc.states_valid_boxes(st, lo2, hi2))
     ctx.close()

@@ -123,6 +123,27 @@ def test_planner_parity_single_batching_graphml(orc, wl, tmp_path):
     assert nsol >= 1
 
 
+def test_planner_parity_config1_full_size(orc, wl):
+    """BASELINE config 1 at its real size: 2-D 1024^2 occupancy image, 10^4-vertex Halton roadmap, hybrid
+    batching, resolution 1e-3 — every solve() call compared with the oracle planner."""
+    pix = wl.image_world(1024, seed=1)
+    op, gp = _make(orc, wl, 2, 10 ** 4, ("image", pix), {"batching_type": "hybrid", "graph_type": "halton",
+                                                          "increment": 0.2, "prune_threshold": 1.05}, 1e-3,
+                   None, None)
+    nsol = _run_both(op, gp, [0.1, 0.1], [0.9, 0.9], False, max_calls=40, budget=120)
+    assert nsol >= 3 and gp.best_cost < 2.0
+
+
+def test_planner_parity_config3_full_size(orc, wl):
+    """BASELINE config 3 at its real size: 7-DoF, 500 boxes, 10^6-vertex Halton roadmap, vertex batching
+    (admitted sets 100, 200, 400, ... and the complete graph over them, VertexBatching.hpp:94-138)."""
+    d = 7
+    lo, hi = wl.box_world(d, 500, seed=3)
+    op, gp = _make(orc, wl, d, 10 ** 6, ("boxes", lo, hi), {"batching_type": "vertex"}, 0.01, None, None)
+    nsol = _run_both(op, gp, np.full(d, 0.1), np.full(d, 0.9), False, max_calls=30, budget=200)
+    assert nsol >= 2
+
+
 def test_planner_errors_mirror_reference(wl):
     from batching_pomp_b200.planner import Planner, PlannerError
     lo, hi = wl.box_world(2, 10, seed=3)
