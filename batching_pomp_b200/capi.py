@@ -32,6 +32,9 @@ SIGNATURES = {
     "bpomp_bisect_perm": (C.c_int, [C.c_uint32, c_i32p]),
     "bpomp_world_set_image": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int]),
     "bpomp_world_set_boxes": (C.c_int, [vp, vp, vp, C.c_int]),
+    "bpomp_world_set_bounds": (C.c_int, [vp, vp, vp]),
+    "bpomp_set_option": (C.c_int, [vp, C.c_char_p, C.c_int64]),
+    "bpomp_get_counter": (C.c_int, [vp, C.c_char_p, C.POINTER(C.c_int64)]),
     "bpomp_states_valid": (C.c_int, [vp, vp, C.c_int64, vp]),
     "bpomp_states_valid_dev": (C.c_int, [vp, vp, C.c_int64, vp]),
     "bpomp_states_prune": (C.c_int, [vp, vp, C.c_int64, vp, vp, C.c_double, C.c_int, vp]),
@@ -151,6 +154,23 @@ class Context:
     def set_world_boxes(self, lo, hi):
         lo, hi = _f64(lo).reshape(-1, self.dim), _f64(hi).reshape(-1, self.dim)
         self._ck(self.lib.bpomp_world_set_boxes(self.h, _ptr(lo), _ptr(hi), lo.shape[0]))
+
+    def set_bounds(self, lo, hi):
+        """State-space bounds hint (scalars broadcast to dim); None, None removes it."""
+        if lo is None:
+            self._ck(self.lib.bpomp_world_set_bounds(self.h, None, None))
+            return
+        lo = _f64(np.broadcast_to(np.asarray(lo, dtype=np.float64), (self.dim,)))
+        hi = _f64(np.broadcast_to(np.asarray(hi, dtype=np.float64), (self.dim,)))
+        self._ck(self.lib.bpomp_world_set_bounds(self.h, _ptr(lo), _ptr(hi)))
+
+    def set_option(self, name, value):
+        self._ck(self.lib.bpomp_set_option(self.h, name.encode(), int(value)))
+
+    def counter(self, name):
+        v = C.c_int64(0)
+        self._ck(self.lib.bpomp_get_counter(self.h, name.encode(), C.byref(v)))
+        return int(v.value)
 
     def states_valid(self, states):
         s = _f64(states).reshape(-1, self.dim)

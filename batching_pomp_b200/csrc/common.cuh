@@ -70,6 +70,20 @@ struct BoxWorldView {
   size_t rmask_bytes, lohi_bytes;
 };
 
+// Tables of the fast box-world edge kernel (fastpath.cuh, edge_check_fast.cu).
+struct FastWorldView {
+  int enabled;                  // 0: this world is evaluated by the general kernel only
+  int nps;                      // pairs of dimension slots = (dim+1)/2
+  int nboxes;
+  double qs[BPOMP_DIM_MAX];     // q_j(x) = fma(x, qs_j, qo_j)
+  double qo[BPOMP_DIM_MAX];
+  const uint4* tmask;           // broad-phase mask rows, fp_row_offset() layout (fastpath.cuh)
+  const uint4* qbox;            // [nboxes][2] x 16 B: lo_q[8] then hi_q[8], u16 each
+  const float* perm_s;          // float(1 + perm_n[slot]) rows for n = 2..FP_NMAX at fp_perm_off(n)
+  const float* perm4;           // the rows of n <= FP_PERM4_NMAX in the padded layout staged into shared memory
+  size_t tmask_bytes, qbox_bytes;
+};
+
 struct ImageWorldView {
   int W, H;
   int tiles_x;                  // number of 8x8 tiles per row
@@ -104,7 +118,14 @@ struct bpomp_ctx {
   int world = WORLD_NONE;
   BoxWorldView boxes{};
   ImageWorldView image{};
-  DevBuf d_lohi, d_rmask, d_bits, d_work;
+  FastWorldView fast{};
+  DevBuf d_lohi, d_rmask, d_bits, d_work, d_tmask, d_qbox, d_perm_s, d_perm4;
+  std::vector<double> h_box_lo, h_box_hi;   // host copy of the boxes (tables are rebuilt when bounds change)
+  bool have_bounds = false;
+  double bounds_lo[BPOMP_DIM_MAX] = {0}, bounds_hi[BPOMP_DIM_MAX] = {0};
+  int fast_mode = 1;                        // 0: never use the fast kernel (testing / tuning)
+  int fast_warps = 0;                       // > 0: cap on the warps per CTA of the fast kernel (tuning)
+  int64_t fast_min_edges = 4096;            // smaller batches go to the general kernel alone (one launch)
 
   // vertex table (elements of mVertexNN)
   DevBuf d_verts, d_active;
@@ -149,6 +170,12 @@ int bp_launch_edge_check(bpomp_ctx* ctx, const double* d_from, const double* d_t
                          const uint32_t* d_to_ids, int64_t count, uint8_t* d_valid, int32_t* d_first,
                          uint32_t* d_nstates, bool deferred_only);
 int bp_launch_states_valid(bpomp_ctx* ctx, const double* d_states, int64_t count, uint8_t* d_out);
+// fast box-world kernel (edge_check_fast.cu): evaluates the edges it can and marks the rest BPOMP_EDGE_SLOW;
+// returns 1 if it was launched, 0 if it does not apply to this call, < 0 on error
+int bp_launch_edge_check_fast(bpomp_ctx* ctx, const double* d_from, const double* d_to, const uint32_t* d_from_ids,
+                              const uint32_t* d_to_ids, int64_t count, uint8_t* d_valid, int32_t* d_first,
+                              uint32_t* d_nstates);
+int bp_build_fast_world(bpomp_ctx* ctx);
 
 // ---------------------------------------------------------------------------
 // Device arithmetic.  Everything that must be bit-equal to the reference's unfused x86-64

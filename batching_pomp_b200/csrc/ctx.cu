@@ -7,6 +7,7 @@
 #include <queue>
 
 #include "common.cuh"
+#include "fastpath.cuh"
 
 static std::string g_create_error;
 
@@ -190,6 +191,30 @@ static int create_impl(bpomp_ctx* ctx) {
                                ctx->stream));
   BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   BP_TRY(bpomp_perm_reserve(ctx, 256));
+  // sample coordinates s = 1 + perm_n[slot] as floats for the fast kernel's range search (fastpath.cuh)
+  {
+    std::vector<float> ps(fp_perm_off(FP_NMAX + 1u), 0.0f);
+    std::vector<int32_t> perm;
+    for (uint32_t n = 2; n <= FP_NMAX; ++n) {
+      bp_bisect_perm_host(n, perm);
+      for (uint32_t i = 0; i < n; ++i) ps[fp_perm_off(n) + i] = (float)(1 + perm[i]);
+    }
+    BP_TRY(bp_reserve(ctx, ctx->d_perm_s, ps.size() * sizeof(float), false));
+    BP_CUDA(ctx, cudaMemcpyAsync(ctx->d_perm_s.p, ps.data(), ps.size() * sizeof(float), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->fast.perm_s = ctx->d_perm_s.as<float>();
+    std::vector<float> p4(FP_PERM4_SMEM_BYTES / 4, -1.0f);
+    for (uint32_t n = 3; n <= FP_PERM4_NMAX; ++n) {
+      bp_bisect_perm_host(n, perm);
+      for (uint32_t i = 0; i + 2 < n; ++i) p4[fp_perm4_off(n) + i] = (float)(1 + perm[1 + i]);
+    }
+    BP_TRY(bp_reserve(ctx, ctx->d_perm4, p4.size() * sizeof(float), false));
+    BP_CUDA(ctx, cudaMemcpyAsync(ctx->d_perm4.p, p4.data(), p4.size() * sizeof(float), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->fast.perm4 = ctx->d_perm4.as<float>();
+  }
   return BPOMP_OK;
 }
 
@@ -228,7 +253,7 @@ extern "C" void bpomp_destroy(bpomp_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->d_perm_off, &ctx->d_tfrac, &ctx->d_step, &ctx->d_need, &ctx->d_lohi, &ctx->d_rmask,
-                    &ctx->d_bits, &ctx->d_work, &ctx->d_verts, &ctx->d_active, &ctx->d_nb_rowptr, &ctx->d_nb_col,
+                    &ctx->d_bits, &ctx->d_work, &ctx->d_tmask, &ctx->d_qbox, &ctx->d_perm_s, &ctx->d_perm4, &ctx->d_verts, &ctx->d_active, &ctx->d_nb_rowptr, &ctx->d_nb_col,
                     &ctx->d_nb_dist, &ctx->d_nb_query, &ctx->d_nb_tmp, &ctx->d_nb_tmp2, &ctx->d_grid_cell_start,
                     &ctx->d_grid_ids, &ctx->d_grid_pts, &ctx->d_grid_keys, &ctx->d_bel_pts, &ctx->d_bel_vals,
                     &ctx->s_a, &ctx->s_b, &ctx->s_c, &ctx->s_d, &ctx->s_e, &ctx->s_f, &ctx->s_g, &ctx->s_h, &ctx->s_i,
@@ -279,6 +304,33 @@ extern "C" int bpomp_set_stream(bpomp_ctx* ctx, void* cuda_stream) {
   BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
   return BPOMP_OK;
+}
+
+extern "C" int bpomp_set_option(bpomp_ctx* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) return BPOMP_ERR_INVALID;
+  if (!strcmp(name, "fast_edge_kernel")) ctx->fast_mode = value ? 1 : 0;
+  else if (!strcmp(name, "fast_edge_min_edges")) ctx->fast_min_edges = value < 0 ? 0 : value;
+  else if (!strcmp(name, "fast_edge_warps")) ctx->fast_warps = (int)value;
+  else return bp_fail(ctx, BPOMP_ERR_INVALID, "unknown option '%s'", name);
+  return BPOMP_OK;
+}
+
+extern "C" int bpomp_get_counter(bpomp_ctx* ctx, const char* name, int64_t* value) {
+  if (!ctx || !name || !value) return BPOMP_ERR_INVALID;
+  if (!strcmp(name, "slow_edges")) {  // edges the fast kernel left to the general kernel in the last edge call
+    *value = 0;
+    if (!ctx->d_work.p) return BPOMP_OK;
+    int v = 0;
+    BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    BP_CUDA(ctx, cudaMemcpy(&v, ctx->d_work.as<unsigned long long>() + 16, sizeof(int), cudaMemcpyDeviceToHost));
+    *value = v;
+    return BPOMP_OK;
+  }
+  if (!strcmp(name, "fast_world")) {
+    *value = ctx->fast.enabled;
+    return BPOMP_OK;
+  }
+  return bp_fail(ctx, BPOMP_ERR_INVALID, "unknown counter '%s'", name);
 }
 
 extern "C" void* bpomp_get_stream(bpomp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }

@@ -8,6 +8,7 @@
 // for 1 or 32 active lanes, and a 7-DoF edge at the default resolution has only ~5 checked samples).
 #include <cfloat>
 
+#include "fastpath.cuh"
 #include "world.cuh"
 
 #ifndef EC_THREADS
@@ -26,7 +27,9 @@ struct EdgeArgs {
   uint8_t* valid;
   int32_t* first;
   uint32_t* nstates;         // may be null
-  int deferred_only;         // re-run: only edges currently marked BPOMP_EDGE_DEFERRED
+  int only_status;           // 0: every edge; else only edges whose status byte equals it (BPOMP_EDGE_DEFERRED
+                             // on the re-run after a sample-order upload, BPOMP_EDGE_SLOW after the fast kernel)
+  const int* gate;           // non-null: the CTA exits at once when *gate == 0 (no edge was left to this pass)
   double L;
   unsigned long long* work;  // dynamic tile counter (zeroed before the launch)
 };
@@ -94,7 +97,7 @@ __device__ __forceinline__ void load_endpoints(const EdgeArgs& a, int64_t e, dou
 template <int D, bool INDEXED>
 __device__ __forceinline__ bool edge_prologue(const EdgeArgs& a, const PermView& pv, int64_t e, double* f, double* t,
                                               uint32_t& n, uint32_t& off) {
-  if (a.deferred_only && a.valid[e] != BPOMP_EDGE_DEFERRED) return false;
+  if (a.only_status && a.valid[e] != (uint8_t)a.only_status) return false;
   load_endpoints<D, INDEXED>(a, e, f, t);
   double dist = __dsqrt_rn(bp_dist2<D>(f, t));  // BP.cpp:163 distance(source, target)
   n = bp_nstates(dist, a.L);                     // BP.cpp:440-445
@@ -157,6 +160,7 @@ template <int D, bool INDEXED, bool STAGE, int W4>
 __global__ void __launch_bounds__(EC_THREADS, 1)
     edge_check_boxes_kernel(EdgeArgs a, BoxWorldView w, PermView pv) {
   extern __shared__ __align__(16) unsigned char smem[];
+  if (a.gate && *reinterpret_cast<const volatile int*>(a.gate) == 0) return;
   // layout: [WarpScratch x EC_WARPS][mbarrier 16 B][prefix masks][lohi]
   WarpScratch* ws = reinterpret_cast<WarpScratch*>(smem) + (threadIdx.x >> 5);
   constexpr size_t kScratch = (sizeof(WarpScratch) * EC_WARPS + 15) / 16 * 16;
@@ -367,6 +371,7 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
 // ---------------------------------------------------------------------------
 template <bool INDEXED>
 __global__ void __launch_bounds__(256) edge_check_image_kernel(EdgeArgs a, ImageWorldView im, PermView pv) {
+  if (a.gate && *reinterpret_cast<const volatile int*>(a.gate) == 0) return;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.count;
        e += (int64_t)gridDim.x * blockDim.x) {
     double f[2], t[2];
@@ -435,14 +440,22 @@ int bp_launch_edge_check(bpomp_ctx* ctx, const double* d_from, const double* d_t
                          uint32_t* d_nstates, bool deferred_only) {
   if (ctx->world == WORLD_NONE) return bp_fail(ctx, BPOMP_ERR_NO_WORLD, "no collision world set");
   if (count <= 0) return BPOMP_OK;
+  // Box worlds the fast kernel covers: it evaluates the edges it can and marks the rest BPOMP_EDGE_SLOW; the
+  // general kernel below then runs on exactly those (its CTAs exit at once when there are none).
+  int fast = 0;
+  if (!deferred_only) {
+    fast = bp_launch_edge_check_fast(ctx, d_from, d_to, d_from_ids, d_to_ids, count, d_valid, d_first, d_nstates);
+    if (fast < 0) return fast;
+  }
   EdgeArgs a;
   a.from = d_from; a.to = d_to; a.from_ids = d_from_ids; a.to_ids = d_to_ids;
   a.verts = ctx->d_verts.as<double>();
   a.count = count; a.valid = d_valid; a.first = d_first; a.nstates = d_nstates;
-  a.deferred_only = deferred_only ? 1 : 0;
+  a.only_status = deferred_only ? (int)BPOMP_EDGE_DEFERRED : (fast ? (int)BPOMP_EDGE_SLOW : 0);
   a.L = ctx->L;
   BP_TRY(bp_reserve(ctx, ctx->d_work, 256, false));
   a.work = ctx->d_work.as<unsigned long long>() + ctx->work_slot;  // one counter per pipeline lane
+  a.gate = fast ? reinterpret_cast<const int*>(ctx->d_work.as<unsigned long long>() + 16 + ctx->work_slot) : nullptr;
   BP_CUDA(ctx, cudaMemsetAsync(a.work, 0, sizeof(unsigned long long), ctx->stream));
   const bool indexed = d_from_ids != nullptr;
   if (ctx->world == WORLD_IMAGE) {

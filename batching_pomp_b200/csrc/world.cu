@@ -5,6 +5,8 @@
 #include <cstring>
 
 #include "world.cuh"
+#include "fastpath.cuh"
+#include "fastpath_host.hpp"
 
 // ---------------------------------------------------------------------------
 // World upload
@@ -104,6 +106,62 @@ extern "C" int bpomp_world_set_boxes(bpomp_ctx* ctx, const double* lo, const dou
   w.rmask = ctx->d_rmask.as<uint4>();
   w.lohi = ctx->d_lohi.as<double2>();
   ctx->world = WORLD_BOXES;
+  ctx->h_box_lo.assign(lo, lo + (size_t)nboxes * D);
+  ctx->h_box_hi.assign(hi, hi + (size_t)nboxes * D);
+  return bp_build_fast_world(ctx);
+}
+
+// Tables of the fast kernel (fastpath.cuh): the quantisation q_j over the region of interest (the bounding
+// region of the boxes, intersected with the state-space bounds when the caller gave them), the 16-bit box
+// bounds, and the broad-phase masks in the team layout.  Worlds the fast kernel does not cover (more than
+// FP_MAXBOXES boxes, non-finite or degenerate extents, coordinates huge relative to the extent) leave
+// fast.enabled = 0 and are evaluated by the general kernel alone.
+int bp_build_fast_world(bpomp_ctx* ctx) {
+  FastWorldView& fw = ctx->fast;
+  const float* perm_s = ctx->d_perm_s.as<float>();
+  const float* perm4 = ctx->d_perm4.as<float>();
+  memset(&fw, 0, sizeof(fw));
+  fw.perm_s = perm_s;
+  fw.perm4 = perm4;
+  const int D = ctx->dim;
+  const int nb = (int)(ctx->h_box_lo.size() / (size_t)D);
+  fw.nboxes = nb;
+  fw.nps = (D + 1) / 2;
+  if (ctx->world != WORLD_BOXES) return BPOMP_OK;
+  FpTables t = fp_build_tables(D, nb, ctx->h_box_lo.data(), ctx->h_box_hi.data(), ctx->have_bounds, ctx->bounds_lo,
+                               ctx->bounds_hi);
+  if (!t.enabled) return BPOMP_OK;
+  for (int j = 0; j < D; ++j) {
+    fw.qs[j] = t.qs[j];
+    fw.qo[j] = t.qo[j];
+  }
+  fw.tmask_bytes = t.tmask.size() * sizeof(uint32_t);
+  fw.qbox_bytes = t.qbox.size() * sizeof(uint16_t);
+  BP_TRY(bp_reserve(ctx, ctx->d_tmask, fw.tmask_bytes, false));
+  BP_TRY(bp_reserve(ctx, ctx->d_qbox, fw.qbox_bytes, false));
+  BP_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmask.p, t.tmask.data(), fw.tmask_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  BP_CUDA(ctx, cudaMemcpyAsync(ctx->d_qbox.p, t.qbox.data(), fw.qbox_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  fw.tmask = ctx->d_tmask.as<uint4>();
+  fw.qbox = ctx->d_qbox.as<uint4>();
+  fw.enabled = 1;
+  return BPOMP_OK;
+}
+
+extern "C" int bpomp_world_set_bounds(bpomp_ctx* ctx, const double* lo, const double* hi) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (!lo || !hi) {
+    ctx->have_bounds = false;
+  } else {
+    for (int j = 0; j < ctx->dim; ++j) {
+      if (!(lo[j] < hi[j]) || !std::isfinite(lo[j]) || !std::isfinite(hi[j]))
+        return bp_fail(ctx, BPOMP_ERR_INVALID, "bounds must be finite with lo < hi in every dimension");
+      ctx->bounds_lo[j] = lo[j];
+      ctx->bounds_hi[j] = hi[j];
+    }
+    ctx->have_bounds = true;
+  }
+  if (ctx->world == WORLD_BOXES) return bp_build_fast_world(ctx);
   return BPOMP_OK;
 }
 

@@ -76,6 +76,13 @@ BPOMP_API int bpomp_sync(bpomp_ctx* ctx);
  * ctx's own stream. */
 BPOMP_API int bpomp_set_stream(bpomp_ctx* ctx, void* cuda_stream);
 BPOMP_API void* bpomp_get_stream(bpomp_ctx* ctx);
+/* Tuning / testing switches; results never depend on them.  name: "fast_edge_kernel" (1 = use the fast
+ * box-world edge kernel where it applies (default), 0 = general kernel only), "fast_edge_min_edges" (batches
+ * below this go to the general kernel alone, default 4096), "fast_edge_warps" (cap on its warps per CTA, 0 = auto). */
+BPOMP_API int bpomp_set_option(bpomp_ctx* ctx, const char* name, int64_t value);
+/* Diagnostics: "slow_edges" = edges of the last edge call that the fast kernel left to the general one (waits
+ * for the stream); "fast_world" = 1 if the current world has the fast kernel's tables. */
+BPOMP_API int bpomp_get_counter(bpomp_ctx* ctx, const char* name, int64_t* value);
 /* Number of kernel launches issued by this ctx so far (bench.py's gpu_launches). */
 BPOMP_API uint64_t bpomp_launch_count(const bpomp_ctx* ctx);
 
@@ -95,6 +102,12 @@ BPOMP_API int bpomp_world_set_image(bpomp_ctx* ctx, const uint8_t* pix, int widt
 /* n-D axis-aligned boxes lo/hi[nboxes][dim]; a state is invalid iff it lies in the closed
  * box lo <= x <= hi of any box. */
 BPOMP_API int bpomp_world_set_boxes(bpomp_ctx* ctx, const double* lo, const double* hi, int nboxes);
+
+/* Optional: the bounds of the state space (RealVectorStateSpace::getBounds(), low/high[dim]).  A hint only —
+ * results never depend on it: the broad-phase grid of the box world is laid over the part of the obstacles'
+ * bounding region that lies inside the bounds, which is where the planner's edges are (finer cells, fewer
+ * candidate boxes per edge).  NULL, NULL removes the hint. */
+BPOMP_API int bpomp_world_set_bounds(bpomp_ctx* ctx, const double* lo, const double* hi);
 
 /* isValid for a batch of states — src/BatchingPOMP.cpp:654, 777, 784.  out[i] = 1 valid / 0 not. */
 BPOMP_API int bpomp_states_valid(bpomp_ctx* ctx, const double* states, int64_t count, uint8_t* out);
