@@ -12,6 +12,7 @@
 
 #define BP_ABSENT 0xFFFFFFFFu
 #define BP_GRID_C 32   // broad-phase cells per dimension
+#define BP_SLOW_LIST_CAP (1 << 20)  // entries of the fast kernel's left-over list (beyond it: status scan)
 #define BP_SPAN 8      // cell ranges [c0, c0+span], span < BP_SPAN, have a combined mask row
 
 // ---------------------------------------------------------------------------
@@ -123,6 +124,7 @@ struct bpomp_ctx {
   std::vector<double> h_box_lo, h_box_hi;   // host copy of the boxes (tables are rebuilt when bounds change)
   bool have_bounds = false;
   double bounds_lo[BPOMP_DIM_MAX] = {0}, bounds_hi[BPOMP_DIM_MAX] = {0};
+  DevBuf d_slow_list[4];                    // per pipeline lane: indices of the edges the fast kernel left over
   int fast_mode = 1;                        // 0: never use the fast kernel (testing / tuning)
   int fast_warps = 0;                       // > 0: cap on the warps per CTA of the fast kernel (tuning)
   int64_t fast_min_edges = 4096;            // smaller batches go to the general kernel alone (one launch)

@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <queue>
 
 #include "common.cuh"
@@ -209,6 +210,34 @@ static int create_impl(bpomp_ctx* ctx) {
       bp_bisect_perm_host(n, perm);
       for (uint32_t i = 0; i + 2 < n; ++i) p4[fp_perm4_off(n) + i] = (float)(1 + perm[1 + i]);
     }
+    // thresholds of nStates on the squared distance (fastpath.cuh: fp_nstates_thr), by bisection over the bit
+    // patterns of the positive doubles with the host's IEEE sqrt and division
+    {
+      double thr[FP_NTHR + 2u];
+      const double L = ctx->L;
+      auto nst = [L](double s) { return std::floor(std::sqrt(s) / L); };
+      for (uint32_t k = 0; k < FP_NTHR + 2u; ++k) {
+        thr[k] = 0.0;
+        if (k < 3) continue;
+        double hi = ((double)k + 2.0) * L;
+        hi *= hi;
+        uint64_t a = 0, b;
+        memcpy(&b, &hi, 8);
+        if (!(nst(hi) >= (double)k) || !std::isfinite(hi)) {  // degenerate L: never use the table beyond here
+          thr[k] = std::numeric_limits<double>::infinity();
+          continue;
+        }
+        while (b - a > 1) {  // invariant: nst(a) < k <= nst(b)
+          const uint64_t m = a + (b - a) / 2;
+          double sm;
+          memcpy(&sm, &m, 8);
+          if (nst(sm) >= (double)k) b = m;
+          else a = m;
+        }
+        memcpy(&thr[k], &b, 8);
+      }
+      memcpy(reinterpret_cast<char*>(p4.data()) + FP_PERM4_BYTES, thr, FP_THR_BYTES);
+    }
     BP_TRY(bp_reserve(ctx, ctx->d_perm4, p4.size() * sizeof(float), false));
     BP_CUDA(ctx, cudaMemcpyAsync(ctx->d_perm4.p, p4.data(), p4.size() * sizeof(float), cudaMemcpyHostToDevice,
                                  ctx->stream));
@@ -259,6 +288,7 @@ extern "C" void bpomp_destroy(bpomp_ctx* ctx) {
                     &ctx->s_a, &ctx->s_b, &ctx->s_c, &ctx->s_d, &ctx->s_e, &ctx->s_f, &ctx->s_g, &ctx->s_h, &ctx->s_i,
                     &ctx->s_j, &ctx->s_scan};
   for (DevBuf* b : bufs) bp_free(*b);
+  for (int l = 0; l < 4; ++l) bp_free(ctx->d_slow_list[l]);
   for (int l = 0; l < 3; ++l) {
     bp_free(ctx->lane_a[l]);
     bp_free(ctx->lane_b[l]);

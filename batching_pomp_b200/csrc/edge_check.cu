@@ -29,7 +29,10 @@ struct EdgeArgs {
   uint32_t* nstates;         // may be null
   int only_status;           // 0: every edge; else only edges whose status byte equals it (BPOMP_EDGE_DEFERRED
                              // on the re-run after a sample-order upload, BPOMP_EDGE_SLOW after the fast kernel)
-  const int* gate;           // non-null: the CTA exits at once when *gate == 0 (no edge was left to this pass)
+  const int* gate;           // non-null: number of edges the fast kernel left to this pass; the CTA exits at
+                             // once when it is 0
+  const uint32_t* list;      // with gate: their indices, when *gate <= list_cap (else the status bytes are scanned)
+  int list_cap;
   double L;
   unsigned long long* work;  // dynamic tile counter (zeroed before the launch)
 };
@@ -96,8 +99,8 @@ __device__ __forceinline__ void load_endpoints(const EdgeArgs& a, int64_t e, dou
 // Phase A shared by both worlds.  Returns false when the edge is already decided (outputs written).
 template <int D, bool INDEXED>
 __device__ __forceinline__ bool edge_prologue(const EdgeArgs& a, const PermView& pv, int64_t e, double* f, double* t,
-                                              uint32_t& n, uint32_t& off) {
-  if (a.only_status && a.valid[e] != (uint8_t)a.only_status) return false;
+                                              uint32_t& n, uint32_t& off, int only_status) {
+  if (only_status && a.valid[e] != (uint8_t)only_status) return false;
   load_endpoints<D, INDEXED>(a, e, f, t);
   double dist = __dsqrt_rn(bp_dist2<D>(f, t));  // BP.cpp:163 distance(source, target)
   n = bp_nstates(dist, a.L);                     // BP.cpp:440-445
@@ -160,7 +163,18 @@ template <int D, bool INDEXED, bool STAGE, int W4>
 __global__ void __launch_bounds__(EC_THREADS, 1)
     edge_check_boxes_kernel(EdgeArgs a, BoxWorldView w, PermView pv) {
   extern __shared__ __align__(16) unsigned char smem[];
-  if (a.gate && *reinterpret_cast<const volatile int*>(a.gate) == 0) return;
+  int only_status = a.only_status;
+  int64_t total = a.count;       // edges this launch walks
+  const uint32_t* elist = nullptr;  // their indices (null: 0..count-1)
+  if (a.gate) {
+    const int left = *reinterpret_cast<const volatile int*>(a.gate);
+    if (left == 0) return;
+    if (a.list && left <= a.list_cap) {
+      total = left;
+      elist = a.list;
+      only_status = 0;
+    }
+  }
   // layout: [WarpScratch x EC_WARPS][mbarrier 16 B][prefix masks][lohi]
   WarpScratch* ws = reinterpret_cast<WarpScratch*>(smem) + (threadIdx.x >> 5);
   constexpr size_t kScratch = (sizeof(WarpScratch) * EC_WARPS + 15) / 16 * 16;
@@ -199,13 +213,16 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
     unsigned long long chunk = 0;
     if (lane == 0) chunk = atomicAdd(a.work, 1ull);
     chunk = __shfl_sync(0xffffffffu, chunk, 0);
-    const int64_t chunk_base = (int64_t)chunk * (EC_CHUNK * 32);
-    if (chunk_base >= a.count) break;
-  for (int ti = 0; ti < EC_CHUNK; ++ti) {
+    // a left-over list is short: one tile per claim spreads it over all warps
+    const int chunk_tiles = elist ? 1 : EC_CHUNK;
+    const int64_t chunk_base = (int64_t)chunk * (chunk_tiles * 32);
+    if (chunk_base >= total) break;
+  for (int ti = 0; ti < chunk_tiles; ++ti) {
     const int64_t base = chunk_base + (int64_t)ti * 32;
-    if (base >= a.count) break;
-    const int64_t e = base + lane;
-    if (!INDEXED && ti + 1 < EC_CHUNK) {  // pull the next tile's endpoint rows (contiguous) towards L2
+    if (base >= total) break;
+    const bool inb = base + lane < total;
+    const int64_t e = !inb ? 0 : (elist ? (int64_t)__ldg(elist + base + lane) : base + lane);
+    if (!INDEXED && !elist && ti + 1 < chunk_tiles) {  // pull the next tile's endpoint rows (contiguous) towards L2
       const int64_t nb = base + 32;
       constexpr int kLines = (32 * D * 8 + 127) / 128 + 1;
       if (nb < a.count && lane < kLines) {
@@ -221,7 +238,7 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
 #pragma unroll
     for (int j = 0; j < D; ++j) { f[j] = 0.0; t[j] = 0.0; }
     uint32_t n = 0, off = 0;
-    bool need = e < a.count && edge_prologue<D, INDEXED>(a, pv, e, f, t, n, off);
+    bool need = inb && edge_prologue<D, INDEXED>(a, pv, e, f, t, n, off, only_status);
 
     // ---- B. broad phase ------------------------------------------------------------------------
     int nc = 0;
@@ -371,12 +388,12 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
 // ---------------------------------------------------------------------------
 template <bool INDEXED>
 __global__ void __launch_bounds__(256) edge_check_image_kernel(EdgeArgs a, ImageWorldView im, PermView pv) {
-  if (a.gate && *reinterpret_cast<const volatile int*>(a.gate) == 0) return;
+  if (a.gate && *reinterpret_cast<const volatile int*>(a.gate) == 0) return;  // (never set for the image world)
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.count;
        e += (int64_t)gridDim.x * blockDim.x) {
     double f[2], t[2];
     uint32_t n, off;
-    if (!edge_prologue<2, INDEXED>(a, pv, e, f, t, n, off)) continue;
+    if (!edge_prologue<2, INDEXED>(a, pv, e, f, t, n, off, a.only_status)) continue;
     double d0 = __dsub_rn(t[0], f[0]), d1 = __dsub_rn(t[1], f[1]);
     const double* tf = pv.tfrac + off;
     int32_t bad = -1;
@@ -456,6 +473,8 @@ int bp_launch_edge_check(bpomp_ctx* ctx, const double* d_from, const double* d_t
   BP_TRY(bp_reserve(ctx, ctx->d_work, 256, false));
   a.work = ctx->d_work.as<unsigned long long>() + ctx->work_slot;  // one counter per pipeline lane
   a.gate = fast ? reinterpret_cast<const int*>(ctx->d_work.as<unsigned long long>() + 16 + ctx->work_slot) : nullptr;
+  a.list = fast ? ctx->d_slow_list[ctx->work_slot].as<uint32_t>() : nullptr;
+  a.list_cap = fast ? BP_SLOW_LIST_CAP : 0;
   BP_CUDA(ctx, cudaMemsetAsync(a.work, 0, sizeof(unsigned long long), ctx->stream));
   const bool indexed = d_from_ids != nullptr;
   if (ctx->world == WORLD_IMAGE) {

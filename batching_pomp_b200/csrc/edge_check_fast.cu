@@ -42,9 +42,12 @@ struct FastArgs {
   int32_t* first;
   uint32_t* nstates;         // may be null
   double L;
+  float inv_L;               // 1/L as a float (nStates estimate, fp_nstates_thr)
+  uint32_t magic;            // 0x4B000000 (2^23 as float bits), an operand of the byte permutes
   unsigned long long* work;  // dynamic tile counter (zeroed before the launch)
   int* flags;                // [1] range errors
   int* slow_count;           // number of edges left to the general kernel (its gate)
+  uint32_t* slow_list;       // their indices (the first BP_SLOW_LIST_CAP of them)
   int tma_ok;                // from/to are 16-byte aligned: tiles are fetched with cp.async.bulk
   int nwarps;
   // FP64 tables of the exact test (rare path)
@@ -104,39 +107,53 @@ struct FeWarp {
   uint32_t pad;
 };
 
-// Exact FP64 test of sample `slot` of edge e against box b, with the reference's arithmetic (rare path).
+// Rare path: the search for the first slot >= from_slot (< lim) of edge e inside box b when a sample lies too
+// close to a face for the FP32 ranges (or the edge is longer than the shared-memory table of sample orders):
+// slots in the OUTER range are taken if they are in the INNER range, else tested in FP64 with the reference's
+// arithmetic (RealVectorStateSpace::interpolate, closed-box compare).  Returns the slot or -1.
 template <int D, bool INDEXED>
-__device__ __noinline__ bool fe_exact_inside(const double* from, const double* to, const uint32_t* from_ids,
-                                             const uint32_t* to_ids, const double* verts, const double* tfrac,
-                                             const uint32_t* perm_off, const double2* lohi, int lohi_stride,
-                                             int64_t e, uint32_t n, int slot, int b) {
-  const double* pf;
-  const double* pt;
-  if (INDEXED) {
-    pf = verts + (size_t)__ldg(from_ids + e) * D;
-    pt = verts + (size_t)__ldg(to_ids + e) * D;
-  } else {
-    pf = from + (size_t)e * D;
-    pt = to + (size_t)e * D;
-  }
-  const double tt = __ldg(tfrac + __ldg(perm_off + n) + slot);  // (1+perm[slot])/(n+1), BP.cpp:459
-  const double2* row = lohi + (size_t)b * lohi_stride;
+__device__ __noinline__ int fe_search_exact(const FastArgs* a, const float* perm_s, int64_t e, uint32_t n,
+                                            int from_slot, int lim, int b, float smin, float smax, float imin,
+                                            float imax) {
+  const float* ps = perm_s + fp_perm_off(n);
+  const double* pf = nullptr;
+  const double* pt = nullptr;
+  for (int i = from_slot; i < lim; ++i) {
+    const float s = __ldg(ps + i);
+    if (!(s >= smin && s <= smax)) continue;
+    if (s >= imin && s <= imax) return i;
+    if (!pf) {
+      if (INDEXED) {
+        pf = a->verts + (size_t)__ldg(a->from_ids + e) * D;
+        pt = a->verts + (size_t)__ldg(a->to_ids + e) * D;
+      } else {
+        pf = a->from + (size_t)e * D;
+        pt = a->to + (size_t)e * D;
+      }
+    }
+    const double tt = __ldg(a->tfrac + __ldg(a->perm_off + n) + i);  // (1+perm[slot])/(n+1), BP.cpp:459
+    const double2* row = a->lohi + (size_t)b * a->lohi_stride;
+    bool inside = true;
 #pragma unroll
-  for (int j = 0; j < D; ++j) {
-    const double fj = __ldg(pf + j), tj = __ldg(pt + j);
-    const double x = __dadd_rn(fj, __dmul_rn(__dsub_rn(tj, fj), tt));  // RealVectorStateSpace::interpolate
-    const double2 lh = row[j];
-    if (!(lh.x <= x && x <= lh.y)) return false;
+    for (int j = 0; j < D; ++j) {
+      const double fj = __ldg(pf + j), tj = __ldg(pt + j);
+      const double x = __dadd_rn(fj, __dmul_rn(__dsub_rn(tj, fj), tt));  // RealVectorStateSpace::interpolate
+      const double2 lh = row[j];
+      if (!(lh.x <= x && x <= lh.y)) inside = false;
+    }
+    if (inside) return i;
   }
-  return true;
+  return -1;
 }
 
 template <int D, bool INDEXED>
-__global__ void __launch_bounds__(640, 1) edge_check_fast_kernel(FastArgs a, FastWorldView w) {
+__global__ void __launch_bounds__(640, 1)
+    edge_check_fast_kernel(const __grid_constant__ FastArgs a, const __grid_constant__ FastWorldView w) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint4* s_tmask = reinterpret_cast<uint4*>(smem);
   uint4* s_qbox = reinterpret_cast<uint4*>(smem + w.tmask_bytes);
   float* s_perm = reinterpret_cast<float*>(smem + w.tmask_bytes + w.qbox_bytes);
+  const double* s_thr = reinterpret_cast<const double*>(smem + w.tmask_bytes + w.qbox_bytes + FP_PERM4_BYTES);
   const size_t tables = (w.tmask_bytes + w.qbox_bytes + FP_PERM4_SMEM_BYTES + 127) / 128 * 128;
   FeWarp<D>* ws = reinterpret_cast<FeWarp<D>*>(smem + tables) + (threadIdx.x >> 5);
   __shared__ uint64_t s_tbar;
@@ -298,12 +315,12 @@ __global__ void __launch_bounds__(640, 1) edge_check_fast_kernel(FastArgs a, Fas
       has_static = has_static || st;
       float r;
       asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(Dqf));
-      inv[j] = st ? 0.0f : r;
-      cc[j] = (float)F;  // completed once n is known
-      f[j] = F;          // f now holds q(from)
+      inv[j] = st ? FP_BIG : r;                                   // fastpath.cuh: fp_edge_dim
+      cc[j] = fmaf(-inv[j], (float)F, -8388608.0f * inv[j]);
     }
     const bool safe = qmin >= (int)FP_QOFF - 1 && qmax <= (int)(FP_QOFF + FP_QSCALE);
-    const uint32_t n = bp_nstates(__dsqrt_rn(dist2), a.L);  // BP.cpp:440-445
+    uint32_t n = fp_nstates_thr(dist2, a.inv_L, s_thr);      // BP.cpp:440-445 through exact thresholds
+    if (n == 0u) n = bp_nstates(__dsqrt_rn(dist2), a.L);     // long edge (or NaN): the FP64 formula
     bool need = false;                                       // has slots 1..n-2 to test
     bool slow = false;
     if (live) {
@@ -318,15 +335,6 @@ __global__ void __launch_bounds__(640, 1) edge_check_fast_kernel(FastArgs a, Fas
       } else {
         need = true;
         slow = !safe || n > FP_NMAX || spanmax > FP_SPAN_MAX;
-      }
-    }
-    {
-      const float np1 = (float)(n + 1u);
-#pragma unroll
-      for (int j = 0; j < D; ++j) {
-        const float iv = inv[j] == 0.0f ? FP_BIG : inv[j] * np1;  // (n+1)/Dq, relative error < 2^-21
-        inv[j] = iv;
-        cc[j] = (float)(-(8388608.0 + f[j]) * (double)iv);
       }
     }
     const uint32_t meta = n | (has_static ? 0x10000u : 0u);
@@ -352,64 +360,52 @@ __global__ void __launch_bounds__(640, 1) edge_check_fast_kernel(FastArgs a, Fas
       const uint4 qhi = fe_lds128(qbox_addr + (uint32_t)b * 32u + 16u);
       const uint32_t m_el = __shfl_sync(0xffffffffu, meta, el);
       const uint32_t n_el = m_el & 0xFFFFu;
-      float smin = 0.5f, smax = (float)n_el + 0.5f, imin = smin, imax = smax;
+      float smin = -3.0e38f, smax = 3.0e38f, imin = smin, imax = smax;
       const uint32_t ql[4] = {qlo.x, qlo.y, qlo.z, qlo.w};
       const uint32_t qh[4] = {qhi.x, qhi.y, qhi.z, qhi.w};
 #pragma unroll
       for (int j = 0; j < D; ++j) {
         const float iv = __shfl_sync(0xffffffffu, inv[j], el);
         const float cv = __shfl_sync(0xffffffffu, cc[j], el);
-        const float lo_m = (j & 1) ? fp_magic<1>(ql[j >> 1]) : fp_magic<0>(ql[j >> 1]);
-        const float hi_m = (j & 1) ? fp_magic<1>(qh[j >> 1]) : fp_magic<0>(qh[j >> 1]);
+        const float lo_m = __uint_as_float(__byte_perm(ql[j >> 1], a.magic, (j & 1) ? 0x7432 : 0x7410));
+        const float hi_m = __uint_as_float(__byte_perm(qh[j >> 1], a.magic, (j & 1) ? 0x7432 : 0x7410));
         fp_slab(lo_m, hi_m, iv, cv, smin, smax, imin, imax);
       }
+      fp_range_to_s(n_el, smin, smax, imin, imax);
       // some integer s in [smin, smax]?
       if (pv && smax >= smin && floorf(smax) >= smin) {
         const int curfirst = ws->first[el];
         const int lim = min((int)n_el - 1, curfirst);  // slots 1..n-2, and only those before a known hit
         if (m_el & 0x10000u) imin = 3.0e38f;            // an edge with a static dimension verifies every hit
+        int hit = -1, from_slot = 1;  // from_slot > 0: continue with the exact search from there
         if (n_el <= FP_PERM4_NMAX) {
           // s = 1 + perm[slot] of four slots per 16-byte load; rows start at slot 1 and are padded with -1
           const uint32_t rowa = perm_addr + fp_perm4_off(n_el) * 4u;
+          from_slot = 0;
           for (int i0 = 1; i0 < lim; i0 += 4) {
             float4 s4;
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                          : "=f"(s4.x), "=f"(s4.y), "=f"(s4.z), "=f"(s4.w)
                          : "r"(rowa + (uint32_t)(i0 - 1) * 4u));
             const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
-            int hit = -1;
+            uint32_t ok = 0, sure = 0;
 #pragma unroll
-            for (int q = 3; q >= 0; --q) {
-              const float s = sv[q];
-              if (s >= smin && s <= smax && i0 + q < lim) {
-                bool inside = s >= imin && s <= imax;
-                if (!inside)
-                  inside = fe_exact_inside<D, INDEXED>(a.from, a.to, a.from_ids, a.to_ids, a.verts, a.tfrac, a.perm_off,
-                                                       a.lohi, a.lohi_stride, base + el, n_el, i0 + q, b);
-                if (inside) hit = i0 + q;
-              }
+            for (int q = 0; q < 4; ++q) {
+              ok |= (sv[q] >= smin && sv[q] <= smax) ? (1u << q) : 0u;
+              sure |= (sv[q] >= imin && sv[q] <= imax) ? (1u << q) : 0u;
             }
-            if (hit >= 0) {
-              atomicMin(&ws->first[el], hit);
+            ok &= (1u << min(4, lim - i0)) - 1u;
+            if (ok) {
+              const int q = __ffs((int)ok) - 1;
+              if ((sure >> q) & 1u) hit = i0 + q;
+              else from_slot = i0 + q;  // within a few 1e-5 of a face: verified below
               break;
             }
           }
-        } else {
-          const float* ps = w.perm_s + fp_perm_off(n_el);
-          for (int i = 1; i < lim; ++i) {
-            const float s = __ldg(ps + i);
-            if (s >= smin && s <= smax) {
-              bool inside = s >= imin && s <= imax;
-              if (!inside)
-                inside = fe_exact_inside<D, INDEXED>(a.from, a.to, a.from_ids, a.to_ids, a.verts, a.tfrac, a.perm_off,
-                                                     a.lohi, a.lohi_stride, base + el, n_el, i, b);
-              if (inside) {
-                atomicMin(&ws->first[el], i);
-                break;
-              }
-            }
-          }
         }
+        if (from_slot > 0)
+          hit = fe_search_exact<D, INDEXED>(&a, w.perm_s, base + el, n_el, from_slot, lim, b, smin, smax, imin, imax);
+        if (hit >= 0) atomicMin(&ws->first[el], hit);
       }
     };
 
@@ -496,7 +492,12 @@ __global__ void __launch_bounds__(640, 1) edge_check_fast_kernel(FastArgs a, Fas
     const bool to_slow = need && (slow || ((ws->slowmask >> lane) & 1u));
     {
       const uint32_t sm = __ballot_sync(0xffffffffu, to_slow);
-      if (sm && lane == 0) atomicAdd(a.slow_count, __popc(sm));
+      if (sm) {
+        int at = 0;
+        if (lane == 0) at = atomicAdd(a.slow_count, __popc(sm));
+        at = __shfl_sync(0xffffffffu, at, 0) + __popc(sm & lt);
+        if (to_slow && at < BP_SLOW_LIST_CAP) a.slow_list[at] = (uint32_t)e;
+      }
     }
     if (need) {
       if (to_slow) {
@@ -558,18 +559,22 @@ int bp_launch_edge_check_fast(bpomp_ctx* ctx, const double* d_from, const double
                               const uint32_t* d_to_ids, int64_t count, uint8_t* d_valid, int32_t* d_first,
                               uint32_t* d_nstates) {
   if (ctx->world != WORLD_BOXES || !ctx->fast.enabled || !ctx->fast_mode) return 0;
-  if (count < ctx->fast_min_edges) return 0;
+  if (count < ctx->fast_min_edges || count > 0xFFFFFFFFll) return 0;
   FastArgs a;
   a.from = d_from; a.to = d_to; a.from_ids = d_from_ids; a.to_ids = d_to_ids;
   a.verts = ctx->d_verts.as<double>();
   a.count = count; a.valid = d_valid; a.first = d_first; a.nstates = d_nstates;
   a.L = ctx->L;
+  a.inv_L = (float)(1.0 / ctx->L);
+  a.magic = 0x4B000000u;
   BP_TRY(bp_reserve(ctx, ctx->d_work, 256, false));
   a.work = ctx->d_work.as<unsigned long long>() + 8 + ctx->work_slot;  // slots 0..7 belong to the general kernel
   BP_CUDA(ctx, cudaMemsetAsync(a.work, 0, sizeof(unsigned long long), ctx->stream));
   a.flags = ctx->d_flags;
   a.slow_count = reinterpret_cast<int*>(ctx->d_work.as<unsigned long long>() + 16 + ctx->work_slot);
   BP_CUDA(ctx, cudaMemsetAsync(a.slow_count, 0, sizeof(unsigned long long), ctx->stream));
+  BP_TRY(bp_reserve(ctx, ctx->d_slow_list[ctx->work_slot], (size_t)std::min<int64_t>(count, BP_SLOW_LIST_CAP) * 4, false));
+  a.slow_list = ctx->d_slow_list[ctx->work_slot].as<uint32_t>();
   a.tma_ok = (d_from && ((reinterpret_cast<uintptr_t>(d_from) | reinterpret_cast<uintptr_t>(d_to)) & 15u) == 0) ? 1 : 0;
   a.nwarps = 0;
   a.lohi = ctx->boxes.lohi;

@@ -18,8 +18,10 @@
 //   table:  lo_q = floor(q(lo)) - FP_QSLACK,  hi_q = ceil(q(hi)) + FP_QSLACK      (u16, no clamping occurs)
 //   hence   lo_q + 3 <= q(lo) < lo_q + 4   and   hi_q - 4 < q(hi) <= hi_q - 3.
 // Per edge and dimension (F = q(from_j), T = q(to_j), Dq = T - F, all FP64):
+//   (the kernel works with t = s/(n+1): inv = 1/Dq, and scales the final range by n+1, an exact float)
 //   moving dimension (|Dq| >= 1):  inv = (n+1)/Dq (FP32, relative error <= 2^-21),
-//                                  c = -(2^23 + F)*inv rounded to FP32 (error <= 0.5 ulp = 0.5*|inv|)
+//                                  c = -(2^23 + F)*inv in FP32 (error <= 0.5 ulp = 0.5*|inv|, plus 2^-8*|inv|
+//                                  from F entering as a float)
 //   s(bound) = fma(2^23 + bound_q, inv, c)   — 2^23 + bound_q is the exact float built from the u16 by a
 //   byte permute — is the sample coordinate s = k+1 at which the model line F + Dq*s/(n+1) crosses the
 //   bound, with an error equivalent to <= 0.65 q-units of position:
@@ -33,7 +35,9 @@
 //          whenever F >= lo_q + 2 (every possibly-inside case, since q(lo) - 1 >= lo_q + 2) and hugely
 //          positive for hi symmetrically, so the dimension does not constrain the OUTER range; an edge with a
 //          static dimension never uses the INNER shortcut (its hits are verified exactly).
-// Edges outside the safe zone |q| <= 2^17, with more than FP_NMAX states, with a cell span beyond the mask
+// The 16-bit bounds are only meaningful inside the mapped region, so both endpoints must lie in the safe zone
+// q in [FP_QOFF-1, FP_QOFF+FP_QSCALE+1] (bounds beyond it are clamped to 0 / 65535, which stays conservative
+// for samples inside the zone).  Edges outside the safe zone, with more than FP_NMAX states, with a cell span beyond the mask
 // classes, or with too many candidates are not handled here at all: they are marked BPOMP_EDGE_SLOW and the
 // general kernel (edge_check.cu) evaluates them.
 #pragma once
@@ -90,25 +94,49 @@ FP_HD int fp_class_span(int cls) { return cls < 7 ? cls : FP_SPAN_MAX; }
 
 // Per-edge, per-dimension FP32 data of the slab test.
 struct FpDim {
-  float inv;  // (n+1)/Dq, or FP_BIG for a static dimension
+  float inv;  // 1/Dq, or FP_BIG for a static dimension (t units: t = s/(n+1))
   float c;    // -(2^23 + F) * inv
   bool stat;
 };
 
-FP_HD FpDim fp_edge_dim(double F, double T, uint32_t n) {
+FP_HD FpDim fp_edge_dim(double F, double T) {
   FpDim r;
   const double Dq = T - F;
   const float Dqf = (float)Dq;
   r.stat = fabsf(Dqf) < 1.0f;
-  float inv;
+  float rc;
 #if defined(__CUDA_ARCH__)
-  inv = __fdividef((float)(n + 1u), Dqf);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(Dqf));  // 1 ulp
 #else
-  inv = (float)(n + 1u) / Dqf;
+  rc = 1.0f / Dqf;
 #endif
-  r.inv = r.stat ? FP_BIG : inv;
-  r.c = (float)(-(8388608.0 + F) * (double)r.inv);
+  r.inv = r.stat ? FP_BIG : rc;
+  // c = -(2^23 + F)*inv: the 2^23 part is an exact scaling, F enters as a float (its rounding, <= 2^-8 q-units,
+  // is negligible); one rounding at the end, 0.5 ulp(c) = 0.5*|inv|
+  r.c = fmaf(-r.inv, (float)F, -8388608.0f * r.inv);
   return r;
+}
+
+// nStates of initializeEdgePoints (BP.cpp:440-445) as a function of the SQUARED distance, without the FP64 square
+// root and division: thr[k] (3 <= k <= FP_NTHR) is the smallest double s with floor(sqrt(s)/L) >= k in the
+// reference's arithmetic (host-built by bisection with IEEE sqrt and division; thr[0..2] = 0), so
+// n = max(2, #{k : thr[k] <= s}) exactly.  An FP32 estimate (relative error < 2^-21, i.e. far less than one unit
+// for n < FP_NTHR) picks the neighbourhood; two exact comparisons fix it.  Returns 0 when the estimate is out of
+// the table's range (the caller then uses the FP64 formula).
+#define FP_NTHR 64u
+FP_HD uint32_t fp_nstates_thr(double dist2, float inv_L, const double* thr) {
+  float est;
+#if defined(__CUDA_ARCH__)
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(est) : "f"((float)dist2));
+#else
+  est = sqrtf((float)dist2);
+#endif
+  est *= inv_L;
+  if (!(est < (float)(FP_NTHR - 2u))) return 0u;  // also NaN
+  uint32_t ne = (uint32_t)est;
+  if (ne < 2u) ne = 2u;
+  const double s0 = thr[ne], s1 = thr[ne + 1u];
+  return ne + (dist2 >= s1 ? 1u : 0u) - (dist2 < s0 ? 1u : 0u);
 }
 
 // The exact float 2^23 + v for a 16-bit v held in the low (HI = 0) or high (HI = 1) half of w.
@@ -123,7 +151,16 @@ FP_HD float fp_magic(uint32_t w) {
 #endif
 }
 
-// Narrows the OUTER s-range [smin, smax] and the INNER one [imin, imax] by one dimension's slab.
+// From t units to sample coordinates s = t*(n+1), clamped to the samples of the edge (s = 1..n).
+FP_HD void fp_range_to_s(uint32_t n, float& smin, float& smax, float& imin, float& imax) {
+  const float np1 = (float)(n + 1u);
+  smin = fmaxf(smin * np1, 0.5f);
+  smax = fminf(smax * np1, (float)n + 0.5f);
+  imin = fmaxf(imin * np1, 0.5f);
+  imax = fminf(imax * np1, (float)n + 0.5f);
+}
+
+// Narrows the OUTER range [smin, smax] and the INNER one [imin, imax] by one dimension's slab.
 FP_HD void fp_slab(float lo_m, float hi_m, float inv, float c, float& smin, float& smax, float& imin, float& imax) {
   const float a = fmaf(lo_m, inv, c), b = fmaf(hi_m, inv, c);
   const float enter = fminf(a, b), leave = fmaxf(a, b);
@@ -151,7 +188,9 @@ FP_HD size_t fp_tmask_bytes(int D) {
 // (3 <= n <= FP_PERM4_NMAX) has 32 floats, entry i = float(1 + perm_n[1 + i]) for i < n-2 (the checked
 // slots 1..n-2, BP.cpp:510) and -1 beyond.
 #define FP_PERM4_NMAX 32u
-#define FP_PERM4_SMEM_BYTES ((FP_PERM4_NMAX - 2u) * 32u * 4u)
+#define FP_PERM4_BYTES ((FP_PERM4_NMAX - 2u) * 32u * 4u)
+#define FP_THR_BYTES ((FP_NTHR + 2u) * 8u)
+#define FP_PERM4_SMEM_BYTES (FP_PERM4_BYTES + FP_THR_BYTES) /* one block: the perm rows, then thr[] */
 FP_HD uint32_t fp_perm4_off(uint32_t n) { return (n - 3u) * 32u; }
 
 // Offset of the row of n in the table of float sample coordinates perm_s (rows n = 2..FP_NMAX, row n has n

@@ -51,6 +51,27 @@ static bool inside_exact(const World& w, int b, const double* x) {
   return true;
 }
 
+static double g_thr[FP_NTHR + 2u];
+static void build_thr(double L) {  // as ctx.cu builds the table
+  auto nst = [L](double s) { return std::floor(std::sqrt(s) / L); };
+  for (uint32_t k = 0; k < FP_NTHR + 2u; ++k) {
+    g_thr[k] = 0.0;
+    if (k < 3) continue;
+    double hi = ((double)k + 2.0) * L;
+    hi *= hi;
+    uint64_t a = 0, b;
+    memcpy(&b, &hi, 8);
+    while (b - a > 1) {
+      const uint64_t m = a + (b - a) / 2;
+      double sm;
+      memcpy(&sm, &m, 8);
+      if (nst(sm) >= (double)k) b = m;
+      else a = m;
+    }
+    memcpy(&g_thr[k], &b, 8);
+  }
+}
+
 struct Stats {
   long edges = 0, fast = 0, slow = 0, pairs = 0, hits = 0, exact_tests = 0, blocked = 0, fails = 0;
 };
@@ -74,6 +95,13 @@ static void check_edge(const World& w, const double* f, const double* to, double
     d[j] = dd;
   }
   double q = std::floor(std::sqrt((double)dist2) / L);
+  // nStates through the exact thresholds on the squared distance must equal the FP64 formula
+  {
+    const uint32_t nt = fp_nstates_thr((double)dist2, (float)(1.0 / L), g_thr);
+    const uint32_t nref = !(q >= 2.0) ? 2u : (q > 65535.0 ? 0u : (uint32_t)q);
+    if (nt != 0u && nt != nref) fail(st, "threshold nStates differs", eidx, (int)nt, (int)nref);
+    if (nt == 0u && nref != 0u && nref < FP_NTHR - 4u) fail(st, "threshold nStates gave up early", eidx, 0, (int)nref);
+  }
   if (!(q >= 2.0)) return;
   if (q > 65535.0) return;
   const uint32_t n = (uint32_t)q;
@@ -135,7 +163,7 @@ static void check_edge(const World& w, const double* f, const double* to, double
   float inv[8], cc[8];
   bool has_static = false;
   for (int j = 0; j < D; ++j) {
-    FpDim fd = fp_edge_dim(F[j], T[j], n);
+    FpDim fd = fp_edge_dim(F[j], T[j]);
     inv[j] = fd.inv;
     cc[j] = fd.c;
     has_static = has_static || fd.stat;
@@ -146,7 +174,7 @@ static void check_edge(const World& w, const double* f, const double* to, double
     if (!((cand[(b >> 7) * 4 + ((b >> 5) & 3)] >> (b & 31)) & 1u)) continue;
     st.pairs++;
     const uint16_t* qb = &w.t.qbox[(size_t)b * 16];
-    float smin = 0.5f, smax = (float)n + 0.5f, imin = smin, imax = smax;
+    float smin = -3.0e38f, smax = 3.0e38f, imin = smin, imax = smax;
     for (int j = 0; j < D; ++j) {
       const uint32_t wl = (uint32_t)qb[j & ~1] | ((uint32_t)qb[(j & ~1) + 1] << 16);
       const uint32_t wh = (uint32_t)qb[8 + (j & ~1)] | ((uint32_t)qb[8 + (j & ~1) + 1] << 16);
@@ -154,6 +182,7 @@ static void check_edge(const World& w, const double* f, const double* to, double
       const float hi_m = (j & 1) ? fp_magic<1>(wh) : fp_magic<0>(wh);
       fp_slab(lo_m, hi_m, inv[j], cc[j], smin, smax, imin, imax);
     }
+    fp_range_to_s(n, smin, smax, imin, imax);
     // 2. / 3. against every sample
     for (uint32_t k = 0; k < n; ++k) {
       const float s = (float)(k + 1);
@@ -246,6 +275,7 @@ int main(int argc, char** argv) {
     double ext2 = 0.0;
     for (int j = 0; j < D; ++j) ext2 += 1.0;
     const double L = std::sqrt(ext2) * c.frac;
+    build_thr(L);
     Stats st;
     std::vector<std::vector<int>> perms;
     std::mt19937_64 rng(7 * ci);
