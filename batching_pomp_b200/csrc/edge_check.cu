@@ -173,6 +173,8 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
       total = left;
       elist = a.list;
       only_status = 0;
+      // a short list needs few CTAs (one tile per warp); the others leave before staging the tables
+      if ((int64_t)blockIdx.x * EC_WARPS * 32 >= total) return;
     }
   }
   // layout: [WarpScratch x EC_WARPS][mbarrier 16 B][prefix masks][lohi]

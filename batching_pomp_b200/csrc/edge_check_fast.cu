@@ -27,8 +27,10 @@
 #include "world.cuh"
 
 #define FE_SLOTCAP 40    // non-zero (edge, group) masks collected before they are expanded to pairs
-#define FE_LANECAP 3     // candidates of one (edge, group) slot; more -> the edge is left to the general kernel
-#define FE_LISTCAP 96    // pairs of one expansion: 32 slots x FE_LANECAP
+#define FE_LISTCAP 64    // pairs: fewer than 32 waiting plus at most 32 appended per step
+#ifndef FE_MAXWARPS
+#define FE_MAXWARPS 20
+#endif
 #define FE_CHUNK 4       // tiles claimed per atomic
 
 struct FastArgs {
@@ -103,8 +105,7 @@ struct FeWarp {
   uint32_t list[FE_LISTCAP];       // (edge lane << 16) | box
   int32_t first[32];               // first invalid slot per edge of the tile
   uint64_t bar;                    // mbarrier of the staging buffer
-  uint32_t slowmask;               // edges with more candidates than the lists hold
-  uint32_t pad;
+  uint64_t pad;
 };
 
 // Rare path: the search for the first slot >= from_slot (< lim) of edge e inside box b when a sample lies too
@@ -147,7 +148,7 @@ __device__ __noinline__ int fe_search_exact(const FastArgs* a, const float* perm
 }
 
 template <int D, bool INDEXED>
-__global__ void __launch_bounds__(640, 1)
+__global__ void __launch_bounds__(FE_MAXWARPS * 32, 1)
     edge_check_fast_kernel(const __grid_constant__ FastArgs a, const __grid_constant__ FastWorldView w) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint4* s_tmask = reinterpret_cast<uint4*>(smem);
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(640, 1)
       const int cf = qf >> FP_CELL_SHIFT, ct = qt >> FP_CELL_SHIFT;
       const int c0 = min(cf, ct), span = max(cf, ct) - c0;
       spanmax = max(spanmax, span);
-      roff[j] = fp_row_offset(D, j, (uint32_t)(min(span, 7) * FP_CELLS + c0));
+      roff[j] = fp_row_offset(D, j, (uint32_t)(min(span, FP_CLASSES - 1) * FP_CELLS + c0));
       d[j] = __dsub_rn(d[j], f[j]);                     // interpolate: (to - from)
       dist2 = __dadd_rn(dist2, __dmul_rn(d[j], d[j]));  // distance: (from-to)^2 == (to-from)^2 exactly
       // FP32 slab data (fastpath.cuh: fp_edge_dim, with n applied below)
@@ -348,7 +349,6 @@ __global__ void __launch_bounds__(640, 1)
       }
     }
     ws->first[lane] = 0x7fffffff;
-    if (lane == 0) ws->slowmask = 0u;
     __syncwarp();
 
     // ---- C: one round over list[lbase .. lbase+cntr) (lane = pair) -----------------------------------------
@@ -419,37 +419,35 @@ __global__ void __launch_bounds__(640, 1)
           m = ws->slots[s0 + lane];
           sm = ws->smeta[s0 + lane];
         }
-        const int el = (int)(sm & 0xFFu), g = (int)(sm >> 8);
-        int c = __popc(m.x) + __popc(m.y) + __popc(m.z) + __popc(m.w);
-        if (c > FE_LANECAP) {  // dense neighbourhood: leave the edge to the general kernel
-          atomicOr(&ws->slowmask, 1u << el);
-          c = 0;
-        }
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int y = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += y;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        int pos = incl - c;
-        const uint32_t ebase = ((uint32_t)el << 16) | (uint32_t)(g * 128);
+        const uint32_t ebase = ((sm & 0xFFu) << 16) | ((sm >> 8) * 128u);  // (edge lane << 16) | first box of the group
         unsigned long long m01 = (unsigned long long)m.x | ((unsigned long long)m.y << 32);
         unsigned long long m23 = (unsigned long long)m.z | ((unsigned long long)m.w << 32);
-        while (c > 0) {
-          int bit;
-          if (m01) {
-            bit = __ffsll((long long)m01) - 1;
-            m01 &= m01 - 1;
-          } else {
-            bit = 64 + __ffsll((long long)m23) - 1;
-            m23 &= m23 - 1;
+        // every lane that still has bits appends one pair per step; 32 pairs at a time go through phase C
+        int cntl = 0;
+        uint32_t act = __ballot_sync(0xffffffffu, (m01 | m23) != 0ull);
+        while (act) {
+          if ((m01 | m23) != 0ull) {
+            int bit;
+            if (m01) {
+              bit = __ffsll((long long)m01) - 1;
+              m01 &= m01 - 1;
+            } else {
+              bit = 64 + __ffsll((long long)m23) - 1;
+              m23 &= m23 - 1;
+            }
+            ws->list[cntl + __popc(act & lt)] = ebase + (uint32_t)bit;
           }
-          ws->list[pos++] = ebase + (uint32_t)bit;
-          --c;
+          cntl += __popc(act);
+          if (cntl >= 32) {
+            __syncwarp();
+            pair_round(cntl - 32, 32);
+            cntl -= 32;
+            __syncwarp();
+          }
+          act = __ballot_sync(0xffffffffu, (m01 | m23) != 0ull);
         }
         __syncwarp();
-        for (int p0 = 0; p0 < total; p0 += 32) pair_round(p0, min(32, total - p0));
+        if (cntl > 0) pair_round(0, cntl);
         __syncwarp();
       }
     };
@@ -473,7 +471,8 @@ __global__ void __launch_bounds__(640, 1)
         const bool nz = (m.x | m.y | m.z | m.w) != 0u;
         const uint32_t act = __ballot_sync(0xffffffffu, nz);
         const int add = __popc(act);
-        if (cnts + add > FE_SLOTCAP) {  // rare: make room
+        if (cnts + add > FE_SLOTCAP) {  // rare (dense worlds): make room
+          __syncwarp();
           expand_and_test(cnts);
           cnts = 0;
         }
@@ -483,13 +482,13 @@ __global__ void __launch_bounds__(640, 1)
           ws->smeta[p] = (uint16_t)(lane | (g << 8));
         }
         cnts += add;
-        __syncwarp();
       }
+      __syncwarp();
       if (cnts > 0) expand_and_test(cnts);
     }
 
     // ---- results (lane = edge) -----------------------------------------------------------------------------
-    const bool to_slow = need && (slow || ((ws->slowmask >> lane) & 1u));
+    const bool to_slow = need && slow;
     {
       const uint32_t sm = __ballot_sync(0xffffffffu, to_slow);
       if (sm) {
@@ -526,7 +525,7 @@ static int launch_fast(bpomp_ctx* ctx, FastArgs& a) {
   const size_t per_warp = sizeof(FeWarp<D>);
   const size_t avail = (size_t)ctx->smem_optin - 64;  // the static mbarrier
   if (tables + 4 * per_warp > avail) return 0;
-  int nwarps = (int)std::min<size_t>(20, (avail - tables) / per_warp);
+  int nwarps = (int)std::min<size_t>(FE_MAXWARPS, (avail - tables) / per_warp);
   nwarps &= ~3;  // equal load on the four schedulers
   if (ctx->fast_warps > 0) nwarps = std::min(nwarps, ctx->fast_warps);
   if (nwarps < 4) return 0;

@@ -59,9 +59,11 @@
 #define FP_NMAX 255u            /* largest nStates handled by the fast kernel */
 #define FP_CELLS 32             /* broad-phase cells per dimension = q >> 11 */
 #define FP_CELL_SHIFT 11
-#define FP_CLASSES 8            /* span classes: class k < 7 -> span k, class 7 -> spans 7..FP_SPAN_MAX */
+#ifndef FP_CLASSES
+#define FP_CLASSES 8            /* span classes: class k < FP_CLASSES-1 -> span k, the last -> spans up to FP_SPAN_MAX */
+#endif
 #define FP_SPAN_MAX 13
-#define FP_ROWS_PER_DIM (FP_CLASSES * FP_CELLS) /* 256: row = class*32 + c0 fits one byte */
+#define FP_ROWS_PER_DIM (FP_CLASSES * FP_CELLS) /* row = class*32 + first cell */
 #define FP_MAXBOXES 512         /* 4 groups of 128 boxes, one per lane of a team */
 #define BPOMP_EDGE_SLOW 3u      /* internal status: left to the general kernel */
 
@@ -89,8 +91,8 @@ FP_HD uint32_t fp_q16(double q) {
 FP_HD int fp_cell(double q) { return (int)(fp_q16(q) >> FP_CELL_SHIFT); }
 
 // Span class of a cell range [c0, c0+span]; FP_CLASSES means "not covered" (slow edge).
-FP_HD int fp_class(int span) { return span < 7 ? span : (span <= FP_SPAN_MAX ? 7 : FP_CLASSES); }
-FP_HD int fp_class_span(int cls) { return cls < 7 ? cls : FP_SPAN_MAX; }
+FP_HD int fp_class(int span) { return span < FP_CLASSES - 1 ? span : (span <= FP_SPAN_MAX ? FP_CLASSES - 1 : FP_CLASSES); }
+FP_HD int fp_class_span(int cls) { return cls < FP_CLASSES - 1 ? cls : FP_SPAN_MAX; }
 
 // Per-edge, per-dimension FP32 data of the slab test.
 struct FpDim {
@@ -185,13 +187,16 @@ FP_HD size_t fp_tmask_bytes(int D) {
 }
 
 // Shared-memory copy of the sample coordinates of short edges, four slots per 16-byte load: row n
-// (3 <= n <= FP_PERM4_NMAX) has 32 floats, entry i = float(1 + perm_n[1 + i]) for i < n-2 (the checked
+// (3 <= n <= FP_PERM4_NMAX) has FP_PERM4_ROW floats, entry i = float(1 + perm_n[1 + i]) for i < n-2 (the checked
 // slots 1..n-2, BP.cpp:510) and -1 beyond.
-#define FP_PERM4_NMAX 32u
-#define FP_PERM4_BYTES ((FP_PERM4_NMAX - 2u) * 32u * 4u)
+#ifndef FP_PERM4_NMAX
+#define FP_PERM4_NMAX 16u
+#endif
+#define FP_PERM4_ROW (((FP_PERM4_NMAX - 2u) + 3u) / 4u * 4u) /* floats per row */
+#define FP_PERM4_BYTES ((FP_PERM4_NMAX - 2u) * FP_PERM4_ROW * 4u)
 #define FP_THR_BYTES ((FP_NTHR + 2u) * 8u)
 #define FP_PERM4_SMEM_BYTES (FP_PERM4_BYTES + FP_THR_BYTES) /* one block: the perm rows, then thr[] */
-FP_HD uint32_t fp_perm4_off(uint32_t n) { return (n - 3u) * 32u; }
+FP_HD uint32_t fp_perm4_off(uint32_t n) { return (n - 3u) * FP_PERM4_ROW; }
 
 // Offset of the row of n in the table of float sample coordinates perm_s (rows n = 2..FP_NMAX, row n has n
 // entries: perm_s[off(n) + slot] = float(1 + perm_n[slot])).

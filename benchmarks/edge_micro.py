@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--check", type=int, default=10 ** 6)
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--indexed", type=int, default=0, help="N > 0: also time the indexed form on r-disk rows of an "
+                    "N-vertex 7-D Halton roadmap (the planner's edge path, config 3)")
     ap.add_argument("--variants", default="general,fast,fast+bounds,fast+bounds/8,fast+bounds/12,fast+bounds/16,fast+bounds/20")
     args = ap.parse_args()
     from oracle import oracle
@@ -84,6 +86,52 @@ def main():
         print(json.dumps(rec), flush=True)
         results.append(rec)
         ctx.close()
+    if args.indexed:
+        N = args.indexed
+        verts = workloads.halton(N, d)
+        r = workloads.halton_radius(N, d)
+        for var in ("general", "fast+bounds"):
+            ctx = capi.Context(d, L)
+            if "bounds" in var:
+                ctx.set_bounds(0.0, 1.0)
+            ctx.set_world_boxes(lo, hi)
+            ctx.set_option("fast_edge_kernel", 0 if var == "general" else 1)
+            ctx.vertices_append(verts)
+            nq = 4096
+            q = (np.arange(nq, dtype=np.uint64) * (N // nq)).astype(np.uint32)
+            rp, col, dist = ctx.neighbors_radius(q, r)
+            fi = np.repeat(q, np.diff(rp.astype(np.int64)))
+            keep = fi != col
+            fi, ti = np.ascontiguousarray(fi[keep]), np.ascontiguousarray(col[keep])
+            Ei = fi.size
+            tfi_, tti_ = torch.from_numpy(fi.astype(np.int32)).to(dev), torch.from_numpy(ti.astype(np.int32)).to(dev)
+            ov_, of_, on_ = oracle.edges_check_boxes(verts[fi[:m]], verts[ti[:m]], L, lo, hi, nthreads=oracle.max_threads())
+            ctx.set_stream(stream.cuda_stream)
+
+            def runi():
+                ctx.edges_check_indexed_dev(tfi_.data_ptr(), tti_.data_ptr(), Ei, tv.data_ptr(), tfi.data_ptr(), tn.data_ptr())
+            runi()
+            ctx.sync()
+            slow = ctx.counter("slow_edges")
+            mm = min(m, Ei)
+            ok = (np.array_equal(tv[:mm].cpu().numpy(), ov_[:mm]) and np.array_equal(tfi[:mm].cpu().numpy(), of_[:mm])
+                  and np.array_equal(tn[:mm].cpu().numpy().view(np.uint32), on_[:mm]))
+            for _ in range(3):
+                runi()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(args.reps):
+                runi()
+            e1.record(stream)
+            ctx.sync()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.reps
+            rec = {"variant": "indexed:" + var, "edges": int(Ei), "ms": ms, "edges_per_s": Ei / ms * 1e3,
+                   "frac_hbm_13B": 13 * Ei / ms * 1e-6 / 6550.4, "slow_edges": slow, "parity_ok": bool(ok),
+                   "blocked": float((tv[:Ei] == 0).float().mean())}
+            print(json.dumps(rec), flush=True)
+            results.append(rec)
+            ctx.close()
     if args.out:
         with open(args.out, "w") as f:
             for r in results:

@@ -118,7 +118,7 @@ static void check_edge(const World& w, const double* f, const double* to, double
     const int cf = fp_cell(F[j]), ct = fp_cell(T[j]);
     const int c0 = std::min(cf, ct), span = std::max(cf, ct) - c0;
     spanmax = std::max(spanmax, span);
-    row[j] = std::min(span, 7) * FP_CELLS + c0;
+    row[j] = std::min(span, FP_CLASSES - 1) * FP_CELLS + c0;
   }
   if (!safe || n > FP_NMAX || spanmax > FP_SPAN_MAX) {
     st.slow++;
