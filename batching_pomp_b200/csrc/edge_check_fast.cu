@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(FE_MAXWARPS * 32, 1)
   const bool oddq = (lane & 4) != 0;
   const uint32_t lt = (1u << lane) - 1u;
 
+
   for (;;) {
     // ---- wait for the current tile ------------------------------------------------------------------------
     if (nxt_how == 1) {
@@ -388,19 +389,18 @@ __global__ void __launch_bounds__(FE_MAXWARPS * 32, 1)
                          : "=f"(s4.x), "=f"(s4.y), "=f"(s4.z), "=f"(s4.w)
                          : "r"(rowa + (uint32_t)(i0 - 1) * 4u));
             const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
-            uint32_t ok = 0, sure = 0;
+            bool found = false;  // the first slot in the OUTER range decides
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              ok |= (sv[q] >= smin && sv[q] <= smax) ? (1u << q) : 0u;
-              sure |= (sv[q] >= imin && sv[q] <= imax) ? (1u << q) : 0u;
+              const float sq = sv[q];
+              const bool ok = !found && sq >= smin && sq <= smax && i0 + q < lim;
+              if (ok) {
+                found = true;
+                if (sq >= imin && sq <= imax) hit = i0 + q;
+                else from_slot = i0 + q;  // within a few 1e-5 of a face: verified below
+              }
             }
-            ok &= (1u << min(4, lim - i0)) - 1u;
-            if (ok) {
-              const int q = __ffs((int)ok) - 1;
-              if ((sure >> q) & 1u) hit = i0 + q;
-              else from_slot = i0 + q;  // within a few 1e-5 of a face: verified below
-              break;
-            }
+            if (found) break;
           }
         }
         if (from_slot > 0)

@@ -205,6 +205,7 @@ def run_gpu(args):
     E = args.edges
     L, lo, hi, frm, to = make_workload(E, seed=4 + 100 * rank)  # every rank owns a different shard
     ctx = capi.Context(DIM, L, device=local_rank)
+    ctx.set_bounds(0.0, 1.0)  # RealVectorStateSpace bounds of the unit hypercube (a hint: results do not depend on it)
     ctx.set_world_boxes(lo, hi)
     # a dedicated (non-default) stream: the ctx launches on it and the CUDA events are recorded on it
     stream = torch.cuda.Stream(device=dev)
@@ -385,8 +386,11 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_edge": ALGO_BYTES_PER_EDGE,
-                         "kernel": "edge_check_boxes_kernel<7,false,true,4>", "avg_launch_ms": avg_launch_ms,
-                         "note": "shared-memory / latency bound well before HBM (DESIGN.md 4.1): smem wavefronts 74% of peak, issue slots 56%"},
+                         "kernel": "edge_check_fast_kernel<7,false> (+ the general kernel's launch for left-over edges: "
+                                   "none on this workload, its CTAs exit at once)",
+                         "avg_launch_ms": avg_launch_ms,
+                         "note": "instruction-issue bound (DESIGN.md 4.1): ~32 warp instructions per edge at ~70% of the "
+                                 "issue slots, shared-memory wavefronts ~64% of peak; DRAM at ~40% of the measured copy peak"},
             "e2e": {"value": world * E * e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(2 * E * DIM * 8), "d2h_bytes_per_step": int(E * 5),
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
