@@ -124,6 +124,14 @@ struct bpomp_ctx {
   std::vector<double> h_box_lo, h_box_hi;   // host copy of the boxes (tables are rebuilt when bounds change)
   bool have_bounds = false;
   double bounds_lo[BPOMP_DIM_MAX] = {0}, bounds_hi[BPOMP_DIM_MAX] = {0};
+  // d_work: 80 x u64.  Two alternating sets s of per-lane counters, so that no launch needs a memset: entry
+  // s*32 + l = tile counter of the general kernel, s*32 + 8 + l = tile counter of the fast kernel, s*32 + 16 + l
+  // = number of edges the fast kernel left over.  The fast kernel of a call zeroes the general kernel's counter
+  // of its set; the general kernel zeroes the other set's fast entries for the next call.  64 + l: tile counter
+  // of a general-kernel launch without the fast kernel (memset per launch).
+  int work_epoch[4] = {0, 0, 0, 0};
+  bool work_dirty[4] = {true, true, true, true};
+  const int* last_slow_count = nullptr;
   DevBuf d_slow_list[4];                    // per pipeline lane: indices of the edges the fast kernel left over
   int fast_mode = 1;                        // 0: never use the fast kernel (testing / tuning)
   int fast_warps = 0;                       // > 0: cap on the warps per CTA of the fast kernel (tuning)

@@ -349,10 +349,10 @@ extern "C" int bpomp_get_counter(bpomp_ctx* ctx, const char* name, int64_t* valu
   if (!ctx || !name || !value) return BPOMP_ERR_INVALID;
   if (!strcmp(name, "slow_edges")) {  // edges the fast kernel left to the general kernel in the last edge call
     *value = 0;
-    if (!ctx->d_work.p) return BPOMP_OK;
+    if (!ctx->last_slow_count) return BPOMP_OK;
     int v = 0;
     BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    BP_CUDA(ctx, cudaMemcpy(&v, ctx->d_work.as<unsigned long long>() + 16, sizeof(int), cudaMemcpyDeviceToHost));
+    BP_CUDA(ctx, cudaMemcpy(&v, ctx->last_slow_count, sizeof(int), cudaMemcpyDeviceToHost));
     *value = v;
     return BPOMP_OK;
   }

@@ -33,6 +33,8 @@ struct EdgeArgs {
                              // once when it is 0
   const uint32_t* list;      // with gate: their indices, when *gate <= list_cap (else the status bytes are scanned)
   int list_cap;
+  unsigned long long* reset0;  // with gate: counters of the other set, zeroed here for the next call's fast kernel
+  unsigned long long* reset1;
   double L;
   unsigned long long* work;  // dynamic tile counter (zeroed before the launch)
 };
@@ -167,6 +169,10 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
   int64_t total = a.count;       // edges this launch walks
   const uint32_t* elist = nullptr;  // their indices (null: 0..count-1)
   if (a.gate) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      *a.reset0 = 0ull;
+      *a.reset1 = 0ull;
+    }
     const int left = *reinterpret_cast<const volatile int*>(a.gate);
     if (left == 0) return;
     if (a.list && left <= a.list_cap) {
@@ -472,12 +478,25 @@ int bp_launch_edge_check(bpomp_ctx* ctx, const double* d_from, const double* d_t
   a.count = count; a.valid = d_valid; a.first = d_first; a.nstates = d_nstates;
   a.only_status = deferred_only ? (int)BPOMP_EDGE_DEFERRED : (fast ? (int)BPOMP_EDGE_SLOW : 0);
   a.L = ctx->L;
-  BP_TRY(bp_reserve(ctx, ctx->d_work, 256, false));
-  a.work = ctx->d_work.as<unsigned long long>() + ctx->work_slot;  // one counter per pipeline lane
-  a.gate = fast ? reinterpret_cast<const int*>(ctx->d_work.as<unsigned long long>() + 16 + ctx->work_slot) : nullptr;
-  a.list = fast ? ctx->d_slow_list[ctx->work_slot].as<uint32_t>() : nullptr;
-  a.list_cap = fast ? BP_SLOW_LIST_CAP : 0;
-  BP_CUDA(ctx, cudaMemsetAsync(a.work, 0, sizeof(unsigned long long), ctx->stream));
+  BP_TRY(bp_reserve(ctx, ctx->d_work, 80 * sizeof(unsigned long long), false));
+  const int l = ctx->work_slot;
+  unsigned long long* W = ctx->d_work.as<unsigned long long>();
+  if (fast) {  // counters of this call's set; the fast kernel has zeroed the tile counter (common.cuh: d_work)
+    const int set = ctx->work_epoch[l];
+    a.work = W + set * 32 + l;
+    a.gate = reinterpret_cast<const int*>(W + set * 32 + 16 + l);
+    a.reset0 = W + (1 - set) * 32 + 8 + l;
+    a.reset1 = W + (1 - set) * 32 + 16 + l;
+    a.list = ctx->d_slow_list[l].as<uint32_t>();
+    a.list_cap = BP_SLOW_LIST_CAP;
+  } else {
+    a.work = W + 64 + l;
+    a.gate = nullptr;
+    a.reset0 = a.reset1 = nullptr;
+    a.list = nullptr;
+    a.list_cap = 0;
+    BP_CUDA(ctx, cudaMemsetAsync(a.work, 0, sizeof(unsigned long long), ctx->stream));
+  }
   const bool indexed = d_from_ids != nullptr;
   if (ctx->world == WORLD_IMAGE) {
     int grid = (int)std::min<int64_t>((count + 255) / 256, (int64_t)ctx->num_sms * 8);
@@ -488,6 +507,10 @@ int bp_launch_edge_check(bpomp_ctx* ctx, const double* d_from, const double* d_t
   }
   ctx->launches++;
   BP_CUDA(ctx, cudaGetLastError());
+  if (fast) {  // this call's sets are consistent again: the next call on this lane uses the other set
+    ctx->work_dirty[l] = false;
+    ctx->work_epoch[l] ^= 1;
+  }
   return BPOMP_OK;
 }
 

@@ -46,7 +46,8 @@ struct FastArgs {
   double L;
   float inv_L;               // 1/L as a float (nStates estimate, fp_nstates_thr)
   uint32_t magic;            // 0x4B000000 (2^23 as float bits), an operand of the byte permutes
-  unsigned long long* work;  // dynamic tile counter (zeroed before the launch)
+  unsigned long long* work;  // dynamic tile counter (zero at launch)
+  unsigned long long* reset_general;  // tile counter of the general kernel that follows: zeroed here
   int* flags;                // [1] range errors
   int* slow_count;           // number of edges left to the general kernel (its gate)
   uint32_t* slow_list;       // their indices (the first BP_SLOW_LIST_CAP of them)
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(FE_MAXWARPS * 32, 1)
     return 2;
   };
 
-  fe_mbar_wait(&s_tbar, 0);  // tables resident
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.reset_general = 0ull;
 
   uint32_t bar_parity = 0;
   // dynamic tile distribution, FE_CHUNK consecutive tiles per claim; the claim for the next chunk is made
@@ -231,19 +232,32 @@ __global__ void __launch_bounds__(FE_MAXWARPS * 32, 1)
   int64_t cur = -1, cur_end = -1;  // current tile and end of its chunk
   int64_t nxt = -1;                // prefetched tile (already issued), -1 none
   int nxt_how = 0;
-  auto claim = [&]() -> int64_t {
+  // claims cover FE_CHUNK tiles over the first 7/8 of the batch and single tiles over the rest (balanced tail)
+  const int64_t big_claims = ntiles / 8 * 7 / FE_CHUNK;
+  auto claim = [&](int64_t& first, int64_t& end) {
     unsigned long long c = 0;
     if (lane == 0) c = atomicAdd(a.work, 1ull);
     c = __shfl_sync(0xffffffffu, c, 0);
-    return (int64_t)c * FE_CHUNK;
+    if ((int64_t)c < big_claims) {
+      first = (int64_t)c * FE_CHUNK;
+      end = first + FE_CHUNK;
+    } else {
+      first = big_claims * FE_CHUNK + ((int64_t)c - big_claims);
+      end = first + 1;
+    }
+    end = min(end, ntiles);
   };
   {
-    const int64_t c0 = claim();
+    int64_t c0, c1;
+    claim(c0, c1);
+    if (c0 < ntiles) {  // the first tile is on its way while the tables arrive
+      cur = c0;
+      cur_end = c1;
+      nxt = cur;
+      nxt_how = issue_tile(cur);
+    }
+    fe_mbar_wait(&s_tbar, 0);  // tables resident
     if (c0 >= ntiles) return;
-    cur = c0;
-    cur_end = min(ntiles, c0 + FE_CHUNK);
-    nxt = cur;
-    nxt_how = issue_tile(cur);
   }
   // lanes 4..7 of every quarter-warp walk the dimension pairs in swapped order (and start from another group),
   // so that the eight 16-byte loads of a quarter-warp always fall into eight different bank groups
@@ -278,11 +292,7 @@ __global__ void __launch_bounds__(FE_MAXWARPS * 32, 1)
     __syncwarp();  // every lane has read the staging buffer: the next tile may overwrite it
     {
       int64_t t2 = cur + 1;
-      if (t2 >= cur_end) {
-        const int64_t c0 = claim();
-        t2 = c0;
-        cur_end = min(ntiles, c0 + FE_CHUNK);
-      }
+      if (t2 >= cur_end) claim(t2, cur_end);
       if (t2 < ntiles) {
         nxt = t2;
         nxt_how = issue_tile(t2);
@@ -566,12 +576,21 @@ int bp_launch_edge_check_fast(bpomp_ctx* ctx, const double* d_from, const double
   a.L = ctx->L;
   a.inv_L = (float)(1.0 / ctx->L);
   a.magic = 0x4B000000u;
-  BP_TRY(bp_reserve(ctx, ctx->d_work, 256, false));
-  a.work = ctx->d_work.as<unsigned long long>() + 8 + ctx->work_slot;  // slots 0..7 belong to the general kernel
-  BP_CUDA(ctx, cudaMemsetAsync(a.work, 0, sizeof(unsigned long long), ctx->stream));
+  BP_TRY(bp_reserve(ctx, ctx->d_work, 80 * sizeof(unsigned long long), false));
+  const int l = ctx->work_slot;
+  unsigned long long* W = ctx->d_work.as<unsigned long long>();
+  if (ctx->work_dirty[l]) {  // first use of this lane, or a call that did not complete: zero both sets
+    for (int s2 = 0; s2 < 2; ++s2)
+      for (int k = 0; k < 3; ++k)
+        BP_CUDA(ctx, cudaMemsetAsync(W + s2 * 32 + k * 8 + l, 0, sizeof(unsigned long long), ctx->stream));
+  }
+  ctx->work_dirty[l] = true;  // until the general kernel that cleans up behind this launch is queued
+  const int set = ctx->work_epoch[l];
+  a.work = W + set * 32 + 8 + l;
+  a.reset_general = W + set * 32 + l;
   a.flags = ctx->d_flags;
-  a.slow_count = reinterpret_cast<int*>(ctx->d_work.as<unsigned long long>() + 16 + ctx->work_slot);
-  BP_CUDA(ctx, cudaMemsetAsync(a.slow_count, 0, sizeof(unsigned long long), ctx->stream));
+  a.slow_count = reinterpret_cast<int*>(W + set * 32 + 16 + l);
+  ctx->last_slow_count = a.slow_count;
   BP_TRY(bp_reserve(ctx, ctx->d_slow_list[ctx->work_slot], (size_t)std::min<int64_t>(count, BP_SLOW_LIST_CAP) * 4, false));
   a.slow_list = ctx->d_slow_list[ctx->work_slot].as<uint32_t>();
   a.tma_ok = (d_from && ((reinterpret_cast<uintptr_t>(d_from) | reinterpret_cast<uintptr_t>(d_to)) & 15u) == 0) ? 1 : 0;
@@ -582,6 +601,7 @@ int bp_launch_edge_check_fast(bpomp_ctx* ctx, const double* d_from, const double
   a.tfrac = ctx->d_tfrac.as<double>();
   const bool indexed = d_from_ids != nullptr;
   int rc = indexed ? launch_fast_dim<true>(ctx, a) : launch_fast_dim<false>(ctx, a);
+  if (rc == 0) ctx->work_dirty[l] = false;  // nothing was launched: the counters are still zero
   if (rc <= 0) return rc;
   ctx->launches++;
   BP_CUDA(ctx, cudaGetLastError());
