@@ -419,82 +419,78 @@ __global__ void __launch_bounds__(FE_MAXWARPS * 32, 1)
       }
     };
 
-    // ---- expansion of the non-zero slots [0, cnts) into (edge, box) pairs, then the pair rounds -------------
-    auto expand_and_test = [&](int cnts) {
-      for (int s0 = 0; s0 < cnts; s0 += 32) {
-        const bool sv = s0 + lane < cnts;
-        uint4 m = make_uint4(0u, 0u, 0u, 0u);
-        uint32_t sm = 0;
-        if (sv) {
-          m = ws->slots[s0 + lane];
-          sm = ws->smeta[s0 + lane];
-        }
-        const uint32_t ebase = ((sm & 0xFFu) << 16) | ((sm >> 8) * 128u);  // (edge lane << 16) | first box of the group
-        unsigned long long m01 = (unsigned long long)m.x | ((unsigned long long)m.y << 32);
-        unsigned long long m23 = (unsigned long long)m.z | ((unsigned long long)m.w << 32);
-        // every lane that still has bits appends one pair per step; 32 pairs at a time go through phase C
-        int cntl = 0;
-        uint32_t act = __ballot_sync(0xffffffffu, (m01 | m23) != 0ull);
-        while (act) {
-          if ((m01 | m23) != 0ull) {
-            int bit;
-            if (m01) {
-              bit = __ffsll((long long)m01) - 1;
-              m01 &= m01 - 1;
-            } else {
-              bit = 64 + __ffsll((long long)m23) - 1;
-              m23 &= m23 - 1;
-            }
-            ws->list[cntl + __popc(act & lt)] = ebase + (uint32_t)bit;
-          }
-          cntl += __popc(act);
-          if (cntl >= 32) {
-            __syncwarp();
-            pair_round(cntl - 32, 32);
-            cntl -= 32;
-            __syncwarp();
-          }
-          act = __ballot_sync(0xffffffffu, (m01 | m23) != 0ull);
-        }
-        __syncwarp();
-        if (cntl > 0) pair_round(0, cntl);
-        __syncwarp();
-      }
-    };
-
-    // ---- B. lane = edge: AND of the D mask rows, one 128-box group per round; lane l takes group (l + r) & 3
-    int cnts = 0;  // non-zero slots in ws->slots
+    // ---- B. lane = edge: AND of the D mask rows, one 128-box group per round (lane l takes group (l + r) & 3);
+    // the non-zero (edge, group) masks are collected in ws->slots, then expanded to (edge, box) pairs that go
+    // through phase C 32 at a time.  (One copy of each stage in the code: the kernel fits the instruction cache.)
     if (__any_sync(0xffffffffu, fastedge)) {
+      int r = 0;
+      for (;;) {
+        int cnts = 0;  // non-zero slots in ws->slots
 #pragma unroll 1
-      for (int r = 0; r < 4; ++r) {
-        const int g = (lane + r) & 3;
-        uint4 m = make_uint4(0u, 0u, 0u, 0u);
-        if (fastedge) {
-          const uint32_t gaddr = tmask_addr + (uint32_t)g * 16u;
-          m = fe_lds128(gaddr + roff[0]);
+        while (r < 4) {
+          const int g = (lane + r) & 3;
+          uint4 m = make_uint4(0u, 0u, 0u, 0u);
+          if (fastedge) {
+            const uint32_t gaddr = tmask_addr + (uint32_t)g * 16u;
+            m = fe_lds128(gaddr + roff[0]);
 #pragma unroll
-          for (int j = 1; j < D; ++j) {
-            const uint4 v = fe_lds128(gaddr + roff[j]);
-            m.x &= v.x; m.y &= v.y; m.z &= v.z; m.w &= v.w;
+            for (int j = 1; j < D; ++j) {
+              const uint4 v = fe_lds128(gaddr + roff[j]);
+              m.x &= v.x; m.y &= v.y; m.z &= v.z; m.w &= v.w;
+            }
+          }
+          const bool nz = (m.x | m.y | m.z | m.w) != 0u;
+          const uint32_t act = __ballot_sync(0xffffffffu, nz);
+          const int add = __popc(act);
+          if (cnts + add > FE_SLOTCAP) break;  // rare (dense worlds): expand what is there, then redo this round
+          if (nz) {
+            const int p = cnts + __popc(act & lt);
+            ws->slots[p] = m;
+            ws->smeta[p] = (uint16_t)(lane | (g << 8));
+          }
+          cnts += add;
+          ++r;
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int s0 = 0; s0 < cnts; s0 += 32) {
+          uint4 m = make_uint4(0u, 0u, 0u, 0u);
+          uint32_t sm = 0;
+          if (s0 + lane < cnts) {
+            m = ws->slots[s0 + lane];
+            sm = ws->smeta[s0 + lane];
+          }
+          const uint32_t ebase = ((sm & 0xFFu) << 16) | ((sm >> 8) * 128u);  // (edge lane << 16) | first box of the group
+          unsigned long long m01 = (unsigned long long)m.x | ((unsigned long long)m.y << 32);
+          unsigned long long m23 = (unsigned long long)m.z | ((unsigned long long)m.w << 32);
+          // every lane that still has bits appends one pair per step
+          int cntl = 0;
+          for (;;) {
+            const uint32_t act = __ballot_sync(0xffffffffu, (m01 | m23) != 0ull);
+            if ((m01 | m23) != 0ull) {
+              int bit;
+              if (m01) {
+                bit = __ffsll((long long)m01) - 1;
+                m01 &= m01 - 1;
+              } else {
+                bit = 64 + __ffsll((long long)m23) - 1;
+                m23 &= m23 - 1;
+              }
+              ws->list[cntl + __popc(act & lt)] = ebase + (uint32_t)bit;
+            }
+            cntl += __popc(act);
+            if (cntl >= 32 || (act == 0u && cntl > 0)) {  // a full round, or the rest
+              __syncwarp();
+              const int take = min(cntl, 32);
+              pair_round(cntl - take, take);
+              cntl -= take;
+              __syncwarp();
+            }
+            if (act == 0u && cntl == 0) break;
           }
         }
-        const bool nz = (m.x | m.y | m.z | m.w) != 0u;
-        const uint32_t act = __ballot_sync(0xffffffffu, nz);
-        const int add = __popc(act);
-        if (cnts + add > FE_SLOTCAP) {  // rare (dense worlds): make room
-          __syncwarp();
-          expand_and_test(cnts);
-          cnts = 0;
-        }
-        if (nz) {
-          const int p = cnts + __popc(act & lt);
-          ws->slots[p] = m;
-          ws->smeta[p] = (uint16_t)(lane | (g << 8));
-        }
-        cnts += add;
+        if (r >= 4) break;
       }
-      __syncwarp();
-      if (cnts > 0) expand_and_test(cnts);
     }
 
     // ---- results (lane = edge) -----------------------------------------------------------------------------
