@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
   int64_t total = a.count;       // edges this launch walks
   const uint32_t* elist = nullptr;  // their indices (null: 0..count-1)
   if (a.gate) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the fast kernel has completed and its writes are visible
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       *a.reset0 = 0ull;
       *a.reset1 = 0ull;
@@ -436,7 +437,23 @@ static int launch_boxes(bpomp_ctx* ctx, const EdgeArgs& a) {
       default: k = edge_check_boxes_kernel<D, INDEXED, true, 0>; break;
     }
     BP_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged));
-    k<<<grid, EC_THREADS, staged, ctx->stream>>>(a, w, ctx->perm_view());
+    if (a.gate) {
+      // follow-up of the fast kernel: programmatic dependent launch, so that this kernel's launch latency is
+      // hidden behind the fast kernel (it waits for it with griddepcontrol.wait before touching its results)
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(EC_THREADS);
+      cfg.dynamicSmemBytes = staged;
+      cfg.stream = ctx->stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      BP_CUDA(ctx, cudaLaunchKernelEx(&cfg, k, a, w, ctx->perm_view()));
+    } else {
+      k<<<grid, EC_THREADS, staged, ctx->stream>>>(a, w, ctx->perm_view());
+    }
   } else {
     auto k = edge_check_boxes_kernel<D, INDEXED, false, 0>;
     BP_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base));

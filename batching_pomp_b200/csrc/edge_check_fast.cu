@@ -31,7 +31,12 @@
 #ifndef FE_MAXWARPS
 #define FE_MAXWARPS 20
 #endif
-#define FE_CHUNK 4       // tiles claimed per atomic
+#ifndef FE_CHUNK
+#define FE_CHUNK 16      // consecutive tiles per static claim (long contiguous runs are kinder to DRAM)
+#endif
+#ifndef FE_TAIL8
+#define FE_TAIL8 7       // eighths of the batch claimed in chunks; the rest in single tiles
+#endif
 
 struct FastArgs {
   const double* from;        // [count][D] or null (indexed)
@@ -232,24 +237,39 @@ __global__ void __launch_bounds__(FE_MAXWARPS * 32, 1)
   int64_t cur = -1, cur_end = -1;  // current tile and end of its chunk
   int64_t nxt = -1;                // prefetched tile (already issued), -1 none
   int nxt_how = 0;
-  // claims cover FE_CHUNK tiles over the first 7/8 of the batch and single tiles over the rest (balanced tail)
-  const int64_t big_claims = ntiles / 8 * 7 / FE_CHUNK;
-  auto claim = [&](int64_t& first, int64_t& end) {
-    unsigned long long c = 0;
-    if (lane == 0) c = atomicAdd(a.work, 1ull);
-    c = __shfl_sync(0xffffffffu, c, 0);
-    if ((int64_t)c < big_claims) {
-      first = (int64_t)c * FE_CHUNK;
+  // Tile distribution.  The first FE_TAIL8/8 of the batch is dealt statically, FE_CHUNK consecutive tiles at a
+  // time, chunk c to warp (c mod #warps) — no atomics (one atomic per tile on a single address would saturate
+  // the L2 atomic unit); the rest is claimed dynamically, one tile per atomic, which balances the tail and
+  // absorbs SMs that are shared with another kernel (e.g. NCCL's).  A warp always knows its next claim one chunk
+  // ahead, so the atomic's latency is not exposed.
+  const int64_t big_claims = ntiles / 8 * FE_TAIL8 / FE_CHUNK;
+  const int64_t nwarps_grid = (int64_t)gridDim.x * (blockDim.x >> 5);
+  int64_t stat_next = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  unsigned long long ahead = 0;  // the claim made ahead (lane 0's copy counts)
+  auto claim_issue = [&]() {
+    if (stat_next < big_claims) {
+      ahead = (unsigned long long)stat_next;
+      stat_next += nwarps_grid;
+    } else if (lane == 0) {
+      ahead = (unsigned long long)big_claims + atomicAdd(a.work, 1ull);
+    }
+  };
+  auto claim_take = [&](int64_t& first, int64_t& end) {
+    const int64_t c = (int64_t)__shfl_sync(0xffffffffu, ahead, 0);
+    if (c < big_claims) {
+      first = c * FE_CHUNK;
       end = first + FE_CHUNK;
     } else {
-      first = big_claims * FE_CHUNK + ((int64_t)c - big_claims);
+      first = big_claims * FE_CHUNK + (c - big_claims);
       end = first + 1;
     }
     end = min(end, ntiles);
   };
   {
     int64_t c0, c1;
-    claim(c0, c1);
+    claim_issue();
+    claim_take(c0, c1);
+    claim_issue();
     if (c0 < ntiles) {  // the first tile is on its way while the tables arrive
       cur = c0;
       cur_end = c1;
@@ -292,7 +312,10 @@ __global__ void __launch_bounds__(FE_MAXWARPS * 32, 1)
     __syncwarp();  // every lane has read the staging buffer: the next tile may overwrite it
     {
       int64_t t2 = cur + 1;
-      if (t2 >= cur_end) claim(t2, cur_end);
+      if (t2 >= cur_end) {
+        claim_take(t2, cur_end);
+        claim_issue();
+      }
       if (t2 < ntiles) {
         nxt = t2;
         nxt_how = issue_tile(t2);
