@@ -303,6 +303,7 @@ BatchingPOMP::Edge BatchingPOMP::findEdge(Vertex u, Vertex v) const {
 
 void BatchingPOMP::clearVertex(Vertex v) {  // boost::clear_vertex, BatchingManager.hpp:163
   for (const OutEdge& oe : mOut[v]) {
+    if (!mEdges[oe.eid].removed) ++mNumRemovedEdges;
     mEdges[oe.eid].removed = true;
     if (oe.eid < mHashedUpTo) {
       const Edge* it = mEdgeIndex.find(edgeKey(v, oe.target));
@@ -794,12 +795,13 @@ std::vector<BatchingPOMP::Edge> BatchingPOMP::selectEdges(const std::vector<Edge
     std::reverse(r.begin(), r.end());
     return r;
   }
-  // failfast: ascending probFree; maxinf: ascending |probFree-0.5|.  Exact ties: path position
-  // (std::sort over pair<double,Edge> orders them by edge descriptor in the reference — unpinned).
+  // failfast: ascending probFree; maxinf: ascending |probFree-0.5|.  Exact ties: edge creation order —
+  // std::sort over pair<double,Edge> orders equal keys by the edge descriptor, which Boost orders by the
+  // address of the edge's property object, i.e. by allocation order on a fresh heap (Selector.hpp:113-146).
   std::vector<std::pair<std::pair<double, size_t>, Edge>> lst;
   for (size_t i = 0; i < ePath.size(); ++i) {
     double p = mEdges[ePath[i]].probFree;
-    lst.push_back({{mSelType == "failfast" ? p : std::fabs(p - 0.5), i}, ePath[i]});
+    lst.push_back({{mSelType == "failfast" ? p : std::fabs(p - 0.5), (size_t)ePath[i]}, ePath[i]});
   }
   std::sort(lst.begin(), lst.end());
   for (size_t i = 0; i < lst.size(); ++i) r[i] = lst[i].second;
@@ -998,12 +1000,15 @@ bool BatchingPOMP::astar(bool zeroHeuristic, bool single) {
   mSpecCache.clear();  // speculative probFree values are valid for one search (one belief-model state)
   mSearchEdgesNeeded = 0;
   if (mSpecStamp.size() < nv) mSpecStamp.resize(nv, 0);
-  const double alpha = mCurrentAlpha;
-  const double* goalState = vertexState(mGoalVertex);
-  auto h = [&](Vertex u) -> double {
-    if (zeroHeuristic) return 0.0;                                 // zero_heuristic, BP.cpp:203-206
-    return alpha * rvDistance(vertexState(u), goalState, mDim);     // exp_distance_heuristic, BP.cpp:187-190
-  };
+  // The heuristic is ZERO in every search, as in the reference as compiled: BP.cpp:870-915 passes
+  // `*heuristicFn` — static type boost::astar_heuristic<Graph,double> — to boost::astar_search, which takes
+  // its heuristic BY VALUE; the derived zero_heuristic / exp_distance_heuristic objects (BP.cpp:179-207) are
+  // sliced away and the base class's operator(), which is not virtual, returns 0.  Verified here by running
+  // the reference's own source (oracle/_ref, tests/test_oracle_vs_reference.py): with alpha*distance as the
+  // heuristic the later searches of a batch expand fewer vertices than the reference does (fewer edges
+  // created, fewer belief lookups).
+  (void)zeroHeuristic;
+  auto h = [&](Vertex) -> double { return 0.0; };
   const double radius = bmCurrRadius;  // captured when the visitor is built, BP.cpp:904
   Vertex s = mStartVertex;
   touch(s);

@@ -153,7 +153,8 @@ public:
 
   unsigned int getDimension() const { return mDim; }
   size_t numVertices() const { return mOut.size(); }
-  size_t numEdges() const { return mEdges.size(); }
+  // boost::num_edges(g): edges of vertices that pruneVertices cleared (BatchingManager.hpp:163) do not count
+  size_t numEdges() const { return mEdges.size() - mNumRemovedEdges; }
   const double* vertexState(Vertex v) const { return &mVState[(size_t)v * mDim]; }
   /// The device context; null until the first call that needed the GPU (setProblemDefinition / solve).
   bpomp_ctx* context() const { return mCtx; }
@@ -219,6 +220,7 @@ private:
   std::vector<double> mVState;                 // [nv][dim]
   std::vector<std::vector<OutEdge>> mOut;
   std::vector<EProps> mEdges;
+  size_t mNumRemovedEdges = 0;
   std::vector<uint8_t> mNNActive;              // membership in mVertexNN
   util::FlatMap64<Edge> mEdgeIndex;  // (min,max) -> edge id, replaces boost::edge's linear scan
   uint32_t mFlushed;                           // vertices already resident in the device table

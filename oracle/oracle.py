@@ -374,3 +374,137 @@ class OraclePlanner:
     @property
     def num_belief(self):
         return int(self._l.orcp_num_belief(self._h))
+
+
+# ---------------------------------------------------------------------------------------------------
+# The REFERENCE itself (oracle/_ref/libbpomp_ref.so: /root/reference/src/BatchingPOMP.cpp and the headers it
+# includes, compiled against the API stand-ins of oracle/standins — oracle/Makefile target `ref`,
+# oracle/ref_planner_shim.cpp).  Only used to pin the oracle above; never timed, never shipped.
+# ---------------------------------------------------------------------------------------------------
+def _reflib():
+    global _ref
+    if _ref is None:
+        _ref = C.CDLL(_REF_PATH)
+    if not getattr(_ref, "_bound", False):
+        if hasattr(_ref, "refp_create"):
+            _ref.refp_create.restype = C.c_void_p
+            _ref.refp_create.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
+            _ref.refp_error.restype = C.c_char_p
+            for f in ("refp_best_cost", "refp_alpha", "refp_radius", "refp_segment_length"):
+                getattr(_ref, f).restype = C.c_double
+            for f in ("refp_num_vertices", "refp_num_edges", "refp_solution_count"):
+                getattr(_ref, f).restype = C.c_uint64
+            _ref.refp_num_batches.restype = C.c_uint
+        _ref._bound = True
+    return _ref
+
+
+def ref_planner_available():
+    """True when the reference planner was compiled here (oracle/Makefile target `ref`)."""
+    return ref_available() and hasattr(_reflib(), "refp_create")
+
+
+def write_graphml(filename, states, edges=None):
+    """GraphML as the reference reads it (util/RoadmapFromFile.hpp:82-95,136-147): node attribute `state` =
+    space-separated doubles (repr round-trips exactly through `ss >> double`); optional edges."""
+    states = _f64(states)
+    with open(filename, "w") as f:
+        f.write('<?xml version="1.0" encoding="UTF-8"?>\n<graphml xmlns="http://graphml.graphdrawing.org/xmlns">\n')
+        f.write('<key id="d0" for="node" attr.name="state" attr.type="string"/>\n<graph edgedefault="undirected">\n')
+        for i, s in enumerate(states):
+            f.write('<node id="n%d"><data key="d0">%s</data></node>\n' % (i, " ".join(repr(float(x)) for x in s)))
+        if edges is not None:
+            for a, b in np.asarray(edges).reshape(-1, 2):
+                f.write('<edge source="n%d" target="n%d"/>\n' % (int(a), int(b)))
+        f.write('</graph>\n</graphml>\n')
+
+
+class RefPlanner:
+    """batching_pomp::BatchingPOMP — the reference's own class — on the unit hypercube [lo, hi]^d."""
+
+    def __init__(self, d, fraction, lo=0.0, hi=1.0):
+        self._l = _reflib()
+        self.d = d
+        self._h = C.c_void_p(self._l.refp_create(C.c_int(d), C.c_double(lo), C.c_double(hi), C.c_double(fraction)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._l.refp_destroy(self._h)
+            self._h = None
+
+    @property
+    def segment_length(self):
+        return float(self._l.refp_segment_length(self._h))
+
+    def set_world_boxes(self, lo, hi):
+        lo, hi = _f64(lo), _f64(hi)
+        self._l.refp_world_boxes(self._h, _p(lo, c_dp), _p(hi, c_dp), C.c_int(lo.shape[0]))
+
+    def set_world_image(self, pix, thr=128):
+        pix = np.ascontiguousarray(pix, dtype=np.uint8)
+        self._l.refp_world_image(self._h, _p(pix, c_u8p), C.c_int(pix.shape[1]), C.c_int(pix.shape[0]), C.c_int(thr))
+
+    def set_param(self, key, val):
+        if self._l.refp_set_param(self._h, key.encode(), str(val).encode()) != 0:
+            raise KeyError(key)
+
+    def setup(self):
+        r = self._l.refp_setup(self._h)
+        if r != 0:
+            raise RuntimeError(self._l.refp_error(self._h).decode())
+
+    def set_problem(self, start, goal):
+        start, goal = _f64(start), _f64(goal)
+        if self._l.refp_set_problem(self._h, _p(start, c_dp), _p(goal, c_dp)) != 0:
+            raise RuntimeError(self._l.refp_error(self._h).decode())
+
+    def set_ptc_budget(self, n):
+        self._l.refp_set_ptc_budget(self._h, C.c_long(n))
+
+    def solve(self):
+        st = int(self._l.refp_solve(self._h))
+        if st < 0:
+            raise RuntimeError(self._l.refp_error(self._h).decode())
+        return STATUS[st]
+
+    best_cost = property(lambda self: float(self._l.refp_best_cost(self._h)))
+    alpha = property(lambda self: float(self._l.refp_alpha(self._h)))
+    radius = property(lambda self: float(self._l.refp_radius(self._h)))
+    exhausted = property(lambda self: bool(self._l.refp_exhausted(self._h)))
+    num_batches = property(lambda self: int(self._l.refp_num_batches(self._h)))
+    num_vertices = property(lambda self: int(self._l.refp_num_vertices(self._h)))
+    num_edges = property(lambda self: int(self._l.refp_num_edges(self._h)))
+    solution_count = property(lambda self: int(self._l.refp_solution_count(self._h)))
+
+    def path_states(self):
+        out = np.zeros((4096, self.d), dtype=np.float64)
+        n = int(self._l.refp_path_states(self._h, _p(out, c_dp), C.c_int(4096)))
+        return out[:n].copy()
+
+    def counters(self):
+        c = np.zeros(4, dtype=np.uint64)
+        self._l.refp_counters(self._h, _p(c, c_u64p))
+        return {"edge_checks": int(c[0]), "coll_checks": int(c[1]), "searches": int(c[2]), "lookups": int(c[3])}
+
+
+def ref_knn_estimate(pts, vals, queries, K=15, prior=0.5, prior_weight=0.25):
+    """cspacebelief::KNNModel::addPoint / estimate of the reference (KNNModel.hpp:89-134)."""
+    pts, vals, queries = _f64(pts), _f64(vals), _f64(queries)
+    d = queries.shape[1]
+    out = np.empty(queries.shape[0], dtype=np.float64)
+    rc = _reflib().ref_knn_estimate(_p(pts, c_dp), _p(vals, c_dp), C.c_int64(vals.shape[0]), C.c_int(d),
+                                    _p(queries, c_dp), C.c_int64(queries.shape[0]), C.c_int(K), C.c_double(prior),
+                                    C.c_double(prior_weight), _p(out, c_dp))
+    if rc != 0:
+        raise RuntimeError("ref_knn_estimate failed")
+    return out
+
+
+def ref_selector(sel_type, prob_free):
+    """util::Selector<Graph>::selectEdges of the reference: evaluation order of a path's edges (positions)."""
+    p = _f64(prob_free)
+    order = np.zeros(max(p.size, 1), dtype=np.int32)
+    n = int(_reflib().ref_selector(sel_type.encode(), _p(p, c_dp), C.c_int(p.size), _p(order, c_i32p)))
+    if n < 0:
+        raise ValueError("Invalid selector type specified - %s!" % sel_type)
+    return order[:n].copy()

@@ -312,14 +312,16 @@ struct Planner {
     if (selType == "normal") return epath;
     std::vector<uint32_t> r(epath);
     if (selType == "alternate") { std::reverse(r.begin(), r.end()); return r; }
-    // failfast / maxinf: std::sort of pair<double, Edge>.  Edge descriptors compare by (source,target)
-    // of the descriptor then property address in Boost; ties in the double are broken by that order.
-    // Canonical rule here: (key, position on path) — "parity unpinned" for exact ties.
+    // failfast / maxinf: std::sort of pair<double, Edge>.  Boost orders edge descriptors by the address of
+    // their property object, so equal keys come out in allocation-address order.  Canonical rule here: edge
+    // creation order (the address order of an allocator that hands out increasing addresses; the stand-in the
+    // reference is compiled against for the pinning tests uses the same rule) — exact ties are otherwise
+    // "parity unpinned" against a real Boost build.
     std::vector<std::pair<std::pair<double, size_t>, uint32_t>> lst;
     for (size_t i = 0; i < epath.size(); ++i) {
       double p = g.edges[epath[i]].probFree;
       double key = selType == "failfast" ? p : std::fabs(p - 0.5);
-      lst.push_back({{key, i}, epath[i]});
+      lst.push_back({{key, (size_t)epath[i]}, epath[i]});
     }
     std::sort(lst.begin(), lst.end());
     for (size_t i = 0; i < lst.size(); ++i) r[i] = lst[i].second;
@@ -533,10 +535,12 @@ struct Planner {
     std::vector<int64_t> iih(nv, -1);
     pred.resize(nv); dist.assign(nv, kInf);
     for (uint32_t v = 0; v < nv; ++v) pred[v] = v;
-    auto h = [&](uint32_t u) -> double {
-      if (zeroHeuristic) return 0.0;
-      return mCurrentAlpha * vertexDistFun(u, mGoalVertex);  // BP.cpp:187-190
-    };
+    // Zero in every search: BP.cpp:870-915 hands `*heuristicFn` (static type boost::astar_heuristic<Graph,double>)
+    // to boost::astar_search, which takes the heuristic by value — the derived heuristics of BP.cpp:179-207 are
+    // sliced away and the base operator() (non-virtual) returns 0.  Pinned against the reference's own source
+    // compiled here (oracle/_ref; tests/test_oracle_vs_reference.py).
+    (void)zeroHeuristic;
+    auto h = [&](uint32_t) -> double { return 0.0; };
     double radius = bmCurrRadius;  // captured at visitor construction, BP.cpp:904
     uint32_t s = mStartVertex;
     dist[s] = 0.0;
@@ -725,5 +729,10 @@ ORC_API void orcp_counters(void* h, unsigned* out4) {
   out4[0] = p->mNumEdgeChecks; out4[1] = p->mNumCollChecks; out4[2] = p->mNumSearches; out4[3] = p->mNumLookups;
 }
 ORC_API uint64_t orcp_num_vertices(void* h) { return ((Planner*)h)->g.vstate.size(); }
-ORC_API uint64_t orcp_num_edges(void* h) { return ((Planner*)h)->g.edges.size(); }
+// boost::num_edges(g): the edges clear_vertex removed (BatchingManager.hpp:163) do not count
+ORC_API uint64_t orcp_num_edges(void* h) {
+  uint64_t n = 0;
+  for (const EProps& e : ((Planner*)h)->g.edges) n += e.removed ? 0 : 1;
+  return n;
+}
 ORC_API uint64_t orcp_num_belief(void* h) { return ((Planner*)h)->beliefVals.size(); }
