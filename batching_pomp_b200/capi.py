@@ -62,6 +62,18 @@ SIGNATURES = {
     "bpomp_belief_estimate": (C.c_int, [vp, vp, C.c_int64, vp]),
     "bpomp_belief_edge_pfree": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp]),
     "bpomp_belief_edge_pfree_indexed": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp]),
+    "bpomp_belief_estimate_dev": (C.c_int, [vp, vp, C.c_int64, vp]),
+    "bpomp_shard_range": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "bpomp_comm_unique_id": (C.c_int, [vp, C.c_size_t]),
+    "bpomp_comm_init_rank": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+    "bpomp_comm_init": (C.c_int, [C.POINTER(vp), C.c_int]),
+    "bpomp_comm_destroy": (C.c_int, [vp]),
+    "bpomp_comm_rank": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "bpomp_edges_check_sharded": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp, vp]),
+    "bpomp_edges_check_sharded_dev": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp]),
+    "bpomp_comm_wait": (C.c_int, [vp]),
+    "bpomp_neighbors_radius_sharded": (C.c_int, [vp, vp, C.c_uint32, C.c_double, c_u64p]),
+    "bpomp_belief_estimate_sharded": (C.c_int, [vp, vp, C.c_int64, vp]),
 }
 
 _lib = None
@@ -282,6 +294,45 @@ class Context:
         self._ck(self.lib.bpomp_edge_states(self.h, _ptr(f), _ptr(t), _ptr(out), n.value, C.byref(n)))
         return out
 
+    # ---- multi-GPU ----------------------------------------------------------------------
+    def comm_init_rank(self, nranks, rank, unique_id):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._ck(self.lib.bpomp_comm_init_rank(self.h, int(nranks), int(rank), buf))
+
+    def comm_rank(self):
+        r, n = C.c_int(0), C.c_int(1)
+        self._ck(self.lib.bpomp_comm_rank(self.h, C.byref(r), C.byref(n)))
+        return int(r.value), int(n.value)
+
+    def comm_wait(self):
+        self._ck(self.lib.bpomp_comm_wait(self.h))
+
+    def edges_check_sharded(self, frm, to):
+        f, t = _f64(frm).reshape(-1, self.dim), _f64(to).reshape(-1, self.dim)
+        n = f.shape[0]
+        valid = np.empty(n, dtype=np.uint8)
+        first = np.empty(n, dtype=np.int32)
+        ns = np.empty(n, dtype=np.uint32)
+        self._ck(self.lib.bpomp_edges_check_sharded(self.h, _ptr(f), _ptr(t), n, _ptr(valid), _ptr(first), _ptr(ns)))
+        return valid, first, ns
+
+    def edges_check_sharded_dev(self, d_from, d_to, shard_count, d_valid, d_first, d_nstates, d_packed, d_packed_all):
+        self._ck(self.lib.bpomp_edges_check_sharded_dev(self.h, _ptr(d_from), _ptr(d_to), int(shard_count), _ptr(d_valid),
+                                                        _ptr(d_first), _ptr(d_nstates) if d_nstates else None,
+                                                        _ptr(d_packed), _ptr(d_packed_all)))
+
+    def neighbors_radius_sharded(self, query_ids, r):
+        q = _u32(query_ids)
+        nnz = C.c_uint64(0)
+        self._ck(self.lib.bpomp_neighbors_radius_sharded(self.h, _ptr(q), q.size, float(r), C.byref(nnz)))
+        return self._fetch(q.size, int(nnz.value))
+
+    def belief_estimate_sharded(self, queries):
+        q = _f64(queries).reshape(-1, self.dim)
+        out = np.empty(q.shape[0], dtype=np.float64)
+        self._ck(self.lib.bpomp_belief_estimate_sharded(self.h, _ptr(q), q.shape[0], _ptr(out)))
+        return out
+
     # ---- belief --------------------------------------------------------------------------
     def belief_config(self, k=15, prior=0.5, prior_weight=0.25):
         self._ck(self.lib.bpomp_belief_config(self.h, int(k), float(prior), float(prior_weight)))
@@ -325,6 +376,31 @@ class Context:
         nl = np.empty(n, dtype=np.uint32)
         self._ck(self.lib.bpomp_belief_edge_pfree_indexed(self.h, _ptr(f), _ptr(t), n, _ptr(pf), _ptr(nl)))
         return pf, nl
+
+
+def shard_range(count, nranks, rank):
+    b, e = C.c_int64(0), C.c_int64(0)
+    rc = load().bpomp_shard_range(int(count), int(nranks), int(rank), C.byref(b), C.byref(e))
+    if rc != 0:
+        raise BpompError(rc, "bpomp_shard_range")
+    return int(b.value), int(e.value)
+
+
+def comm_unique_id():
+    """128-byte NCCL id made by rank 0 (pass it to every rank's Context.comm_init_rank)."""
+    buf = (C.c_char * 128)()
+    rc = load().bpomp_comm_unique_id(buf, 128)
+    if rc != 0:
+        raise BpompError(rc, load().bpomp_last_error(None).decode())
+    return bytes(buf)
+
+
+def comm_init_all(contexts):
+    """One process driving several contexts (contexts[i] becomes rank i)."""
+    arr = (vp * len(contexts))(*[c.h for c in contexts])
+    rc = load().bpomp_comm_init(arr, len(contexts))
+    if rc != 0:
+        raise BpompError(rc, load().bpomp_last_error(contexts[0].h).decode())
 
 
 def bisect_perm(n):

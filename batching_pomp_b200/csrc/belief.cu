@@ -438,6 +438,13 @@ extern "C" int bpomp_belief_estimate(bpomp_ctx* ctx, const double* queries, int6
   return BPOMP_OK;
 }
 
+extern "C" int bpomp_belief_estimate_dev(bpomp_ctx* ctx, const double* d_queries, int64_t nq, double* d_out) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  if (nq < 0 || (nq > 0 && (!d_queries || !d_out))) return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
+  if (nq == 0) return BPOMP_OK;
+  return knn_estimate_dispatch(ctx, d_queries, nq, d_out, ctx->s_c, ctx->s_d);
+}
+
 // count pass + scan + (resolve missing sample orders); leaves nst in s_e, offsets in s_g
 template <int D>
 static int edges_count_scan(bpomp_ctx* ctx, const EdgeSrc& src, int64_t count, int mode, const int32_t* d_first,

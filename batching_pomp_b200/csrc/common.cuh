@@ -96,8 +96,11 @@ enum WorldKind { WORLD_NONE = 0, WORLD_BOXES = 1, WORLD_IMAGE = 2 };
 // ---------------------------------------------------------------------------
 // The context.
 // ---------------------------------------------------------------------------
+struct bpomp_comm;  // comm.cu
+
 struct bpomp_ctx {
   int device = 0;
+  bpomp_comm* comm = nullptr;  // multi-GPU communicator (comm.cu), null for a single GPU
   int dim = 0;
   double L = 0.0;
   int num_sms = 148;
@@ -186,6 +189,10 @@ int bp_launch_edge_check_fast(bpomp_ctx* ctx, const double* d_from, const double
                               const uint32_t* d_to_ids, int64_t count, uint8_t* d_valid, int32_t* d_first,
                               uint32_t* d_nstates);
 int bp_build_fast_world(bpomp_ctx* ctx);
+// device buffers in and out; uploads missing sample orders and re-runs the affected edges (waits for the stream)
+int bp_edges_check_resolved(bpomp_ctx* ctx, const double* d_from, const double* d_to, const uint32_t* d_from_ids,
+                            const uint32_t* d_to_ids, int64_t count, uint8_t* d_valid, int32_t* d_first,
+                            uint32_t* d_nstates);
 
 // ---------------------------------------------------------------------------
 // Device arithmetic.  Everything that must be bit-equal to the reference's unfused x86-64

@@ -281,6 +281,7 @@ extern "C" void bpomp_destroy(bpomp_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  bpomp_comm_destroy(ctx);
   DevBuf* bufs[] = {&ctx->d_perm_off, &ctx->d_tfrac, &ctx->d_step, &ctx->d_need, &ctx->d_lohi, &ctx->d_rmask,
                     &ctx->d_bits, &ctx->d_work, &ctx->d_tmask, &ctx->d_qbox, &ctx->d_perm_s, &ctx->d_perm4, &ctx->d_verts, &ctx->d_active, &ctx->d_nb_rowptr, &ctx->d_nb_col,
                     &ctx->d_nb_dist, &ctx->d_nb_query, &ctx->d_nb_tmp, &ctx->d_nb_tmp2, &ctx->d_grid_cell_start,

@@ -581,6 +581,13 @@ static int resolve_deferred(bpomp_ctx* ctx, const double* d_from, const double* 
   return BPOMP_OK;
 }
 
+int bp_edges_check_resolved(bpomp_ctx* ctx, const double* d_from, const double* d_to, const uint32_t* d_from_ids,
+                            const uint32_t* d_to_ids, int64_t count, uint8_t* d_valid, int32_t* d_first,
+                            uint32_t* d_nstates) {
+  BP_TRY(bp_launch_edge_check(ctx, d_from, d_to, d_from_ids, d_to_ids, count, d_valid, d_first, d_nstates, false));
+  return resolve_deferred(ctx, d_from, d_to, d_from_ids, d_to_ids, count, d_valid, d_first, d_nstates);
+}
+
 // Large host-buffer batches are pipelined: chunks of EC_PIPE_CHUNK edges alternate over EC_PIPE_LANES
 // streams, each doing H2D -> kernel -> D2H on its own staging buffers, so the copies of one chunk overlap
 // the kernel and the copies of the others (the call is PCIe-bound: 112 B in + 5..9 B out per 7-DoF edge).

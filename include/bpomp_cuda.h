@@ -31,6 +31,7 @@
 #ifndef BPOMP_CUDA_H_
 #define BPOMP_CUDA_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -201,6 +202,7 @@ BPOMP_API int bpomp_belief_size(bpomp_ctx* ctx, uint64_t* count);
 BPOMP_API int bpomp_belief_clear(bpomp_ctx* ctx);
 /* estimate — KNNModel.hpp:101-134 with beliefDistanceFunction (src/BatchingPOMP.cpp:213-219). */
 BPOMP_API int bpomp_belief_estimate(bpomp_ctx* ctx, const double* queries, int64_t nq, double* out);
+BPOMP_API int bpomp_belief_estimate_dev(bpomp_ctx* ctx, const double* d_queries, int64_t nq, double* d_out);
 /* computeAndSetEdgeFreeProbability — src/BatchingPOMP.cpp:464-493: pfree[e] = prod over slots
  * i = 1, 1+step, ... < n-1 of (1 - estimate(state_i)), step = (unsigned)(n/log(n));
  * nlookups[e] = number of estimate calls (mNumLookups, :480).  nlookups may be NULL. */
@@ -208,6 +210,42 @@ BPOMP_API int bpomp_belief_edge_pfree(bpomp_ctx* ctx, const double* from, const 
                                       double* pfree, uint32_t* nlookups);
 BPOMP_API int bpomp_belief_edge_pfree_indexed(bpomp_ctx* ctx, const uint32_t* from_ids, const uint32_t* to_ids,
                                               int64_t count, double* pfree, uint32_t* nlookups);
+
+/* ---- multi-GPU (no counterpart in the reference, which is one thread in one process) ------
+ * One bpomp_ctx per GPU.  The collision world, the vertex table and the belief points are REPLICATED: every
+ * rank makes the same bpomp_world_* / bpomp_vertices_* / bpomp_belief_* calls.  The units of a batch (edges,
+ * query vertices, belief queries) are sharded, rank g owning [count*g/G, count*(g+1)/G) (bpomp_shard_range);
+ * every rank evaluates its shard and the results are all-gathered device-to-device over NCCL (NVLink /
+ * NVSwitch), so each rank returns the complete result in the unsharded order.  The *_sharded calls are
+ * collective: every rank calls them with the same arguments.  NCCL is loaded at run time (libnccl.so.2). */
+BPOMP_API int bpomp_shard_range(int64_t count, int nranks, int rank, int64_t* begin, int64_t* end);
+/* One process (or thread) per GPU: rank 0 makes the id (128 bytes), every rank passes it to init_rank. */
+BPOMP_API int bpomp_comm_unique_id(void* id, size_t bytes);
+BPOMP_API int bpomp_comm_init_rank(bpomp_ctx* ctx, int nranks, int rank, const void* id);
+/* One process driving ngpus contexts (ctxs[i] becomes rank i).  Collective calls on them must then be made
+ * from one thread per context. */
+BPOMP_API int bpomp_comm_init(bpomp_ctx** ctxs, int ngpus);
+BPOMP_API int bpomp_comm_destroy(bpomp_ctx* ctx);
+BPOMP_API int bpomp_comm_rank(bpomp_ctx* ctx, int* rank, int* nranks);
+/* bpomp_edges_check over all ranks: the same host arrays on every rank, results complete on every rank. */
+BPOMP_API int bpomp_edges_check_sharded(bpomp_ctx* ctx, const double* from, const double* to, int64_t count,
+                                        uint8_t* valid, int32_t* first_invalid_slot, uint32_t* nstates);
+/* Device-resident form for equal shards: this rank's shard in, its results out, and the status flags of ALL
+ * ranks merged in packed form (bpomp_edge_status_pack_dev layout per shard, shards in rank order:
+ * d_packed_all holds nranks * ((shard_count+15)/16) words).  First-invalid slots stay with the shard owner
+ * (it replays the belief inserts).  Asynchronous: the merge runs on the communicator's own stream and overlaps
+ * the next batch's kernel; bpomp_comm_wait makes the ctx stream wait for it. */
+BPOMP_API int bpomp_edges_check_sharded_dev(bpomp_ctx* ctx, const double* d_from_shard, const double* d_to_shard,
+                                            int64_t shard_count, uint8_t* d_valid_shard, int32_t* d_first_shard,
+                                            uint32_t* d_nstates_shard, uint32_t* d_packed_shard,
+                                            uint32_t* d_packed_all);
+BPOMP_API int bpomp_comm_wait(bpomp_ctx* ctx);
+/* bpomp_neighbors_radius with the query vertices sharded; afterwards the complete CSR is this ctx's
+ * neighbour result (bpomp_neighbors_fetch / bpomp_neighbors_device). */
+BPOMP_API int bpomp_neighbors_radius_sharded(bpomp_ctx* ctx, const uint32_t* query_ids, uint32_t nq, double r,
+                                             uint64_t* nnz);
+/* bpomp_belief_estimate with the queries sharded. */
+BPOMP_API int bpomp_belief_estimate_sharded(bpomp_ctx* ctx, const double* queries, int64_t nq, double* out);
 
 #ifdef __cplusplus
 }
