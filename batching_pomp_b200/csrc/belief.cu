@@ -29,6 +29,7 @@
 
 extern "C" int bpomp_belief_config(bpomp_ctx* ctx, int k, double prior, double prior_weight) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (k < 1 || k > BK_KMAX) return bp_fail(ctx, BPOMP_ERR_INVALID, "k must be in 1..%d", BK_KMAX);
   ctx->knn = k;
   ctx->prior = prior;
@@ -38,12 +39,14 @@ extern "C" int bpomp_belief_config(bpomp_ctx* ctx, int k, double prior, double p
 
 extern "C" int bpomp_belief_size(bpomp_ctx* ctx, uint64_t* count) {
   if (!ctx || !count) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   *count = ctx->bel_count;
   return BPOMP_OK;
 }
 
 extern "C" int bpomp_belief_clear(bpomp_ctx* ctx) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   ctx->bel_count = 0;
   return BPOMP_OK;
 }
@@ -59,6 +62,7 @@ static int belief_grow(bpomp_ctx* ctx, uint64_t extra) {
 
 extern "C" int bpomp_belief_append(bpomp_ctx* ctx, const double* states, const double* values, int64_t count) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (count < 0 || (count > 0 && (!states || !values))) return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
   if (count == 0) return BPOMP_OK;
   BP_TRY(belief_grow(ctx, (uint64_t)count));
@@ -426,6 +430,7 @@ static int knn_estimate_dispatch(bpomp_ctx* ctx, const double* d_q, int64_t nq, 
 
 extern "C" int bpomp_belief_estimate(bpomp_ctx* ctx, const double* queries, int64_t nq, double* out) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (nq < 0 || (nq > 0 && (!queries || !out))) return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
   if (nq == 0) return BPOMP_OK;
   size_t bytes = (size_t)nq * ctx->dim * sizeof(double);
@@ -440,6 +445,7 @@ extern "C" int bpomp_belief_estimate(bpomp_ctx* ctx, const double* queries, int6
 
 extern "C" int bpomp_belief_estimate_dev(bpomp_ctx* ctx, const double* d_queries, int64_t nq, double* d_out) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (nq < 0 || (nq > 0 && (!d_queries || !d_out))) return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
   if (nq == 0) return BPOMP_OK;
   return knn_estimate_dispatch(ctx, d_queries, nq, d_out, ctx->s_c, ctx->s_d);
@@ -577,6 +583,7 @@ static int append_checked_dispatch(bpomp_ctx* ctx, const EdgeSrc& src, int64_t c
 extern "C" int bpomp_belief_edge_pfree(bpomp_ctx* ctx, const double* from, const double* to, int64_t count,
                                        double* pfree, uint32_t* nlookups) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (count < 0 || (count > 0 && (!from || !to || !pfree))) return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
   if (count == 0) return BPOMP_OK;
   EdgeSrc src;
@@ -587,6 +594,7 @@ extern "C" int bpomp_belief_edge_pfree(bpomp_ctx* ctx, const double* from, const
 extern "C" int bpomp_belief_edge_pfree_indexed(bpomp_ctx* ctx, const uint32_t* from_ids, const uint32_t* to_ids,
                                                int64_t count, double* pfree, uint32_t* nlookups) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (count < 0 || (count > 0 && (!from_ids || !to_ids || !pfree)))
     return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
   if (count == 0) return BPOMP_OK;
@@ -598,6 +606,7 @@ extern "C" int bpomp_belief_edge_pfree_indexed(bpomp_ctx* ctx, const uint32_t* f
 extern "C" int bpomp_belief_append_checked(bpomp_ctx* ctx, const double* from, const double* to,
                                            const int32_t* first_invalid_slot, int64_t count) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (count < 0 || (count > 0 && (!from || !to || !first_invalid_slot)))
     return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
   if (count == 0) return BPOMP_OK;

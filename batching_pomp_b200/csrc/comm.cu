@@ -117,6 +117,7 @@ static int comm_attach(bpomp_ctx* ctx, ncclComm_t comm, int nranks, int rank) {
 
 extern "C" int bpomp_comm_init_rank(bpomp_ctx* ctx, int nranks, int rank, const void* id) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (nranks < 1 || rank < 0 || rank >= nranks || !id) return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
   if (ctx->comm) return bp_fail(ctx, BPOMP_ERR_INVALID, "this context already has a communicator");
   if (!nccl_load()) return bp_fail(ctx, BPOMP_ERR_CUDA, "%s", g_nccl.err.c_str());
@@ -143,6 +144,7 @@ extern "C" int bpomp_comm_init(bpomp_ctx** ctxs, int ngpus) {
 
 extern "C" int bpomp_comm_destroy(bpomp_ctx* ctx) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   bpomp_comm* c = ctx->comm;
   if (!c) return BPOMP_OK;
   cudaSetDevice(ctx->device);
@@ -161,6 +163,7 @@ extern "C" int bpomp_comm_destroy(bpomp_ctx* ctx) {
 
 extern "C" int bpomp_comm_rank(bpomp_ctx* ctx, int* rank, int* nranks) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (rank) *rank = ctx->comm ? ctx->comm->rank : 0;
   if (nranks) *nranks = ctx->comm ? ctx->comm->nranks : 1;
   return BPOMP_OK;
@@ -193,6 +196,7 @@ static std::vector<int64_t> shard_bounds(int64_t count, int nranks) {
 
 #define BP_NEED_COMM(ctx)                                                                                \
   if (!(ctx)) return BPOMP_ERR_INVALID;                                                                  \
+  bp_enter(ctx);                                                                                         \
   if (!(ctx)->comm) return bp_fail((ctx), BPOMP_ERR_INVALID, "no communicator: call bpomp_comm_init / bpomp_comm_init_rank first")
 
 // ---------------------------------------------------------------------------
@@ -247,6 +251,9 @@ extern "C" int bpomp_edges_check_sharded_dev(bpomp_ctx* ctx, const double* d_fro
     return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
   bpomp_comm* c = ctx->comm;
   BP_TRY(bpomp_edges_check_dev(ctx, d_from_shard, d_to_shard, shard_count, d_valid_shard, d_first_shard, d_nstates_shard));
+  // the previous merge (which ran under the kernel just queued) must be done before the packed buffers are
+  // written again: with two alternating buffer sets nothing that is still being gathered is overwritten
+  if (c->pending) BP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, c->ev_done, 0));
   BP_TRY(bpomp_edge_status_pack_dev(ctx, d_valid_shard, shard_count, d_packed_shard));
   BP_CUDA(ctx, cudaEventRecord(c->ev_ready, ctx->stream));
   BP_CUDA(ctx, cudaStreamWaitEvent(c->stream, c->ev_ready, 0));

@@ -170,6 +170,10 @@ struct bpomp_ctx {
   PermView perm_view() const;
 };
 
+// Every entry point makes the context's device current first: a process may drive several contexts (one per
+// GPU) from one or several threads, and the CUDA current device is per-thread state.
+inline void bp_enter(const bpomp_ctx* ctx) { cudaSetDevice(ctx->device); }
+
 // internal cross-file helpers
 int bp_read_flags(bpomp_ctx* ctx);
 int bp_perm_ensure_rows(bpomp_ctx* ctx, const std::vector<uint32_t>& ns);

@@ -145,6 +145,7 @@ int bp_perm_ensure_rows(bpomp_ctx* ctx, const std::vector<uint32_t>& ns) {
 
 extern "C" int bpomp_perm_reserve(bpomp_ctx* ctx, uint32_t nmax) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (nmax > BPOMP_NSTATES_MAX) nmax = BPOMP_NSTATES_MAX;
   if (nmax <= ctx->perm_reserved) return BPOMP_OK;
   std::vector<uint32_t> ns;
@@ -314,6 +315,7 @@ int bp_read_flags(bpomp_ctx* ctx) {
 
 extern "C" int bpomp_sync(bpomp_ctx* ctx) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   BP_TRY(bp_read_flags(ctx));
   if (ctx->h_flags[1]) {
     ctx->h_flags[1] = 0;
@@ -332,6 +334,7 @@ extern "C" int bpomp_sync(bpomp_ctx* ctx) {
 
 extern "C" int bpomp_set_stream(bpomp_ctx* ctx, void* cuda_stream) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
   return BPOMP_OK;
@@ -339,6 +342,7 @@ extern "C" int bpomp_set_stream(bpomp_ctx* ctx, void* cuda_stream) {
 
 extern "C" int bpomp_set_option(bpomp_ctx* ctx, const char* name, int64_t value) {
   if (!ctx || !name) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (!strcmp(name, "fast_edge_kernel")) ctx->fast_mode = value ? 1 : 0;
   else if (!strcmp(name, "fast_edge_min_edges")) ctx->fast_min_edges = value < 0 ? 0 : value;
   else if (!strcmp(name, "fast_edge_warps")) ctx->fast_warps = (int)value;
@@ -348,6 +352,7 @@ extern "C" int bpomp_set_option(bpomp_ctx* ctx, const char* name, int64_t value)
 
 extern "C" int bpomp_get_counter(bpomp_ctx* ctx, const char* name, int64_t* value) {
   if (!ctx || !name || !value) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (!strcmp(name, "slow_edges")) {  // edges the fast kernel left to the general kernel in the last edge call
     *value = 0;
     if (!ctx->last_slow_count) return BPOMP_OK;
@@ -372,6 +377,7 @@ extern "C" uint64_t bpomp_launch_count(const bpomp_ctx* ctx) { return ctx ? ctx-
 // ---------------------------------------------------------------------------
 extern "C" int bpomp_vertices_append(bpomp_ctx* ctx, const double* states, uint32_t count, uint32_t* first_id) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (first_id) *first_id = ctx->nverts;
   if (count == 0) return BPOMP_OK;
   if (!states) return bp_fail(ctx, BPOMP_ERR_INVALID, "states is NULL");
@@ -392,6 +398,7 @@ extern "C" int bpomp_vertices_append(bpomp_ctx* ctx, const double* states, uint3
 
 extern "C" int bpomp_vertices_set_active(bpomp_ctx* ctx, const uint32_t* ids, uint32_t count, int flag) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (count == 0) return BPOMP_OK;
   if (!ids) return bp_fail(ctx, BPOMP_ERR_INVALID, "ids is NULL");
   for (uint32_t i = 0; i < count; ++i)
@@ -406,12 +413,14 @@ extern "C" int bpomp_vertices_set_active(bpomp_ctx* ctx, const uint32_t* ids, ui
 
 extern "C" int bpomp_vertices_count(bpomp_ctx* ctx, uint32_t* count) {
   if (!ctx || !count) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   *count = ctx->nverts;
   return BPOMP_OK;
 }
 
 extern "C" int bpomp_vertices_clear(bpomp_ctx* ctx) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   ctx->nverts = 0;
   ctx->h_active.clear();
   ctx->grid_valid = false;

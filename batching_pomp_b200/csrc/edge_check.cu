@@ -537,6 +537,7 @@ int bp_launch_edge_check(bpomp_ctx* ctx, const double* d_from, const double* d_t
 extern "C" int bpomp_edges_check_dev(bpomp_ctx* ctx, const double* d_from, const double* d_to, int64_t count,
                                      uint8_t* d_valid, int32_t* d_first, uint32_t* d_nstates) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (count < 0 || (count > 0 && (!d_from || !d_to || !d_valid || !d_first)))
     return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
   return bp_launch_edge_check(ctx, d_from, d_to, nullptr, nullptr, count, d_valid, d_first, d_nstates, false);
@@ -546,6 +547,7 @@ extern "C" int bpomp_edges_check_indexed_dev(bpomp_ctx* ctx, const uint32_t* d_f
                                              int64_t count, uint8_t* d_valid, int32_t* d_first,
                                              uint32_t* d_nstates) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (count < 0 || (count > 0 && (!d_from_ids || !d_to_ids || !d_valid || !d_first)))
     return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
   return bp_launch_edge_check(ctx, nullptr, nullptr, d_from_ids, d_to_ids, count, d_valid, d_first, d_nstates, false);
@@ -707,6 +709,7 @@ static int edges_check_host(bpomp_ctx* ctx, const double* from, const double* to
 extern "C" int bpomp_edges_check(bpomp_ctx* ctx, const double* from, const double* to, int64_t count,
                                  uint8_t* valid, int32_t* first_invalid_slot, uint32_t* nstates) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (count < 0 || (count > 0 && (!from || !to || !valid || !first_invalid_slot)))
     return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
   return edges_check_host(ctx, from, to, nullptr, nullptr, count, valid, first_invalid_slot, nstates);
@@ -716,6 +719,7 @@ extern "C" int bpomp_edges_check_indexed(bpomp_ctx* ctx, const uint32_t* from_id
                                          int64_t count, uint8_t* valid, int32_t* first_invalid_slot,
                                          uint32_t* nstates) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (count < 0 || (count > 0 && (!from_ids || !to_ids || !valid || !first_invalid_slot)))
     return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
   return edges_check_host(ctx, nullptr, nullptr, from_ids, to_ids, count, valid, first_invalid_slot, nstates);
@@ -781,6 +785,7 @@ static int status_grid(bpomp_ctx* ctx, int64_t count) {
 
 extern "C" int bpomp_edge_status_pack_dev(bpomp_ctx* ctx, const uint8_t* d_valid, int64_t count, uint32_t* d_packed) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (count < 0 || (count > 0 && (!d_valid || !d_packed))) return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
   if (count == 0) return BPOMP_OK;
   status_pack_kernel<<<status_grid(ctx, count), 256, 0, ctx->stream>>>(d_valid, count, d_packed);
@@ -792,6 +797,7 @@ extern "C" int bpomp_edge_status_pack_dev(bpomp_ctx* ctx, const uint8_t* d_valid
 extern "C" int bpomp_edge_status_unpack_dev(bpomp_ctx* ctx, const uint32_t* d_packed, int64_t count,
                                             uint8_t* d_valid) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (count < 0 || (count > 0 && (!d_valid || !d_packed))) return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
   if (count == 0) return BPOMP_OK;
   status_unpack_kernel<<<status_grid(ctx, count), 256, 0, ctx->stream>>>(d_packed, count, d_valid);
@@ -812,6 +818,7 @@ __global__ void edge_nstates_kernel(const double* f, const double* t, int D, dou
 extern "C" int bpomp_edge_states(bpomp_ctx* ctx, const double* from, const double* to, double* out, uint32_t cap,
                                  uint32_t* nstates) {
   if (!ctx || !from || !to || !nstates) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   const int D = ctx->dim;
   BP_TRY(bp_reserve(ctx, ctx->s_a, 2 * D * sizeof(double) + 16, false));
   double* df = ctx->s_a.as<double>();

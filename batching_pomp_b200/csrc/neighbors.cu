@@ -870,6 +870,7 @@ static int neighbors_dispatch(bpomp_ctx* ctx, const uint32_t* d_query, uint32_t 
 
 extern "C" int bpomp_neighbors_radius(bpomp_ctx* ctx, const uint32_t* query_ids, uint32_t nq, double r, uint64_t* nnz) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (nq > 0 && !query_ids) return bp_fail(ctx, BPOMP_ERR_INVALID, "query_ids is NULL");
   if (!(r >= 0.0)) return bp_fail(ctx, BPOMP_ERR_INVALID, "radius must be >= 0");
   for (uint32_t i = 0; i < nq; ++i)
@@ -890,6 +891,7 @@ extern "C" int bpomp_neighbors_radius(bpomp_ctx* ctx, const uint32_t* query_ids,
 
 extern "C" int bpomp_neighbors_all(bpomp_ctx* ctx, double r, uint64_t* nnz) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (!(r >= 0.0)) return bp_fail(ctx, BPOMP_ERR_INVALID, "radius must be >= 0");
   if (ctx->nverts == 0) {
     ctx->nb_nnz = 0;
@@ -904,6 +906,7 @@ extern "C" int bpomp_neighbors_all(bpomp_ctx* ctx, double r, uint64_t* nnz) {
 
 extern "C" int bpomp_neighbors_fetch(bpomp_ctx* ctx, uint64_t* row_ptr, uint32_t* col, double* dist) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (row_ptr)
     BP_CUDA(ctx, cudaMemcpyAsync(row_ptr, ctx->d_nb_rowptr.p, ((size_t)ctx->nb_nq + 1) * sizeof(uint64_t),
                                  cudaMemcpyDeviceToHost, ctx->stream));
@@ -920,6 +923,7 @@ extern "C" int bpomp_neighbors_fetch(bpomp_ctx* ctx, uint64_t* row_ptr, uint32_t
 extern "C" int bpomp_neighbors_device(bpomp_ctx* ctx, const uint64_t** d_row_ptr, const uint32_t** d_col,
                                       const double** d_dist) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (d_row_ptr) *d_row_ptr = ctx->d_nb_rowptr.as<uint64_t>();
   if (d_col) *d_col = ctx->d_nb_col.as<uint32_t>();
   if (d_dist) *d_dist = ctx->d_nb_dist.as<double>();

@@ -13,6 +13,7 @@
 // ---------------------------------------------------------------------------
 extern "C" int bpomp_world_set_image(bpomp_ctx* ctx, const uint8_t* pix, int width, int height, int threshold) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (ctx->dim != 2) return bp_fail(ctx, BPOMP_ERR_INVALID, "the image world needs dim == 2 (ctx has %d)", ctx->dim);
   if (!pix || width <= 0 || height <= 0) return bp_fail(ctx, BPOMP_ERR_INVALID, "bad image");
   // Pack to 8x8-pixel tiles of one bit per pixel ("free" = pix >= threshold): a 4096^2 map is
@@ -37,6 +38,7 @@ extern "C" int bpomp_world_set_image(bpomp_ctx* ctx, const uint8_t* pix, int wid
 
 extern "C" int bpomp_world_set_boxes(bpomp_ctx* ctx, const double* lo, const double* hi, int nboxes) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (nboxes < 0 || (nboxes > 0 && (!lo || !hi))) return bp_fail(ctx, BPOMP_ERR_INVALID, "bad boxes");
   const int D = ctx->dim;
   BoxWorldView& w = ctx->boxes;
@@ -150,6 +152,7 @@ int bp_build_fast_world(bpomp_ctx* ctx) {
 
 extern "C" int bpomp_world_set_bounds(bpomp_ctx* ctx, const double* lo, const double* hi) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (!lo || !hi) {
     ctx->have_bounds = false;
   } else {
@@ -218,12 +221,14 @@ int bp_launch_states_valid(bpomp_ctx* ctx, const double* d_states, int64_t count
 
 extern "C" int bpomp_states_valid_dev(bpomp_ctx* ctx, const double* d_states, int64_t count, uint8_t* d_out) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (count < 0 || (count > 0 && (!d_states || !d_out))) return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
   return bp_launch_states_valid(ctx, d_states, count, d_out);
 }
 
 extern "C" int bpomp_states_valid(bpomp_ctx* ctx, const double* states, int64_t count, uint8_t* out) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (count < 0 || (count > 0 && (!states || !out))) return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
   if (ctx->world == WORLD_NONE) return bp_fail(ctx, BPOMP_ERR_NO_WORLD, "no collision world set");
   if (count == 0) return BPOMP_OK;
@@ -268,6 +273,7 @@ __global__ void __launch_bounds__(256) states_prune_kernel(const double* __restr
 extern "C" int bpomp_states_prune(bpomp_ctx* ctx, const double* states, int64_t count, const double* start,
                                   const double* goal, double best_cost, int check_validity, uint8_t* out) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   if (count < 0 || (count > 0 && (!states || !out)) || !start || !goal)
     return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
   if (check_validity && ctx->world == WORLD_NONE) return bp_fail(ctx, BPOMP_ERR_NO_WORLD, "no collision world set");
@@ -315,6 +321,7 @@ extern "C" int bpomp_states_prune(bpomp_ctx* ctx, const double* states, int64_t 
 extern "C" int bpomp_vertices_prune(bpomp_ctx* ctx, uint32_t start_id, uint32_t goal_id, double best_cost,
                                     int check_validity, uint8_t* out) {
   if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
   const uint32_t count = ctx->nverts;
   if (count == 0) return BPOMP_OK;
   if (!out) return bp_fail(ctx, BPOMP_ERR_INVALID, "out is NULL");

@@ -187,10 +187,212 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
+def device_time(torch, stream, ctx, fn, reps, warm=3):
+    """Average device time of fn() (launches on `stream`) in ms: CUDA events on that stream."""
+    for _ in range(warm):
+        fn()
+    ctx.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    ctx.sync()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def peak_hbm():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def extra_indexed_leg(torch, capi, oracle, stream, dev, L, lo, hi, peak, cores):
+    """The planner's own edge path (BASELINE config 3): r-disk rows of the 10^6-vertex 7-D Halton roadmap as indexed
+    edges (source = the expanded vertex) against the 500 boxes; vertex table resident, 8 B of ids per edge in."""
+    N, nq = 10 ** 6, 4096
+    verts = workloads.halton(N, DIM)
+    r = workloads.halton_radius(N, DIM)
+    ctx = capi.Context(DIM, L, device=dev.index)
+    ctx.set_bounds(0.0, 1.0)
+    ctx.set_world_boxes(lo, hi)
+    ctx.vertices_append(verts)
+    q = (np.arange(nq, dtype=np.uint64) * (N // nq)).astype(np.uint32)
+    t0 = time.perf_counter()
+    rp, col, _ = ctx.neighbors_radius(q, r)
+    nb_s = time.perf_counter() - t0
+    fi = np.repeat(q, np.diff(rp.astype(np.int64)))
+    keep = fi != col
+    fi, ti = np.ascontiguousarray(fi[keep]), np.ascontiguousarray(col[keep])
+    E = int(fi.size)
+    ctx.set_stream(stream.cuda_stream)
+    h_fi, h_ti = torch.from_numpy(fi.view(np.int32)).pin_memory(), torch.from_numpy(ti.view(np.int32)).pin_memory()
+    d_fi, d_ti = h_fi.to(dev), h_ti.to(dev)
+    tv = torch.empty(E, dtype=torch.uint8, device=dev)
+    tf = torch.empty(E, dtype=torch.int32, device=dev)
+    tn = torch.empty(E, dtype=torch.int32, device=dev)
+    ms = device_time(torch, stream, ctx, lambda: ctx.edges_check_indexed_dev(d_fi.data_ptr(), d_ti.data_ptr(), E, tv.data_ptr(),
+                                                                             tf.data_ptr(), tn.data_ptr()), reps=10)
+    # end to end from pinned host id arrays
+    hv = torch.empty(E, dtype=torch.uint8).pin_memory()
+    hf = torch.empty(E, dtype=torch.int32).pin_memory()
+    fi_p, ti_p = h_fi.numpy().view(np.uint32), h_ti.numpy().view(np.uint32)
+
+    def e2e():
+        ctx._ck(ctx.lib.bpomp_edges_check_indexed(ctx.h, capi._ptr(fi_p), capi._ptr(ti_p), E, capi._ptr(hv.numpy()),
+                                                  capi._ptr(hf.numpy()), None))
+    e2e()
+    w0 = time.perf_counter()
+    for _ in range(5):
+        e2e()
+    e2e_s = (time.perf_counter() - w0) / 5
+    # parity + CPU column on a sample
+    m = min(E, 1_000_000)
+    t0 = time.perf_counter()
+    ov, of, on = oracle.edges_check_boxes(verts[fi[:m]], verts[ti[:m]], L, lo, hi, nthreads=cores)
+    cpu = m / (time.perf_counter() - t0)
+    parity_check("indexed leg", (tv.cpu().numpy(), tf.cpu().numpy(), tn.cpu().numpy().view(np.uint32)), (ov, of, on))
+    parity_check("indexed leg, end to end", (hv.numpy(), hf.numpy(), tn.cpu().numpy().view(np.uint32)), (ov, of, on))
+    algo = 13 * E + N * DIM * 8
+    ctx.close()
+    return {"workload": "config3 roadmap edges: %d r-disk rows (r = haltonRadius) of the 10^6-vertex 7-D Halton roadmap, "
+                        "indexed endpoints, 500 boxes" % nq,
+            "edges": E, "value": E / ms * 1e3, "unit": UNIT, "ms": ms,
+            "roofline": {"bound": "hbm", "algorithmic_bytes": algo, "achieved": algo / ms * 1e-6, "peak": peak, "unit": "GB/s",
+                         "frac": algo / ms * 1e-6 / peak,
+                         "note": "13 B per edge + the 56 MB vertex table once; instruction-issue bound like the headline"},
+            "e2e": {"value": E / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * E, "d2h_bytes_per_step": 5 * E,
+                    "call": "bpomp_edges_check_indexed (pinned host id arrays)"},
+            "cpu_port_value": cpu, "cpu_cores": cores, "parity_checked_edges": m,
+            "neighbor_rows_seconds": nb_s, "blocked_fraction": float((tv == 0).float().mean())}
+
+
+def extra_image_leg(torch, capi, oracle, stream, dev, peak, cores):
+    """BASELINE config 2's edge evaluation: every roadmap edge (u < v) of the 10^6-vertex 2-D Halton roadmap at
+    r = haltonRadius against the 4096^2 occupancy image, indexed endpoints."""
+    d, N, size, frac = 2, 10 ** 6, 4096, 1e-4
+    verts = workloads.halton(N, d)
+    r = workloads.halton_radius(N, d)
+    L2 = workloads.segment_length(d, frac)
+    pix = workloads.image_world(size, seed=2)
+    ctx = capi.Context(d, L2, device=dev.index)
+    ctx.set_world_image(pix)
+    ctx.vertices_append(verts)
+    t0 = time.perf_counter()
+    rp, col, _ = ctx.neighbors_all(r)
+    nb_s = time.perf_counter() - t0
+    rows = np.repeat(np.arange(N, dtype=np.uint32), np.diff(rp.astype(np.int64)))
+    keep = rows < col
+    fi, ti = np.ascontiguousarray(rows[keep]), np.ascontiguousarray(col[keep])
+    E = int(fi.size)
+    ctx.set_stream(stream.cuda_stream)
+    d_fi, d_ti = torch.from_numpy(fi.view(np.int32)).to(dev), torch.from_numpy(ti.view(np.int32)).to(dev)
+    tv = torch.empty(E, dtype=torch.uint8, device=dev)
+    tf = torch.empty(E, dtype=torch.int32, device=dev)
+    tn = torch.empty(E, dtype=torch.int32, device=dev)
+    ms = device_time(torch, stream, ctx, lambda: ctx.edges_check_indexed_dev(d_fi.data_ptr(), d_ti.data_ptr(), E, tv.data_ptr(),
+                                                                             tf.data_ptr(), tn.data_ptr()), reps=10)
+    m = min(E, 1_000_000)
+    t0 = time.perf_counter()
+    ov, of, on = oracle.edges_check_image(verts[fi[:m]], verts[ti[:m]], L2, pix, nthreads=cores)
+    cpu = m / (time.perf_counter() - t0)
+    parity_check("image leg", (tv.cpu().numpy(), tf.cpu().numpy(), tn.cpu().numpy().view(np.uint32)), (ov, of, on))
+    algo = 13 * E + N * d * 8
+    ctx.close()
+    return {"workload": "config2 roadmap edges: all %d edges (u < v) of the 10^6-vertex 2-D Halton roadmap at r = haltonRadius, "
+                        "4096^2 occupancy image, resolution 1e-4, indexed endpoints" % E,
+            "edges": E, "value": E / ms * 1e3, "unit": UNIT, "ms": ms,
+            "roofline": {"bound": "hbm", "algorithmic_bytes": algo, "achieved": algo / ms * 1e-6, "peak": peak, "unit": "GB/s",
+                         "frac": algo / ms * 1e-6 / peak},
+            "cpu_port_value": cpu, "cpu_cores": cores, "parity_checked_edges": m,
+            "densification_seconds": nb_s, "csr_neighbours": int(col.size),
+            "blocked_fraction": float((tv == 0).float().mean()), "mean_nstates": float(tn.float().mean())}
+
+
+def _anytime(p, start, goal, single, max_solutions, time_cap):
+    t0 = time.perf_counter()
+    if single:
+        p.setup(); p.set_problem(start, goal)
+    else:
+        p.set_problem(start, goal); p.setup()
+    first, costs, paths, st = None, [], [], "UNKNOWN"
+    for _ in range(400):
+        left = time_cap - (time.perf_counter() - t0)
+        if left <= 0:
+            st = "BENCH_TIME_CAP"
+            break
+        st = p.solve(max_seconds=left)
+        if len(p.path()) and (not costs or p.best_cost < costs[-1][1]):
+            costs.append((time.perf_counter() - t0, p.best_cost))
+            paths.append(np.asarray(p.path_states()).copy())
+            if first is None:
+                first = time.perf_counter() - t0
+        if st in ("EXACT_SOLUTION", "TIMEOUT") or len(costs) >= max_solutions:
+            break
+    return {"time_to_first_path_s": first, "time_to_best_path_s": costs[-1][0] if costs else None,
+            "best_cost": costs[-1][1] if costs else None, "solutions": len(costs), "final_status": st,
+            "counters": p.counters(), "paths": paths, "costs": [c for _, c in costs]}
+
+
+def extra_planner_leg(oracle):
+    """The second half of BASELINE's metric: wall time to the first and to the best path of the whole planner loop
+    (src/BatchingPOMP.cpp:819-1017), GPU host planner beside the single-threaded CPU oracle planner (the reference is
+    single-threaded), same roadmaps, paths compared solution by solution."""
+    from batching_pomp_b200.planner import Planner
+    out = {}
+    # config 1: 2-D image, N = 10^4, hybrid batching
+    d, N, frac = 2, 10 ** 4, 1e-3
+    pix = workloads.image_world(1024, seed=1)
+    roadmap = workloads.halton(N, d)
+    params = {"batching_type": "hybrid", "graph_type": "halton", "increment": 0.2, "prune_threshold": 1.05}
+    # config 3: 7-DoF boxes, N = 10^6, vertex batching
+    d3, N3 = 7, 10 ** 6
+    lo3, hi3 = workloads.box_world(d3, 500, seed=3)
+    roadmap3 = workloads.halton(N3, d3)
+    for name, mk in (("config1", lambda cls: (cls, d, frac, ("image", pix), roadmap, params, 12, 60.0)),
+                     ("config3", lambda cls: (cls, d3, 0.01, ("boxes", lo3, hi3), roadmap3, {"batching_type": "vertex"}, 6, 40.0))):
+        res = {}
+        for side in ("gpu", "cpu_oracle"):
+            _, dd, fr, world, rm, prm, nsol, cap = mk(side)
+            if side == "gpu":
+                kw = {"image": world[1]} if world[0] == "image" else {"boxes": (world[1], world[2])}
+                p = Planner(dd, segment_fraction=fr, **kw)
+                if hasattr(p, "set_roadmap_view"):
+                    p.set_roadmap_view(rm)
+                else:
+                    p.set_roadmap(rm)
+            else:
+                p = oracle.OraclePlanner(dd, workloads.segment_length(dd, fr), workloads.max_extent(dd), 1.0)
+                if world[0] == "image":
+                    p.set_world_image(world[1])
+                else:
+                    p.set_world_boxes(world[1], world[2])
+                p.set_roadmap(rm)
+            for k, v in prm.items():
+                p.set_param(k, v)
+            res[side] = _anytime(p, np.full(dd, 0.1), np.full(dd, 0.9), False, nsol, cap)
+            if side == "gpu":
+                res[side]["gpu_launches"] = p.gpu_launches
+                res[side]["phase_seconds"] = p.times()
+        k = min(res["gpu"]["solutions"], res["cpu_oracle"]["solutions"])
+        same = k > 0 and all(np.array_equal(a, b) for a, b in zip(res["gpu"]["paths"][:k], res["cpu_oracle"]["paths"][:k])) \
+            and res["gpu"]["costs"][:k] == res["cpu_oracle"]["costs"][:k]
+        if not same:
+            sys.stderr.write("PARITY FAILURE (planner %s): the GPU planner's solutions differ from the CPU oracle planner's\n" % name)
+            os._exit(3)
+        for side in res:
+            res[side].pop("paths")
+            res[side].pop("costs")
+        out[name] = {"gpu": res["gpu"], "cpu_oracle": res["cpu_oracle"], "paths_identical": True, "solutions_compared": k}
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from batching_pomp_b200 import capi, sharding
+    from batching_pomp_b200 import capi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -201,8 +403,9 @@ def run_gpu(args):
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-
-    E = args.edges
+    strong = args.scaling == "strong"
+    # weak scaling: every rank owns args.edges edges; strong scaling: args.edges in total, split evenly
+    E = args.edges if not strong else (args.edges // world) // 16 * 16
     L, lo, hi, frm, to = make_workload(E, seed=4 + 100 * rank)  # every rank owns a different shard
     ctx = capi.Context(DIM, L, device=local_rank)
     ctx.set_bounds(0.0, 1.0)  # RealVectorStateSpace bounds of the unit hypercube (a hint: results do not depend on it)
@@ -211,73 +414,54 @@ def run_gpu(args):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
+    if world > 1:  # the library's own communicator (bpomp_comm_init_rank): the id travels through the process group
+        ids = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init_rank(world, rank, ids[0])
 
     # pinned host copies (e2e) and device-resident copies (value)
     h_from = torch.from_numpy(frm).pin_memory()
     h_to = torch.from_numpy(to).pin_memory()
     h_valid = torch.empty(E, dtype=torch.uint8).pin_memory()
     h_first = torch.empty(E, dtype=torch.int32).pin_memory()
-    h_ns = torch.empty(E, dtype=torch.int32).pin_memory()
     d_from = h_from.to(dev, non_blocking=True)
     d_to = h_to.to(dev, non_blocking=True)
-    d_valid = torch.empty(E, dtype=torch.uint8, device=dev)
-    d_first = torch.empty(E, dtype=torch.int32, device=dev)
     d_ns = torch.empty(E, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
 
-    # N > 1: the all-gather that merges step k's first-invalid slots runs on its own stream and overlaps
-    # step k+1's kernel; results alternate between two buffer sets so the kernel never overwrites data
-    # that is still being gathered.
+    # N > 1: the merge of step k's status flags (packed to 2 bits per edge, one ncclAllGather on the communicator's
+    # stream inside bpomp_edges_check_sharded_dev) overlaps step k+1's kernel; results alternate between two buffer
+    # sets so that a kernel never overwrites data that is still being gathered.
     nbuf = 2 if world > 1 else 1
-    d_valid = [d_valid] + [torch.empty_like(d_valid) for _ in range(nbuf - 1)]
-    d_first = [d_first] + [torch.empty_like(d_first) for _ in range(nbuf - 1)]
-    gathered = [torch.empty(world * E, dtype=torch.uint8, device=dev) for _ in range(nbuf)] if world > 1 else None
-    words = (E + 15) // 16  # status flags travel packed, 2 bits per edge (bpomp_edge_status_pack_dev)
+    d_valid = [torch.empty(E, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+    d_first = [torch.empty(E, dtype=torch.int32, device=dev) for _ in range(nbuf)]
+    words = (E + 15) // 16
     packed = [torch.empty(words, dtype=torch.int32, device=dev) for _ in range(nbuf)] if world > 1 else None
     packed_all = [torch.empty(world * words, dtype=torch.int32, device=dev) for _ in range(nbuf)] if world > 1 else None
-    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
     kernel_ms = []
-    pending = [None] * nbuf
     step_no = [0]
 
     def step(timed):
         k = step_no[0] % nbuf
         step_no[0] += 1
-        if pending[k] is not None:  # the gather that last read this buffer set must be done
-            finish(k)
         if timed:
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-        ctx.edges_check_dev(d_from.data_ptr(), d_to.data_ptr(), E, d_valid[k].data_ptr(), d_first[k].data_ptr(),
-                            d_ns.data_ptr())
+        if world > 1:
+            # (the wait for the merge that last used this buffer set is inside: same communicator stream order)
+            ctx.edges_check_sharded_dev(d_from.data_ptr(), d_to.data_ptr(), E, d_valid[k].data_ptr(), d_first[k].data_ptr(),
+                                        d_ns.data_ptr(), packed[k].data_ptr(), packed_all[k].data_ptr())
+        else:
+            ctx.edges_check_dev(d_from.data_ptr(), d_to.data_ptr(), E, d_valid[k].data_ptr(), d_first[k].data_ptr(),
+                                d_ns.data_ptr())
         if timed:
             e1.record(stream)
             kernel_ms.append((e0, e1, E))
-        if world > 1:
-            ctx.edge_status_pack_dev(d_valid[k].data_ptr(), E, packed[k].data_ptr())
-            ev = torch.cuda.Event()
-            ev.record(stream)
-            with torch.cuda.stream(comm_stream):
-                comm_stream.wait_event(ev)
-                pending[k] = sharding.allgather_equal(packed[k], packed_all[k], async_op=True)[1]
-
-    def finish(k):
-        """Buffer set k: wait for its gather and expand every rank's packed flags to the merged byte array."""
-        pending[k].wait()  # the kernel stream waits for the collective
-        pending[k] = None
-        if E % 16 == 0:
-            ctx.edge_status_unpack_dev(packed_all[k].data_ptr(), world * E, gathered[k].data_ptr())
-        else:
-            for g in range(world):
-                ctx.edge_status_unpack_dev(packed_all[k][g * words:].data_ptr(), E, gathered[k][g * E:].data_ptr())
 
     def drain():
-        for k in range(nbuf):
-            if pending[k] is not None:
-                finish(k)
         if world > 1:
-            stream.wait_stream(comm_stream)
+            ctx.comm_wait()
 
     def barrier():
         if world > 1:
@@ -310,10 +494,11 @@ def run_gpu(args):
     kern_ms_per_step = sum(ms for ms, _ in per_launch) / args.steps
     avg_launch_ms = sum(ms for ms, _ in per_launch) / len(per_launch)
     edges_per_launch = sum(n for _, n in per_launch) / len(per_launch)
+    last = (step_no[0] - 1) % nbuf  # buffer set of the last step
 
     # ---- end to end through the host-buffer C ABI ("e2e") -------------------------------------
     f_np, t_np = h_from.numpy(), h_to.numpy()
-    v_np, fi_np, ns_np = h_valid.numpy(), h_first.numpy(), h_ns.numpy().view(np.uint32)
+    v_np, fi_np = h_valid.numpy(), h_first.numpy()
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
         ctx.edges_check_into(f_np, t_np, v_np, fi_np, None)
@@ -326,23 +511,35 @@ def run_gpu(args):
     e2e_s = time.perf_counter() - w0
     sampler.active = False
     sampler.stop_flag = True
-    # the device-resident and the end-to-end paths must agree
-    assert np.array_equal(fi_np, d_first[0].cpu().numpy()), "e2e and device-resident results differ"
 
+    merged_ok = True
     if world > 1:
         t = torch.tensor([elapsed_ms, e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms, e2e_s = float(t[0]), float(t[1])
-        # merged result sanity: this rank's shard must sit at its slot of the gathered buffer
-        assert torch.equal(gathered[0][rank * E:(rank + 1) * E], d_valid[0])
+        # merged result sanity: this rank's shard must sit at its slot of the gathered packed flags
+        mine = torch.empty(E, dtype=torch.uint8, device=dev)
+        ctx.edge_status_unpack_dev(packed_all[last][rank * words:].data_ptr(), E, mine.data_ptr())
+        ctx.sync()
+        merged_ok = bool(torch.equal(mine, d_valid[last]))
+        assert merged_ok, "merged status flags differ from the shard's own"
+
+    # parity gate on every rank: the oracle outputs of the cpu_baseline sample (rank 0, N = 1) or of a short oracle
+    # pass against what the device-resident step and the end-to-end call produced in this very run
+    cores = len(os.sched_getaffinity(0))
+    cb = cpu_baseline_run(L, lo, hi, frm, to, target_s=12.0) if (not args.no_cpu and world == 1) else None
+    if cb:
+        want = cb["outputs"]
+    else:
+        from oracle import oracle
+        m = min(E, 200000)
+        want = oracle.edges_check_boxes(frm[:m], to[:m], L, lo, hi, nthreads=max(1, cores // world))
+    ns_dev = d_ns.cpu().numpy().view(np.uint32)
+    checked = parity_check("device-resident step", (d_valid[last].cpu().numpy(), d_first[last].cpu().numpy(), ns_dev), want)
+    parity_check("end-to-end call", (v_np, fi_np, ns_dev), want)
 
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak = float(json.load(open(peaks_path))["hbm_gbs"])
-            peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
-        else:
-            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        peak, peak_src = peak_hbm()
         achieved = ALGO_BYTES_PER_EDGE * edges_per_launch / (avg_launch_ms * 1e-3) / 1e9
         # DRAM bytes per launch of the timed kernel come from the committed `ncu --set full` capture of this
         # same kernel (a profiler cannot run inside a timed bench); the record names the kernel and capture it
@@ -359,29 +556,17 @@ def run_gpu(args):
                     traffic_src = "no ncu capture of kernel build '%s' at %d edges/launch committed" % (KERNEL_TAG, int(edges_per_launch))
             except Exception:
                 traffic = None
-        # the CPU baseline is timed on rank 0 of the single-GPU run only (multi-GPU runs stay short)
-        cb = cpu_baseline_run(L, lo, hi, frm, to, target_s=12.0) if (not args.no_cpu and world == 1) else None
-        # parity gate: the oracle outputs of the cpu_baseline sample (or, without that leg, of a short oracle
-        # pass) against what the device-resident step and the end-to-end call produced in this very run
-        if cb:
-            want = cb["outputs"]
-        else:
-            from oracle import oracle
-            m = min(E, 200000)
-            want = oracle.edges_check_boxes(frm[:m], to[:m], L, lo, hi, nthreads=len(os.sched_getaffinity(0)))
-        ns_dev = d_ns.cpu().numpy().view(np.uint32)
-        checked = parity_check("device-resident step", (d_valid[0].cpu().numpy(), d_first[0].cpu().numpy(), ns_dev), want)
-        parity_check("end-to-end call", (v_np, fi_np, ns_dev), want)
         value = world * E * args.steps / (elapsed_ms * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(E, world, {
-                "merge": ("nccl all_gather of the edge status flags (packed to 2 bits/edge, unpacked to 1 B/edge on "
-                          "every rank) per step, overlapped with the next "
-                          "step's kernel (double-buffered results); first-invalid slots stay with the shard "
-                          "owner, which replays the belief inserts") if world > 1 else "none (single GPU)"}),
+                "scaling_mode": ("strong: %d edges in total" % (E * world)) if strong else "weak: %d edges per GPU" % E,
+                "merge": ("bpomp_edges_check_sharded_dev: the status flags packed to 2 bits/edge and merged with one "
+                          "ncclAllGather per step on the library's communicator stream, overlapped with the next step's "
+                          "kernel (double-buffered results); first-invalid slots stay with the shard owner, which "
+                          "replays the belief inserts") if world > 1 else "none (single GPU)"}),
             "kernel_ms_per_step": kern_ms_per_step,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
@@ -390,11 +575,13 @@ def run_gpu(args):
                                    "none on this workload, its CTAs exit at once)",
                          "avg_launch_ms": avg_launch_ms,
                          "note": "instruction-issue bound (DESIGN.md 4.1): ~32 warp instructions per edge at ~70% of the "
-                                 "issue slots, shared-memory wavefronts ~64% of peak; DRAM at ~40% of the measured copy peak"},
+                                 "issue slots, shared-memory wavefronts ~64% of peak; DRAM at ~45% of the measured copy peak"},
             "e2e": {"value": world * E * e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(2 * E * DIM * 8), "d2h_bytes_per_step": int(E * 5),
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                    "call": "bpomp_edges_check (pinned host buffers; chunked over 3 streams: H2D, kernel, D2H overlap)"},
+                    "h2d_GBps_per_rank": 2 * E * DIM * 8 / (e2e_s / e2e_steps) / 1e9,
+                    "call": "bpomp_edges_check (pinned host buffers; chunked over 3 streams: H2D, kernel, D2H overlap): "
+                            "bound by the host link (PCIe), 112 B per edge in"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "blocked_fraction": float((fi_np >= 1).mean()),
@@ -404,6 +591,13 @@ def run_gpu(args):
         }
         if cb:
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if world == 1 and not args.no_extras:
+            from oracle import oracle
+            extras = {}
+            extras["indexed_edges"] = extra_indexed_leg(torch, capi, oracle, stream, dev, L, lo, hi, peak, cores)
+            extras["image_edges"] = extra_image_leg(torch, capi, oracle, stream, dev, peak, cores)
+            extras["planner"] = extra_planner_leg(oracle)
+            line["extra"] = extras
         print(json.dumps(line))
     ctx.close()
     if world > 1:
@@ -418,7 +612,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--edges", type=int, default=10 ** 7)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --edges per GPU (default); strong: --edges in total")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra legs (indexed / image edges, planner times)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3
