@@ -395,25 +395,89 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
 // ---------------------------------------------------------------------------
 // Image world (2-D)
 // ---------------------------------------------------------------------------
+// Thread per edge.  The samples of an edge lie inside the pixel bounding box of its endpoints (floor(x*W) is
+// monotone), and a roadmap edge is a few pixels long: when that box spans at most 2 x 2 tiles of 8 x 8 pixels the
+// four tiles (32 bytes, one byte per pixel row of a tile) are copied ONCE into the thread's window in shared
+// memory (stride 9 words: conflict-free) and every sample is one byte load from that window — no global load
+// depends on a sample, so there is no dependent-load chain and no early exit: every lane runs the same
+// straight-line code over the slots and the invalid slots are collected in a bit mask (first invalid slot =
+// lowest set bit).  The few longer edges of a warp are then evaluated cooperatively, lane = sample.
+#define EC_IMG_THREADS 256
 template <bool INDEXED>
-__global__ void __launch_bounds__(256) edge_check_image_kernel(EdgeArgs a, ImageWorldView im, PermView pv) {
+__global__ void __launch_bounds__(EC_IMG_THREADS) edge_check_image_kernel(EdgeArgs a, ImageWorldView im, PermView pv) {
   if (a.gate && *reinterpret_cast<const volatile int*>(a.gate) == 0) return;  // (never set for the image world)
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.count;
-       e += (int64_t)gridDim.x * blockDim.x) {
-    double f[2], t[2];
-    uint32_t n, off;
-    if (!edge_prologue<2, INDEXED>(a, pv, e, f, t, n, off, a.only_status)) continue;
-    double d0 = __dsub_rn(t[0], f[0]), d1 = __dsub_rn(t[1], f[1]);
+  __shared__ uint32_t s_win[EC_IMG_THREADS * 9];
+  const double Wd = (double)im.W, Hd = (double)im.H;
+  const int lane = threadIdx.x & 31;
+  uint32_t* win = s_win + threadIdx.x * 9;
+  const unsigned char* winb = reinterpret_cast<const unsigned char*>(win);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t rounds = (a.count + stride - 1) / stride;
+  for (int64_t rd = 0; rd < rounds; ++rd) {  // warp-uniform trip count: the lanes of a warp stay together
+    const int64_t e = rd * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double f[2] = {0.0, 0.0}, t[2] = {0.0, 0.0};
+    uint32_t n = 0, off = 0;
+    const bool need = e < a.count && edge_prologue<2, INDEXED>(a, pv, e, f, t, n, off, a.only_status);
+    const double d0 = __dsub_rn(t[0], f[0]), d1 = __dsub_rn(t[1], f[1]);
     const double* tf = pv.tfrac + off;
-    int32_t bad = -1;
-    for (uint32_t i = 1; i + 1 < n; ++i) {
-      double tt = __ldg(tf + i);
-      double x0 = __dadd_rn(f[0], __dmul_rn(d0, tt));
-      double x1 = __dadd_rn(f[1], __dmul_rn(d1, tt));
-      if (!bp_valid_image(x0, x1, im)) { bad = (int32_t)i; break; }
+    int32_t bad = 0x7fffffff;
+    // strictly inside [0,1): no sample reaches pixel W (x = 1.0) and no clamp is needed
+    const bool inside = f[0] >= 0.0 && f[0] < 1.0 && f[1] >= 0.0 && f[1] < 1.0 && t[0] >= 0.0 && t[0] < 1.0 &&
+                        t[1] >= 0.0 && t[1] < 1.0;
+    bool fastpath = false;
+    if (need && inside && n <= 33u) {
+      const int cf = bp_floor_int(__dmul_rn(f[0], Wd)), ct = bp_floor_int(__dmul_rn(t[0], Wd));
+      const int rf = bp_floor_int(__dmul_rn(f[1], Hd)), rt = bp_floor_int(__dmul_rn(t[1], Hd));
+      const int tx0 = min(cf, ct) >> 3, tx1 = max(cf, ct) >> 3, ty0 = min(rf, rt) >> 3, ty1 = max(rf, rt) >> 3;
+      if (tx1 - tx0 <= 1 && ty1 - ty0 <= 1) {
+        fastpath = true;
+        const unsigned long long* r0 = im.bits + (size_t)ty0 * im.tiles_x;
+        const unsigned long long* r1 = im.bits + (size_t)ty1 * im.tiles_x;
+        const unsigned long long T00 = __ldg(r0 + tx0), T01 = __ldg(r0 + tx1), T10 = __ldg(r1 + tx0), T11 = __ldg(r1 + tx1);
+        // window bytes: [(tile row * 2 + tile col) * 8 + pixel row] = the 8 pixels of that row of that tile
+        win[0] = (uint32_t)T00; win[1] = (uint32_t)(T00 >> 32); win[2] = (uint32_t)T01; win[3] = (uint32_t)(T01 >> 32);
+        win[4] = (uint32_t)T10; win[5] = (uint32_t)(T10 >> 32); win[6] = (uint32_t)T11; win[7] = (uint32_t)(T11 >> 32);
+        const int cbase = tx0 << 3, rbase = ty0 << 3;
+        uint32_t invalid = 0;  // bit i: slot i is in collision
+#pragma unroll 4
+        for (uint32_t i = 1; i + 1 < n; ++i) {
+          const double tt = __ldg(tf + i);
+          const double x0 = __dadd_rn(f[0], __dmul_rn(d0, tt));  // inside the endpoints' box
+          const double x1 = __dadd_rn(f[1], __dmul_rn(d1, tt));
+          const int col = bp_floor_int(__dmul_rn(x0, Wd)) - cbase;  // 0..15
+          const int row = bp_floor_int(__dmul_rn(x1, Hd)) - rbase;
+          const uint32_t byte = winb[((row & 8) << 1) | (col & 8) | (row & 7)];
+          invalid |= (((byte >> (col & 7)) & 1u) ^ 1u) << i;
+        }
+        if (invalid) bad = __ffs((int)invalid) - 1;
+      }
     }
-    a.valid[e] = bad < 0 ? BPOMP_EDGE_FREE : BPOMP_EDGE_BLOCKED;
-    a.first[e] = bad;
+    // the other edges of the warp (long, or touching the border of the unit square): lane = sample
+    uint32_t slow = __ballot_sync(0xffffffffu, need && !fastpath);
+    while (slow) {
+      const int src = __ffs((int)slow) - 1;
+      slow &= slow - 1;
+      const double sf0 = __shfl_sync(0xffffffffu, f[0], src), sf1 = __shfl_sync(0xffffffffu, f[1], src);
+      const double sd0 = __shfl_sync(0xffffffffu, d0, src), sd1 = __shfl_sync(0xffffffffu, d1, src);
+      const uint32_t sn = __shfl_sync(0xffffffffu, n, src), soff = __shfl_sync(0xffffffffu, off, src);
+      int32_t first = 0x7fffffff;
+      for (uint32_t i0 = 1; i0 + 1 < sn && first == 0x7fffffff; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        bool hit = false;
+        if (i + 1 < sn) {
+          const double tt = __ldg(pv.tfrac + soff + i);
+          hit = !bp_valid_image(__dadd_rn(sf0, __dmul_rn(sd0, tt)), __dadd_rn(sf1, __dmul_rn(sd1, tt)), im);
+        }
+        const uint32_t hits = __ballot_sync(0xffffffffu, hit);
+        if (hits) first = (int32_t)(i0 + __ffs((int)hits) - 1);
+      }
+      if (lane == src) bad = first;
+    }
+    if (need) {
+      const bool blocked = bad != 0x7fffffff;
+      a.valid[e] = blocked ? BPOMP_EDGE_BLOCKED : BPOMP_EDGE_FREE;
+      a.first[e] = blocked ? bad : -1;
+    }
   }
 }
 
@@ -516,9 +580,9 @@ int bp_launch_edge_check(bpomp_ctx* ctx, const double* d_from, const double* d_t
   }
   const bool indexed = d_from_ids != nullptr;
   if (ctx->world == WORLD_IMAGE) {
-    int grid = (int)std::min<int64_t>((count + 255) / 256, (int64_t)ctx->num_sms * 8);
-    if (indexed) edge_check_image_kernel<true><<<grid, 256, 0, ctx->stream>>>(a, ctx->image, ctx->perm_view());
-    else edge_check_image_kernel<false><<<grid, 256, 0, ctx->stream>>>(a, ctx->image, ctx->perm_view());
+    int grid = (int)std::min<int64_t>((count + EC_IMG_THREADS - 1) / EC_IMG_THREADS, (int64_t)ctx->num_sms * 8);
+    if (indexed) edge_check_image_kernel<true><<<grid, EC_IMG_THREADS, 0, ctx->stream>>>(a, ctx->image, ctx->perm_view());
+    else edge_check_image_kernel<false><<<grid, EC_IMG_THREADS, 0, ctx->stream>>>(a, ctx->image, ctx->perm_view());
   } else {
     BP_TRY(indexed ? launch_boxes_dim<true>(ctx, a) : launch_boxes_dim<false>(ctx, a));
   }

@@ -34,6 +34,9 @@
 #ifndef FE_CHUNK
 #define FE_CHUNK 16      // consecutive tiles per static claim (long contiguous runs are kinder to DRAM)
 #endif
+#ifndef FE_CHUNK_DYN
+#define FE_CHUNK_DYN 4   // tiles per dynamic claim of the indexed form
+#endif
 #ifndef FE_TAIL8
 #define FE_TAIL8 7       // eighths of the batch claimed in chunks; the rest in single tiles
 #endif
@@ -242,7 +245,9 @@ __global__ void __launch_bounds__(FE_MAXWARPS * 32, 1)
   // the L2 atomic unit); the rest is claimed dynamically, one tile per atomic, which balances the tail and
   // absorbs SMs that are shared with another kernel (e.g. NCCL's).  A warp always knows its next claim one chunk
   // ahead, so the atomic's latency is not exposed.
-  const int64_t big_claims = ntiles / 8 * FE_TAIL8 / FE_CHUNK;
+  // (indexed endpoints are gathered from all over the vertex table anyway and their tiles differ a lot in cost —
+  // the rows of a CSR share a source — so there everything is claimed dynamically, FE_CHUNK_DYN tiles at a time)
+  const int64_t big_claims = INDEXED ? 0 : ntiles / 8 * FE_TAIL8 / FE_CHUNK;
   const int64_t nwarps_grid = (int64_t)gridDim.x * (blockDim.x >> 5);
   int64_t stat_next = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   unsigned long long ahead = 0;  // the claim made ahead (lane 0's copy counts)
@@ -260,8 +265,9 @@ __global__ void __launch_bounds__(FE_MAXWARPS * 32, 1)
       first = c * FE_CHUNK;
       end = first + FE_CHUNK;
     } else {
-      first = big_claims * FE_CHUNK + (c - big_claims);
-      end = first + 1;
+      constexpr int64_t kDyn = INDEXED ? FE_CHUNK_DYN : 1;
+      first = big_claims * FE_CHUNK + (c - big_claims) * kDyn;
+      end = first + kDyn;
     }
     end = min(end, ntiles);
   };

@@ -6,11 +6,15 @@
 
 #ifdef __CUDACC__
 
+// floor(v) as an int for |v| < 2^31 without a conversion instruction: adding 2^52 + 2^51 with round-down leaves
+// floor(v) in the low word of the sum (FP64 -> int conversions are slow; this is one FP64 add).
+__device__ __forceinline__ int bp_floor_int(double v) { return __double2loint(__dadd_rd(v, 6755399441055744.0)); }
+
 // 2-D occupancy image (README.md:56 convention; SURVEY.md §8c definition).
 __device__ __forceinline__ bool bp_valid_image(double x0, double x1, const ImageWorldView& im) {
   if (!(x0 >= 0.0 && x0 <= 1.0 && x1 >= 0.0 && x1 <= 1.0)) return false;
-  int col = __double2int_rd(__dmul_rn(x0, (double)im.W));
-  int row = __double2int_rd(__dmul_rn(x1, (double)im.H));
+  int col = bp_floor_int(__dmul_rn(x0, (double)im.W));  // x in [0,1]: the product is far below 2^31
+  int row = bp_floor_int(__dmul_rn(x1, (double)im.H));
   col = min(col, im.W - 1);
   row = min(row, im.H - 1);
   unsigned long long tile = __ldg(im.bits + (size_t)(row >> 3) * im.tiles_x + (col >> 3));

@@ -187,7 +187,7 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
-def device_time(torch, stream, ctx, fn, reps, warm=3):
+def device_time(torch, stream, ctx, fn, reps, warm=20):
     """Average device time of fn() (launches on `stream`) in ms: CUDA events on that stream."""
     for _ in range(warm):
         fn()

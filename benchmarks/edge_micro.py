@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--check", type=int, default=10 ** 6)
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--image", type=int, default=0, help="N > 0: time the image-world kernel on all edges (u < v) of an "
+                    "N-vertex 2-D Halton roadmap against the 4096^2 image (config 2), indexed")
     ap.add_argument("--indexed", type=int, default=0, help="N > 0: also time the indexed form on r-disk rows of an "
                     "N-vertex 7-D Halton roadmap (the planner's edge path, config 3)")
     ap.add_argument("--variants", default="general,fast,fast+bounds,fast+bounds/8,fast+bounds/12,fast+bounds/16,fast+bounds/20")
@@ -86,6 +88,50 @@ def main():
         print(json.dumps(rec), flush=True)
         results.append(rec)
         ctx.close()
+    if args.image:
+        N, d2, size, frac = args.image, 2, 4096, 1e-4
+        v2 = workloads.halton(N, d2)
+        r2 = workloads.halton_radius(N, d2)
+        L2 = workloads.segment_length(d2, frac)
+        pix = workloads.image_world(size, seed=2)
+        ctx = capi.Context(d2, L2)
+        ctx.set_world_image(pix)
+        ctx.vertices_append(v2)
+        rp, col, dist = ctx.neighbors_all(r2)
+        rows = np.repeat(np.arange(N, dtype=np.uint32), np.diff(rp.astype(np.int64)))
+        keep = rows < col
+        fi, ti = np.ascontiguousarray(rows[keep]), np.ascontiguousarray(col[keep])
+        Ei = fi.size
+        tfi_, tti_ = torch.from_numpy(fi.astype(np.int32)).to(dev), torch.from_numpy(ti.astype(np.int32)).to(dev)
+        iv = torch.empty(Ei, dtype=torch.uint8, device=dev)
+        ifi = torch.empty(Ei, dtype=torch.int32, device=dev)
+        inn = torch.empty(Ei, dtype=torch.int32, device=dev)
+        mm = min(m, Ei)
+        ov_, of_, on_ = oracle.edges_check_image(v2[fi[:mm]], v2[ti[:mm]], L2, pix, nthreads=oracle.max_threads())
+        ctx.set_stream(stream.cuda_stream)
+
+        def runim():
+            ctx.edges_check_indexed_dev(tfi_.data_ptr(), tti_.data_ptr(), Ei, iv.data_ptr(), ifi.data_ptr(), inn.data_ptr())
+        runim()
+        ctx.sync()
+        ok = (np.array_equal(iv[:mm].cpu().numpy(), ov_) and np.array_equal(ifi[:mm].cpu().numpy(), of_)
+              and np.array_equal(inn[:mm].cpu().numpy().view(np.uint32), on_))
+        for _ in range(20):
+            runim()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.reps):
+            runim()
+        e1.record(stream)
+        ctx.sync()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.reps
+        rec = {"variant": "image:indexed", "edges": int(Ei), "ms": ms, "edges_per_s": Ei / ms * 1e3,
+               "frac_hbm_13B": (13 * Ei + N * 16) / ms * 1e-6 / 6550.4, "parity_ok": bool(ok),
+               "blocked": float((iv == 0).float().mean()), "mean_n": float(inn.float().mean())}
+        print(json.dumps(rec), flush=True)
+        results.append(rec)
+        ctx.close()
     if args.indexed:
         N = args.indexed
         verts = workloads.halton(N, d)
@@ -116,7 +162,7 @@ def main():
             mm = min(m, Ei)
             ok = (np.array_equal(tv[:mm].cpu().numpy(), ov_[:mm]) and np.array_equal(tfi[:mm].cpu().numpy(), of_[:mm])
                   and np.array_equal(tn[:mm].cpu().numpy().view(np.uint32), on_[:mm]))
-            for _ in range(3):
+            for _ in range(20):
                 runi()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
