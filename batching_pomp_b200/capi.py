@@ -57,6 +57,7 @@ SIGNATURES = {
     "bpomp_belief_config": (C.c_int, [vp, C.c_int, C.c_double, C.c_double]),
     "bpomp_belief_append": (C.c_int, [vp, vp, vp, C.c_int64]),
     "bpomp_belief_append_checked": (C.c_int, [vp, vp, vp, vp, C.c_int64]),
+    "bpomp_belief_append_checked_indexed": (C.c_int, [vp, vp, vp, vp, vp, C.c_int64]),
     "bpomp_belief_size": (C.c_int, [vp, c_u64p]),
     "bpomp_belief_clear": (C.c_int, [vp]),
     "bpomp_belief_estimate": (C.c_int, [vp, vp, C.c_int64, vp]),
@@ -346,6 +347,12 @@ class Context:
         f, t = _f64(frm).reshape(-1, self.dim), _f64(to).reshape(-1, self.dim)
         fi = np.ascontiguousarray(first_invalid, dtype=np.int32)
         self._ck(self.lib.bpomp_belief_append_checked(self.h, _ptr(f), _ptr(t), _ptr(fi), f.shape[0]))
+
+    def belief_append_checked_indexed(self, from_ids, to_ids, first_invalid, nstates):
+        f, t = _u32(from_ids), _u32(to_ids)
+        fi = np.ascontiguousarray(first_invalid, dtype=np.int32)
+        ns = _u32(nstates)
+        self._ck(self.lib.bpomp_belief_append_checked_indexed(self.h, _ptr(f), _ptr(t), _ptr(fi), _ptr(ns), f.size))
 
     def belief_size(self):
         n = C.c_uint64(0)

@@ -9,6 +9,7 @@
 // summation are sequential in ascending (distance, insertion index), as the CPU oracle defines
 // them, so results are bit-equal to the oracle and within 1e-12 relative of
 // the reference's Eigen-packetised sums.
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -379,6 +380,160 @@ __global__ void __launch_bounds__(256) bk_product_kernel(int64_t count, const ui
 }
 
 // ---------------------------------------------------------------------------
+// Small batches (the planner's per-search calls): computeAndSetEdgeFreeProbability of a batch of edges in ONE
+// launch.  A block takes an edge: nStates, the query slots 1, 1+step, ... (BP.cpp:472-475), and one warp per
+// query: every lane scans the belief points lane, lane+32, ... into its own (distance, index)-ordered list of
+// the k best (shared memory), the 32 lists are merged k times by a warp arg-min on (distance, index) — the
+// same k nearest, in the same order, as the sequential scan of KNNModel::estimate (KNNModel.hpp:108-127) —
+// lane 0 accumulates the weights in that order; thread 0 forms the product over the queries.
+// ---------------------------------------------------------------------------
+#define BKF_WARPS 4
+#define BKF_QMAX 16  // queries per edge: (n-2)/step + 1 <= 12 for n <= 65535
+
+template <int D>
+__device__ __forceinline__ double bkf_estimate_warp(const double* x, const double* __restrict__ pts,
+                                                    const double* __restrict__ vals, uint64_t M, int K, double prior,
+                                                    double prior_weight, double* kd, uint32_t* ki, int lane) {
+  if (M == 0) return prior;  // KNNModel.hpp:104-106
+  int cnt = 0;
+  double worst = DBL_MAX, thr = DBL_MAX;
+  for (uint64_t p = (uint64_t)lane; p < M; p += 32) {
+    const double* pt = pts + p * D;
+    double d2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      const double diff = __dsub_rn(x[j], __ldg(pt + j));
+      d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
+    }
+    if (cnt == K && d2 > thr) continue;
+    const double dist = __dsqrt_rn(d2);
+    if (cnt == K && !(dist < worst)) continue;  // an equidistant later point never displaces
+    int pos = cnt < K ? cnt : K - 1;
+    while (pos > 0 && kd[(pos - 1) * 32] > dist) {
+      kd[pos * 32] = kd[(pos - 1) * 32];
+      ki[pos * 32] = ki[(pos - 1) * 32];
+      --pos;
+    }
+    kd[pos * 32] = dist;
+    ki[pos * 32] = (uint32_t)p;
+    if (cnt < K) ++cnt;
+    if (cnt == K) {
+      worst = kd[(K - 1) * 32];
+      thr = __dmul_rn(__dmul_rn(worst, worst), 1.0 + 9.094947017729282e-13);  // conservative (2^-40)
+    }
+  }
+  const int knn = (uint64_t)K < M ? K : (int)M;  // :108
+  int head = 0;
+  double dot = 0.0, wsum = 0.0;
+  for (int k = 0; k < knn; ++k) {
+    double cd = head < cnt ? kd[head * 32] : DBL_MAX;
+    uint32_t ci = head < cnt ? ki[head * 32] : 0xFFFFFFFFu;
+    const uint32_t mine = ci;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, cd, o);
+      const uint32_t oi = __shfl_xor_sync(0xffffffffu, ci, o);
+      if (od < cd || (od == cd && oi < ci)) {
+        cd = od;
+        ci = oi;
+      }
+    }
+    if (mine == ci && ci != 0xFFFFFFFFu) ++head;  // the winner's list advances (indices are unique)
+    const double distance = fmax(0.0001, cd);     // :121
+    const double w = __ddiv_rn(1.0, distance);    // :122
+    const double v = __ldg(vals + ci);            // :123
+    dot = __dadd_rn(dot, __dmul_rn(w, v));        // weights.dot(values), sequential
+    wsum = __dadd_rn(wsum, w);                    // weights.sum()
+  }
+  double result = __ddiv_rn(dot, wsum);                                                                   // :127
+  result = __ddiv_rn(__dadd_rn(result, __dmul_rn(prior_weight, prior)), __dadd_rn(1.0, prior_weight));  // :130
+  return result;
+}
+
+template <int D>
+__global__ void __launch_bounds__(BKF_WARPS * 32) bk_pfree_fused(EdgeSrc src, int64_t count, double L, PermView pv,
+                                                                 const double* __restrict__ pts,
+                                                                 const double* __restrict__ vals, uint64_t M, int K,
+                                                                 double prior, double prior_weight,
+                                                                 double* __restrict__ pfree, uint32_t* __restrict__ nlook) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* kd = reinterpret_cast<double*>(smem) + (size_t)warp * K * 32 + lane;                       // [K][32] per warp
+  uint32_t* ki = reinterpret_cast<uint32_t*>(smem + (size_t)BKF_WARPS * K * 32 * sizeof(double)) + (size_t)warp * K * 32 + lane;
+  __shared__ double s_est[BKF_QMAX];
+  for (int64_t e = blockIdx.x; e < count; e += gridDim.x) {
+    double f[D], d[D];
+    bk_load<D>(src, e, f, d);
+    uint32_t n = bp_nstates(__dsqrt_rn(bp_dist2<D>(f, d)), L);
+#pragma unroll
+    for (int j = 0; j < D; ++j) d[j] = __dsub_rn(d[j], f[j]);
+    if (n == 0u) {  // more than BPOMP_NSTATES_MAX states
+      if (threadIdx.x == 0) atomicAdd(pv.flags + 1, 1);
+      n = 2u;
+    }
+    uint32_t nqr = 0, step = 1, off = 0;
+    if (n > 2u) {
+      off = __ldg(pv.off + n);
+      if (off == BP_ABSENT) {  // sample order not resident: the host uploads it and redoes the batch
+        if (threadIdx.x == 0) {
+          pv.need[n] = 1;
+          atomicAdd(pv.flags, 1);
+        }
+      } else {
+        step = __ldg(pv.step + n);       // (unsigned)(n / log(n)), BP.cpp:472
+        nqr = (n - 2u + step - 1u) / step;  // i = 1, 1+step, ... < n-1
+      }
+    }
+    for (uint32_t qi = (uint32_t)warp; qi < nqr; qi += BKF_WARPS) {
+      const double tt = __ldg(pv.tfrac + off + 1u + qi * step);
+      double x[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) x[j] = __dadd_rn(f[j], __dmul_rn(d[j], tt));
+      const double est = bkf_estimate_warp<D>(x, pts, vals, M, K, prior, prior_weight, kd, ki, lane);
+      if (lane == 0) s_est[qi] = est;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double r = 1.0;
+      for (uint32_t k = 0; k < nqr; ++k) r = __dmul_rn(r, __dsub_rn(1.0, s_est[k]));  // BP.cpp:473-488, slot order
+      pfree[e] = r;
+      if (nlook) nlook[e] = nqr;
+    }
+    __syncthreads();
+  }
+}
+
+// checkAndSetEdgeBlocked's belief inserts for already-checked edges whose nStates the caller knows: the states
+// of slots 1..c (c = first invalid slot, or n-2 for a free edge) go to out + offs[e]*D, values 0.0 and a final
+// 1.0 for a blocked edge (BP.cpp:523-537).  offs is the caller's exclusive prefix of the c's.
+template <int D>
+__global__ void __launch_bounds__(128) bk_append_known(EdgeSrc src, int64_t count, PermView pv,
+                                                       const int32_t* __restrict__ first_invalid,
+                                                       const uint32_t* __restrict__ nst,
+                                                       const uint64_t* __restrict__ offs, double* __restrict__ out,
+                                                       double* __restrict__ out_vals) {
+  // a warp per edge, lane = slot
+  const int lane = threadIdx.x & 31;
+  for (int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < count;
+       e += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const uint32_t n = nst[e];
+    if (n <= 2u) continue;
+    const int32_t fi = first_invalid[e];
+    const uint32_t c = fi >= 1 ? (uint32_t)fi : n - 2u;
+    const uint64_t o = offs[e];
+    double f[D], t[D];
+    bk_load<D>(src, e, f, t);
+    const double* tf = pv.tfrac + __ldg(pv.off + n);
+    for (uint32_t k = (uint32_t)lane; k < c; k += 32) {
+      const double tt = __ldg(tf + 1u + k);
+#pragma unroll
+      for (int j = 0; j < D; ++j) out[(o + k) * D + j] = __dadd_rn(f[j], __dmul_rn(__dsub_rn(t[j], f[j]), tt));
+      out_vals[o + k] = (fi >= 1 && k + 1 == c) ? 1.0 : 0.0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Host drivers
 // ---------------------------------------------------------------------------
 template <int D>
@@ -489,6 +644,33 @@ static int edges_count_scan(bpomp_ctx* ctx, const EdgeSrc& src, int64_t count, i
 
 template <int D>
 static int edge_pfree_impl(bpomp_ctx* ctx, const EdgeSrc& src, int64_t count, double* pfree, uint32_t* nlookups) {
+  // small batches (a search's worth of edges against a model of moderate size): one launch, one wait
+  if (ctx->fused_pfree && (double)count * 4.0 * (double)std::max<uint64_t>(ctx->bel_count, 1) <= 4e8) {
+    const int K = ctx->knn;
+    BP_TRY(bp_reserve(ctx, ctx->s_h, (size_t)count * (sizeof(double) + sizeof(uint32_t)), false));
+    double* d_pf = ctx->s_h.as<double>();
+    uint32_t* d_nl = reinterpret_cast<uint32_t*>(d_pf + count);
+    const size_t sm = (size_t)BKF_WARPS * K * 32 * (sizeof(double) + sizeof(uint32_t));
+    auto kern = bk_pfree_fused<D>;
+    BP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    const int grid = (int)std::min<int64_t>(count, (int64_t)ctx->num_sms * 16);
+    kern<<<grid, BKF_WARPS * 32, sm, ctx->stream>>>(src, count, ctx->L, ctx->perm_view(), ctx->d_bel_pts.as<double>(),
+                                                    ctx->d_bel_vals.as<double>(), ctx->bel_count, K, ctx->prior,
+                                                    ctx->prior_weight, d_pf, d_nl);
+    ctx->launches++;
+    BP_CUDA(ctx, cudaGetLastError());
+    BP_CUDA(ctx, cudaMemcpyAsync(pfree, d_pf, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (nlookups)
+      BP_CUDA(ctx, cudaMemcpyAsync(nlookups, d_nl, (size_t)count * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    BP_TRY(bp_read_flags(ctx));  // one wait for the results and the flags
+    if (ctx->h_flags[1]) {
+      ctx->h_flags[1] = 0;
+      ctx->h_flags[0] = 0;
+      return bp_fail(ctx, BPOMP_ERR_RANGE, "an edge has more than %u states (segment_length too small)", BPOMP_NSTATES_MAX);
+    }
+    if (!ctx->h_flags[0]) return BPOMP_OK;
+    // some sample orders were missing: the general path below uploads them and redoes the batch
+  }
   uint64_t nq = 0;
   BP_TRY(edges_count_scan<D>(ctx, src, count, 0, nullptr, &nq));
   int grid = (int)std::min<int64_t>((count + 255) / 256, (int64_t)ctx->num_sms * 8);
@@ -601,6 +783,63 @@ extern "C" int bpomp_belief_edge_pfree_indexed(bpomp_ctx* ctx, const uint32_t* f
   EdgeSrc src;
   BP_TRY(upload_edges(ctx, nullptr, nullptr, from_ids, to_ids, count, src));
   return edge_pfree_dispatch(ctx, src, count, pfree, nlookups);
+}
+
+template <int D>
+static int append_known_impl(bpomp_ctx* ctx, const EdgeSrc& src, int64_t count, const int32_t* d_first,
+                             const uint32_t* d_nst, const uint64_t* d_offs, uint64_t total) {
+  BP_TRY(belief_grow(ctx, total));
+  const int grid = (int)std::min<int64_t>((count + 3) / 4, (int64_t)ctx->num_sms * 8);
+  bk_append_known<D><<<grid, 128, 0, ctx->stream>>>(src, count, ctx->perm_view(), d_first, d_nst, d_offs,
+                                                    ctx->d_bel_pts.as<double>() + ctx->bel_count * D,
+                                                    ctx->d_bel_vals.as<double>() + ctx->bel_count);
+  ctx->launches++;
+  BP_CUDA(ctx, cudaGetLastError());
+  ctx->bel_count += total;
+  return BPOMP_OK;
+}
+static int append_known_dispatch(bpomp_ctx* ctx, const EdgeSrc& src, int64_t count, const int32_t* d_first,
+                                 const uint32_t* d_nst, const uint64_t* d_offs, uint64_t total) {
+  BK_DISPATCH(append_known_impl, ctx, src, count, d_first, d_nst, d_offs, total);
+}
+
+extern "C" int bpomp_belief_append_checked_indexed(bpomp_ctx* ctx, const uint32_t* from_ids, const uint32_t* to_ids,
+                                                   const int32_t* first_invalid_slot, const uint32_t* nstates,
+                                                   int64_t count) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
+  if (count < 0 || (count > 0 && (!from_ids || !to_ids || !first_invalid_slot || !nstates)))
+    return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
+  if (count == 0) return BPOMP_OK;
+  std::vector<uint64_t> offs((size_t)count + 1, 0);
+  uint32_t nmax = 0;
+  for (int64_t e = 0; e < count; ++e) {
+    const uint32_t n = nstates[e];
+    if (n < 2u || n > BPOMP_NSTATES_MAX) return bp_fail(ctx, BPOMP_ERR_RANGE, "nstates[%lld] = %u is out of range", (long long)e, n);
+    const int32_t fi = first_invalid_slot[e];
+    if (fi >= 1 && (uint32_t)fi > n - 2u) return bp_fail(ctx, BPOMP_ERR_RANGE, "first_invalid_slot[%lld] exceeds nstates - 2", (long long)e);
+    offs[(size_t)e + 1] = offs[(size_t)e] + (n <= 2u ? 0u : (fi >= 1 ? (uint32_t)fi : n - 2u));
+    nmax = std::max(nmax, n);
+  }
+  const uint64_t total = offs[(size_t)count];
+  if (total == 0) return BPOMP_OK;
+  if (nmax > ctx->perm_reserved) {  // make the sample orders of every nStates in the batch resident
+    std::vector<uint32_t> ns(nstates, nstates + count);
+    std::sort(ns.begin(), ns.end());
+    ns.erase(std::unique(ns.begin(), ns.end()), ns.end());
+    BP_TRY(bp_perm_ensure_rows(ctx, ns));
+  }
+  EdgeSrc src;
+  BP_TRY(upload_edges(ctx, nullptr, nullptr, from_ids, to_ids, count, src));
+  BP_TRY(bp_reserve(ctx, ctx->s_c, (size_t)count * sizeof(int32_t), false));
+  BP_TRY(bp_reserve(ctx, ctx->s_e, (size_t)count * sizeof(uint32_t), false));
+  BP_TRY(bp_reserve(ctx, ctx->s_g, ((size_t)count + 1) * sizeof(uint64_t), false));
+  BP_CUDA(ctx, cudaMemcpyAsync(ctx->s_c.p, first_invalid_slot, (size_t)count * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  BP_CUDA(ctx, cudaMemcpyAsync(ctx->s_e.p, nstates, (size_t)count * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  BP_CUDA(ctx, cudaMemcpyAsync(ctx->s_g.p, offs.data(), ((size_t)count + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  BP_TRY(append_known_dispatch(ctx, src, count, ctx->s_c.as<int32_t>(), ctx->s_e.as<uint32_t>(), ctx->s_g.as<uint64_t>(), total));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `offs` is a host temporary
+  return BPOMP_OK;
 }
 
 extern "C" int bpomp_belief_append_checked(bpomp_ctx* ctx, const double* from, const double* to,

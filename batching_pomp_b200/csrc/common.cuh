@@ -136,6 +136,7 @@ struct bpomp_ctx {
   bool work_dirty[4] = {true, true, true, true};
   const int* last_slow_count = nullptr;
   DevBuf d_slow_list[4];                    // per pipeline lane: indices of the edges the fast kernel left over
+  int fused_pfree = 1;                      // 0: never use the one-launch free-probability kernel (testing)
   int fast_mode = 1;                        // 0: never use the fast kernel (testing / tuning)
   int fast_warps = 0;                       // > 0: cap on the warps per CTA of the fast kernel (tuning)
   int64_t fast_min_edges = 4096;            // smaller batches go to the general kernel alone (one launch)

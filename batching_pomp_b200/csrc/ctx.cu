@@ -346,6 +346,7 @@ extern "C" int bpomp_set_option(bpomp_ctx* ctx, const char* name, int64_t value)
   if (!strcmp(name, "fast_edge_kernel")) ctx->fast_mode = value ? 1 : 0;
   else if (!strcmp(name, "fast_edge_min_edges")) ctx->fast_min_edges = value < 0 ? 0 : value;
   else if (!strcmp(name, "fast_edge_warps")) ctx->fast_warps = (int)value;
+  else if (!strcmp(name, "fused_pfree")) ctx->fused_pfree = value ? 1 : 0;
   else return bp_fail(ctx, BPOMP_ERR_INVALID, "unknown option '%s'", name);
   return BPOMP_OK;
 }

@@ -857,16 +857,12 @@ bool BatchingPOMP::checkAndUpdatePathBlocked(const std::vector<Edge>& ePath) {
       setProbFree(ep, 1.0);
     }
   }
-  // belief inserts of the committed edges, in check order (BP.cpp:523-537), replayed on the device
-  std::vector<double> fs(committed * mDim), ts(committed * mDim);
+  // belief inserts of the committed edges, in check order (BP.cpp:523-537), replayed on the device from the
+  // vertex ids and the nStates the check reported
   uint64_t added = 0;
-  for (size_t i = 0; i < committed; ++i) {
-    std::memcpy(&fs[i * mDim], vertexState(from[i]), sizeof(double) * mDim);
-    std::memcpy(&ts[i * mDim], vertexState(to[i]), sizeof(double) * mDim);
-    added += valid[i] ? ns[i] - 2u : (uint32_t)first[i];
-  }
+  for (size_t i = 0; i < committed; ++i) added += valid[i] ? ns[i] - 2u : (uint32_t)first[i];
   if (added > 0) {
-    BP_DEV(bpomp_belief_append_checked(dev(), fs.data(), ts.data(), first.data(), (int64_t)committed));
+    BP_DEV(bpomp_belief_append_checked_indexed(dev(), from.data(), to.data(), first.data(), ns.data(), (int64_t)committed));
     mBeliefEmpty = false;
   }
   mCollCheckTime += now() - t0;

@@ -79,7 +79,8 @@ BPOMP_API int bpomp_set_stream(bpomp_ctx* ctx, void* cuda_stream);
 BPOMP_API void* bpomp_get_stream(bpomp_ctx* ctx);
 /* Tuning / testing switches; results never depend on them.  name: "fast_edge_kernel" (1 = use the fast
  * box-world edge kernel where it applies (default), 0 = general kernel only), "fast_edge_min_edges" (batches
- * below this go to the general kernel alone, default 4096), "fast_edge_warps" (cap on its warps per CTA, 0 = auto). */
+ * below this go to the general kernel alone, default 4096), "fast_edge_warps" (cap on its warps per CTA, 0 = auto), "fused_pfree" (1 = small free-probability batches run
+ * as one launch (default), 0 = always the tiled multi-launch path). */
 BPOMP_API int bpomp_set_option(bpomp_ctx* ctx, const char* name, int64_t value);
 /* Diagnostics: "slow_edges" = edges of the last edge call that the fast kernel left to the general one (waits
  * for the stream); "fast_world" = 1 if the current world has the fast kernel's tables. */
@@ -198,6 +199,11 @@ BPOMP_API int bpomp_belief_append(bpomp_ctx* ctx, const double* states, const do
  * order with value 0.0, the first invalid one with 1.0.  Edges are processed in array order. */
 BPOMP_API int bpomp_belief_append_checked(bpomp_ctx* ctx, const double* from, const double* to,
                                           const int32_t* first_invalid_slot, int64_t count);
+/* The same for edges given as vertex ids, with the nStates bpomp_edges_check* reported for them (the caller has
+ * both from the check it just made): no endpoint states travel back to the device. */
+BPOMP_API int bpomp_belief_append_checked_indexed(bpomp_ctx* ctx, const uint32_t* from_ids, const uint32_t* to_ids,
+                                                  const int32_t* first_invalid_slot, const uint32_t* nstates,
+                                                  int64_t count);
 BPOMP_API int bpomp_belief_size(bpomp_ctx* ctx, uint64_t* count);
 BPOMP_API int bpomp_belief_clear(bpomp_ctx* ctx);
 /* estimate — KNNModel.hpp:101-134 with beliefDistanceFunction (src/BatchingPOMP.cpp:213-219). */

@@ -289,6 +289,21 @@ BPOMP_API int bpomp_belief_append_checked(bpomp_ctx* c, const double* from, cons
   }
   return BPOMP_OK;
 }
+BPOMP_API int bpomp_belief_append_checked_indexed(bpomp_ctx* c, const uint32_t* from_ids, const uint32_t* to_ids,
+                                                  const int32_t* first_invalid_slot, const uint32_t* nstates,
+                                                  int64_t count) {
+  if (!c) return BPOMP_ERR_INVALID;
+  if (count == 0) return BPOMP_OK;
+  std::vector<double> f, t;
+  int rc = gather(c, from_ids, count, f);
+  if (rc) return rc;
+  rc = gather(c, to_ids, count, t);
+  if (rc) return rc;
+  for (int64_t e = 0; e < count; ++e)
+    if (nstates[e] != orc_edge_states(&f[(size_t)e * c->dim], &t[(size_t)e * c->dim], c->dim, c->L, nullptr, 0))
+      return BPOMP_ERR_RANGE;
+  return bpomp_belief_append_checked(c, f.data(), t.data(), first_invalid_slot, count);
+}
 BPOMP_API int bpomp_belief_edge_pfree_indexed(bpomp_ctx* c, const uint32_t* from_ids, const uint32_t* to_ids,
                                               int64_t count, double* pfree, uint32_t* nlookups) {
   if (!c) return BPOMP_ERR_INVALID;

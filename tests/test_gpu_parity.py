@@ -377,6 +377,59 @@ def test_belief_edge_pfree_and_append_checked(capi, orc, wl):
     ctx.close()
 
 
+@pytest.mark.parametrize("d,K,M,L", [(7, 15, 20000, None), (2, 15, 5000, 0.004), (3, 1, 3000, None), (5, 32, 9000, None),
+                                     (7, 15, 9, None), (2, 15, 600, 0.0002)])
+def test_belief_edge_pfree_one_launch_path(capi, orc, wl, d, K, M, L):
+    """Small batches run computeAndSetEdgeFreeProbability (BP.cpp:464-493) as ONE launch; that path, the
+    tiled multi-launch path and the oracle must agree bit for bit (ties, M < K, absent sample orders)."""
+    L = L or wl.segment_length(d)
+    base = wl.uniform(71, (M, d))
+    base[M // 2:] = base[: M - M // 2]  # duplicates: equal distances, the earlier index must win
+    vals = (wl.uniform(72, (M,)) < 0.4).astype(np.float64)
+    frm, to = wl.random_edges(600, d, seed=73, max_len=1.0)
+    frm[:50] = base[:50]  # zero-distance queries -> the 1e-4 clamp
+    want_pf, want_nl = orc.belief_edge_pfree(frm, to, L, base, vals, K=K, nthreads=orc.max_threads())
+    for fused in (1, 0):
+        ctx = capi.Context(d, L)
+        ctx.belief_config(K, 0.5, 0.25)
+        ctx.set_option("fused_pfree", fused)
+        ctx.belief_append(base, vals)
+        n0 = ctx.launches()
+        pf, nl = ctx.belief_edge_pfree(frm, to)
+        if fused and L >= 0.004:
+            assert ctx.launches() - n0 == 1
+        np.testing.assert_array_equal(nl, want_nl)
+        np.testing.assert_array_equal(pf, want_pf)
+        ctx.close()
+
+
+def test_belief_append_checked_indexed_matches_explicit(capi, orc, wl):
+    d, N = 7, 4000
+    ctx, L, lo, hi = _ctx_boxes(capi, wl, d, 500, seed=3)
+    ctx2, _, _, _ = _ctx_boxes(capi, wl, d, 500, seed=3)
+    verts = wl.halton(N, d)
+    ctx.vertices_append(verts)
+    rng = np.random.default_rng(5)
+    fi = rng.integers(0, N, 3000).astype(np.uint32)
+    ti = rng.integers(0, N, 3000).astype(np.uint32)
+    ti[:10] = fi[:10]  # zero-length edges: two states, nothing to add
+    v, f, n = ctx.edges_check_indexed(fi, ti)
+    ctx.belief_append_checked_indexed(fi, ti, f, n)
+    ctx2.belief_append_checked(verts[fi], verts[ti], f)
+    assert ctx.belief_size() == ctx2.belief_size() > 0
+    q = wl.uniform(9, (2000, d))
+    np.testing.assert_array_equal(ctx.belief_estimate(q), ctx2.belief_estimate(q))
+    fr2, to2 = wl.random_edges(500, d, seed=10, max_len=0.8)
+    a, b = ctx.belief_edge_pfree(fr2, to2), ctx2.belief_edge_pfree(fr2, to2)
+    np.testing.assert_array_equal(a[0], b[0])
+    with pytest.raises(capi.BpompError):
+        ctx.belief_append_checked_indexed(fi[:5], ti[:5], f[:5], np.ones(5, dtype=np.uint32))
+    with pytest.raises(capi.BpompError):
+        ctx.belief_append_checked_indexed(fi[10:12], ti[10:12], np.array([10**6, 1], dtype=np.int32), n[10:12])
+    ctx.close()
+    ctx2.close()
+
+
 def test_indexed_variants_match_explicit(capi, orc, wl):
     d, N = 7, 5000
     ctx, L, lo, hi = _ctx_boxes(capi, wl, d, 500, seed=3)
