@@ -15,6 +15,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "belief_grid.cuh"
 
 #define BK_QB 128    // threads per block
 #ifndef BK_QT
@@ -49,6 +50,7 @@ extern "C" int bpomp_belief_clear(bpomp_ctx* ctx) {
   if (!ctx) return BPOMP_ERR_INVALID;
   bp_enter(ctx);
   ctx->bel_count = 0;
+  ctx->bg_count = 0;
   return BPOMP_OK;
 }
 
@@ -455,7 +457,8 @@ __global__ void __launch_bounds__(BKF_WARPS * 32) bk_pfree_fused(EdgeSrc src, in
                                                                  const double* __restrict__ pts,
                                                                  const double* __restrict__ vals, uint64_t M, int K,
                                                                  double prior, double prior_weight,
-                                                                 double* __restrict__ pfree, uint32_t* __restrict__ nlook) {
+                                                                 double* __restrict__ pfree, uint32_t* __restrict__ nlook,
+                                                                 BelGridView bg) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* kd = reinterpret_cast<double*>(smem) + (size_t)warp * K * 32 + lane;                       // [K][32] per warp
@@ -489,7 +492,13 @@ __global__ void __launch_bounds__(BKF_WARPS * 32) bk_pfree_fused(EdgeSrc src, in
       double x[D];
 #pragma unroll
       for (int j = 0; j < D; ++j) x[j] = __dadd_rn(f[j], __dmul_rn(d[j], tt));
-      const double est = bkf_estimate_warp<D>(x, pts, vals, M, K, prior, prior_weight, kd, ki, lane);
+      double est;
+      if constexpr (D <= 3) {
+        est = bg.Mg > 0 ? bg_estimate_warp<D>(x, bg, pts, vals, M, K, prior, prior_weight, lane)
+                        : bkf_estimate_warp<D>(x, pts, vals, M, K, prior, prior_weight, kd, ki, lane);
+      } else {
+        est = bkf_estimate_warp<D>(x, pts, vals, M, K, prior, prior_weight, kd, ki, lane);
+      }
       if (lane == 0) s_est[qi] = est;
     }
     __syncthreads();
@@ -533,6 +542,76 @@ __global__ void __launch_bounds__(128) bk_append_known(EdgeSrc src, int64_t coun
   }
 }
 
+// KNNModel::estimate of a query array through the index: a warp per query, the k best in registers.
+#define BKG_WARPS 8
+template <int D>
+__global__ void __launch_bounds__(BKG_WARPS * 32) bk_estimate_grid(const double* __restrict__ queries, int64_t nq,
+                                                                   const double* __restrict__ pts,
+                                                                   const double* __restrict__ vals, uint64_t M, int K,
+                                                                   double prior, double prior_weight,
+                                                                   double* __restrict__ out, BelGridView bg) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t qi = (int64_t)blockIdx.x * BKG_WARPS + warp; qi < nq; qi += (int64_t)gridDim.x * BKG_WARPS) {
+    double x[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) x[j] = __ldg(queries + qi * D + j);
+    const double est = bg_estimate_warp<D>(x, bg, pts, vals, M, K, prior, prior_weight, lane);
+    if (lane == 0) out[qi] = est;
+  }
+}
+
+// Brings the grid index of the belief model up to date (D <= 3) and describes it in `g` (g.Mg = 0: no index,
+// the callers scan).  The index covers the prefix [0, bg_count); it is rebuilt once the tail of newer points
+// exceeds 512 + bg_count/16, i.e. after a constant fraction of appends, all on the context's stream.
+template <int D>
+static int bel_grid_prepare(bpomp_ctx* ctx, BelGridView& g) {
+  memset(&g, 0, sizeof(g));
+  if constexpr (D > 3) {
+    return BPOMP_OK;
+  } else {
+    const uint64_t M = ctx->bel_count;
+    if (!ctx->belief_grid || M < 512) return BPOMP_OK;
+    if (ctx->bg_count > M) ctx->bg_count = 0;
+    if (ctx->bg_count == 0 || M - ctx->bg_count > 512 + ctx->bg_count / 16) {
+      // about two points per cell, 2^bits cells per dimension
+      const uint32_t bmax = D == 1 ? 20u : D == 2 ? 10u : 6u;
+      uint32_t bits = 1;
+      while (bits < bmax && std::pow(2.0, (double)(D * bits)) * 2.0 < (double)M) ++bits;
+      const uint32_t G = 1u << bits;
+      const uint64_t cells = 1ull << (D * bits);
+      BP_TRY(bp_reserve(ctx, ctx->d_bg_start, (cells + 1) * sizeof(unsigned long long), false));
+      BP_TRY(bp_reserve(ctx, ctx->d_bg_cnt, cells * sizeof(uint32_t), false));
+      BP_TRY(bp_reserve(ctx, ctx->d_bg_cell, M * sizeof(uint32_t), false));
+      BP_TRY(bp_reserve(ctx, ctx->d_bg_pts, M * D * sizeof(double), false));
+      BP_TRY(bp_reserve(ctx, ctx->d_bg_idx, M * sizeof(uint32_t), false));
+      BP_TRY(bp_reserve(ctx, ctx->d_bg_geom, 9 * sizeof(double), false));
+      const double* pts = ctx->d_bel_pts.as<double>();
+      BP_CUDA(ctx, cudaMemsetAsync(ctx->d_bg_cnt.p, 0, cells * sizeof(uint32_t), ctx->stream));
+      bg_bbox_kernel<D><<<1, 1024, 0, ctx->stream>>>(pts, M, G, ctx->d_bg_geom.as<double>());
+      const int grid = (int)std::min<uint64_t>((M + 255) / 256, (uint64_t)ctx->num_sms * 8);
+      bg_hist_kernel<D><<<grid, 256, 0, ctx->stream>>>(pts, M, bits, ctx->d_bg_geom.as<double>(), ctx->d_bg_cell.as<uint32_t>(),
+                                                       ctx->d_bg_cnt.as<uint32_t>());
+      ctx->launches += 2;
+      BP_TRY(bp_exclusive_scan_u32(ctx, ctx->d_bg_cnt.as<uint32_t>(), cells, ctx->d_bg_start.as<uint64_t>(), ctx->s_scan));
+      bg_scatter_kernel<D><<<grid, 256, 0, ctx->stream>>>(pts, M, ctx->d_bg_cell.as<uint32_t>(), ctx->d_bg_cnt.as<uint32_t>(),
+                                                          ctx->d_bg_start.as<unsigned long long>(), ctx->d_bg_pts.as<double>(),
+                                                          ctx->d_bg_idx.as<uint32_t>());
+      ctx->launches++;
+      BP_CUDA(ctx, cudaGetLastError());
+      ctx->bg_count = M;
+      ctx->bg_bits = bits;
+      ctx->bg_builds++;
+    }
+    g.start = ctx->d_bg_start.as<unsigned long long>();
+    g.pts = ctx->d_bg_pts.as<double>();
+    g.idx = ctx->d_bg_idx.as<uint32_t>();
+    g.geom = ctx->d_bg_geom.as<double>();
+    g.bits = ctx->bg_bits;
+    g.Mg = ctx->bg_count;
+    return BPOMP_OK;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Host drivers
 // ---------------------------------------------------------------------------
@@ -541,6 +620,19 @@ static int knn_estimate_dev(bpomp_ctx* ctx, const double* d_queries, int64_t nq,
   if (nq <= 0) return BPOMP_OK;
   const uint64_t M = ctx->bel_count;
   const int K = ctx->knn;
+  if constexpr (D <= 3) {
+    BelGridView bg;
+    BP_TRY(bel_grid_prepare<D>(ctx, bg));
+    if (bg.Mg > 0) {
+      const int grid = (int)std::min<int64_t>((nq + BKG_WARPS - 1) / BKG_WARPS, (int64_t)ctx->num_sms * 16);
+      bk_estimate_grid<D><<<grid, BKG_WARPS * 32, 0, ctx->stream>>>(d_queries, nq, ctx->d_bel_pts.as<double>(),
+                                                                    ctx->d_bel_vals.as<double>(), M, K, ctx->prior,
+                                                                    ctx->prior_weight, d_out, bg);
+      ctx->launches++;
+      BP_CUDA(ctx, cudaGetLastError());
+      return BPOMP_OK;
+    }
+  }
   int P = 1;
   uint64_t chunk = M ? M : 1;
   if (M > 0) {
@@ -645,7 +737,10 @@ static int edges_count_scan(bpomp_ctx* ctx, const EdgeSrc& src, int64_t count, i
 template <int D>
 static int edge_pfree_impl(bpomp_ctx* ctx, const EdgeSrc& src, int64_t count, double* pfree, uint32_t* nlookups) {
   // small batches (a search's worth of edges against a model of moderate size): one launch, one wait
-  if (ctx->fused_pfree && (double)count * 4.0 * (double)std::max<uint64_t>(ctx->bel_count, 1) <= 4e8) {
+  BelGridView bg;
+  BP_TRY(bel_grid_prepare<D>(ctx, bg));
+  // with the index a query costs the same whatever the size of the model
+  if (ctx->fused_pfree && (bg.Mg > 0 || (double)count * 4.0 * (double)std::max<uint64_t>(ctx->bel_count, 1) <= 4e8)) {
     const int K = ctx->knn;
     BP_TRY(bp_reserve(ctx, ctx->s_h, (size_t)count * (sizeof(double) + sizeof(uint32_t)), false));
     double* d_pf = ctx->s_h.as<double>();
@@ -656,7 +751,7 @@ static int edge_pfree_impl(bpomp_ctx* ctx, const EdgeSrc& src, int64_t count, do
     const int grid = (int)std::min<int64_t>(count, (int64_t)ctx->num_sms * 16);
     kern<<<grid, BKF_WARPS * 32, sm, ctx->stream>>>(src, count, ctx->L, ctx->perm_view(), ctx->d_bel_pts.as<double>(),
                                                     ctx->d_bel_vals.as<double>(), ctx->bel_count, K, ctx->prior,
-                                                    ctx->prior_weight, d_pf, d_nl);
+                                                    ctx->prior_weight, d_pf, d_nl, bg);
     ctx->launches++;
     BP_CUDA(ctx, cudaGetLastError());
     BP_CUDA(ctx, cudaMemcpyAsync(pfree, d_pf, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -159,6 +159,12 @@ struct bpomp_ctx {
   double prior = 0.5, prior_weight = 0.25;
   DevBuf d_bel_pts, d_bel_vals;
   uint64_t bel_count = 0;
+  // exact grid index of the belief points for dim <= 3 (belief_grid.cuh): prefix [0, bg_count) indexed
+  DevBuf d_bg_start, d_bg_cnt, d_bg_cell, d_bg_pts, d_bg_idx, d_bg_geom;
+  uint64_t bg_count = 0;
+  uint32_t bg_bits = 0;
+  uint64_t bg_builds = 0;
+  int belief_grid = 1;                      // 0: always scan the whole model (testing)
 
   // pipelined host-buffer edge checks (edge_check.cu)
   cudaStream_t lane_stream[3] = {nullptr, nullptr, nullptr};

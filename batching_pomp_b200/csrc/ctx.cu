@@ -287,6 +287,7 @@ extern "C" void bpomp_destroy(bpomp_ctx* ctx) {
                     &ctx->d_bits, &ctx->d_work, &ctx->d_tmask, &ctx->d_qbox, &ctx->d_perm_s, &ctx->d_perm4, &ctx->d_verts, &ctx->d_active, &ctx->d_nb_rowptr, &ctx->d_nb_col,
                     &ctx->d_nb_dist, &ctx->d_nb_query, &ctx->d_nb_tmp, &ctx->d_nb_tmp2, &ctx->d_grid_cell_start,
                     &ctx->d_grid_ids, &ctx->d_grid_pts, &ctx->d_grid_keys, &ctx->d_bel_pts, &ctx->d_bel_vals,
+                    &ctx->d_bg_start, &ctx->d_bg_cnt, &ctx->d_bg_cell, &ctx->d_bg_pts, &ctx->d_bg_idx, &ctx->d_bg_geom,
                     &ctx->s_a, &ctx->s_b, &ctx->s_c, &ctx->s_d, &ctx->s_e, &ctx->s_f, &ctx->s_g, &ctx->s_h, &ctx->s_i,
                     &ctx->s_j, &ctx->s_scan};
   for (DevBuf* b : bufs) bp_free(*b);
@@ -347,6 +348,7 @@ extern "C" int bpomp_set_option(bpomp_ctx* ctx, const char* name, int64_t value)
   else if (!strcmp(name, "fast_edge_min_edges")) ctx->fast_min_edges = value < 0 ? 0 : value;
   else if (!strcmp(name, "fast_edge_warps")) ctx->fast_warps = (int)value;
   else if (!strcmp(name, "fused_pfree")) ctx->fused_pfree = value ? 1 : 0;
+  else if (!strcmp(name, "belief_grid")) { ctx->belief_grid = value ? 1 : 0; ctx->bg_count = 0; }
   else return bp_fail(ctx, BPOMP_ERR_INVALID, "unknown option '%s'", name);
   return BPOMP_OK;
 }
@@ -365,6 +367,14 @@ extern "C" int bpomp_get_counter(bpomp_ctx* ctx, const char* name, int64_t* valu
   }
   if (!strcmp(name, "fast_world")) {
     *value = ctx->fast.enabled;
+    return BPOMP_OK;
+  }
+  if (!strcmp(name, "belief_grid_builds")) {  // builds of the belief model's grid index so far
+    *value = (int64_t)ctx->bg_builds;
+    return BPOMP_OK;
+  }
+  if (!strcmp(name, "belief_grid_points")) {  // belief points covered by the index
+    *value = (int64_t)ctx->bg_count;
     return BPOMP_OK;
   }
   return bp_fail(ctx, BPOMP_ERR_INVALID, "unknown counter '%s'", name);

@@ -20,6 +20,7 @@
 #include "graphml.hpp"
 
 namespace batching_pomp {
+namespace core {
 
 namespace {
 const double kInf = std::numeric_limits<double>::max();
@@ -126,7 +127,8 @@ BatchingPOMP::BatchingPOMP(const SpaceInformation& si)
       bmExhausted(false), bmCurrRadius(0.0), bmNumVerticesAdded(0), bmNextVertexTarget(0), bmVertInfl(2.0),
       bmRadiusInfl(1.0), bmInitRadius(0.0), bmMaxRadius(0.0), bmCurrVertex(0), bmEdgeMode(false), mNumSolutions(0),
       mBeliefEmpty(true), mNumEdgeChecks(0), mNumCollChecks(0), mNumSearches(0), mNumLookups(0), mLookupTime(0.0),
-      mCollCheckTime(0.0), mSearchTime(0.0), mDeviceTime(0.0), mSearchHostTime(0.0) {
+      mCollCheckTime(0.0), mSearchTime(0.0), mDeviceTime(0.0), mSearchHostTime(0.0), mBeliefK(15), mBeliefPrior(0.5),
+      mBeliefPriorWeight(0.25) {
   if (mDim == 0 || si.low.size() != mDim || si.high.size() != mDim)
     throw Exception("SpaceInformation: bounds must have `dim` entries");
   // mCheckRadius = 0.5*getLongestValidSegmentLength() is captured at construction (BP.cpp:241,278);
@@ -158,7 +160,7 @@ bpomp_ctx* BatchingPOMP::dev() {
   }
   if (mCtx) {  // recycled: same device / dim / L / world, emptied when it was returned
     mLaunchBase = bpomp_launch_count(mCtx);
-    check(bpomp_belief_config(mCtx, 15, 0.5, 0.25));
+    check(bpomp_belief_config(mCtx, mBeliefK, mBeliefPrior, mBeliefPriorWeight));
     mSpace.reset();
     return mCtx;
   }
@@ -174,8 +176,8 @@ bpomp_ctx* BatchingPOMP::dev() {
     } else {
       check(bpomp_world_set_image(mCtx, si.image.data(), si.imageWidth, si.imageHeight, si.imageThreshold));
     }
-    // default belief model: KNNModel(15, 0.5, 0.25, ...) (BP.cpp:300)
-    check(bpomp_belief_config(mCtx, 15, 0.5, 0.25));
+    // belief model: KNNModel(15, 0.5, 0.25, ...) by default (BP.cpp:300), or the caller's (8-argument constructor)
+    check(bpomp_belief_config(mCtx, mBeliefK, mBeliefPrior, mBeliefPriorWeight));
   } catch (...) {
     bpomp_destroy(mCtx);
     mCtx = nullptr;
@@ -183,6 +185,14 @@ bpomp_ctx* BatchingPOMP::dev() {
   }
   mSpace.reset();
   return mCtx;
+}
+
+void BatchingPOMP::setBeliefModel(int k, double prior, double priorWeight) {
+  if (mCtx) throw Exception("setBeliefModel: the belief model is already resident on the device");
+  if (k < 1 || k > 32) throw Exception("setBeliefModel: k must be in 1..32");
+  mBeliefK = k;
+  mBeliefPrior = prior;
+  mBeliefPriorWeight = priorWeight;
 }
 
 BatchingPOMP::~BatchingPOMP() {
@@ -759,7 +769,7 @@ void BatchingPOMP::computeFreeProbabilities(const std::vector<Edge>& edges) {
   double t0 = now();
   if (mBeliefEmpty) {
     // KNNModel::estimate returns the prior while the model has no points (KNNModel.hpp:104-106)
-    const double prior = 0.5;
+    const double prior = mBeliefPrior;
     for (Edge e : edges) {
       size_t nStates = mEdges[e].nStates;
       unsigned int stepSize = static_cast<unsigned int>(nStates / std::log(nStates));
@@ -1141,4 +1151,5 @@ PlannerStatus BatchingPOMP::solve(const PlannerTerminationCondition& ptc) {
   return PlannerStatus::APPROXIMATE_SOLUTION;
 }
 
+}  // namespace core
 }  // namespace batching_pomp

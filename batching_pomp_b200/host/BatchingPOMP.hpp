@@ -24,6 +24,9 @@
 #include "flat_map.hpp"
 
 namespace batching_pomp {
+// The planner core lives in batching_pomp::core; the class named batching_pomp::BatchingPOMP is the OMPL
+// planner of include/batching_pomp/BatchingPOMP.hpp, which wraps this core.
+namespace core {
 
 /// ompl::base::PlannerStatus::StatusType values (OMPL is not linked; numeric values kept).
 enum class PlannerStatus : int {
@@ -150,6 +153,22 @@ public:
   unsigned int getNumBatches() const { return bmNumBatches; }
   bool isExhausted() const { return bmExhausted; }
   double getCurrentRadius() const { return bmCurrRadius; }
+
+  /// The C-space belief model's parameters: KNNModel(k, prior, priorWeight, ...), BP.cpp:300 and the
+  /// 8-argument constructor (BatchingPOMP.hpp:147-154).  Must be set before the first call that needs the GPU.
+  void setBeliefModel(int k, double prior, double priorWeight);
+  int getBeliefK() const { return mBeliefK; }
+  double getBeliefPrior() const { return mBeliefPrior; }
+  double getBeliefPriorWeight() const { return mBeliefPriorWeight; }
+
+  // read-only views of the two roadmaps (the reference's public members g and full_g, BatchingPOMP.hpp:126-131)
+  size_t roadmapSize() const { return mN; }                                  // num_vertices(full_g)
+  const double* roadmapState(uint32_t i) const { return &mRoadmap[(size_t)i * mDim]; }
+  size_t roadmapEdgeCount() const { return mRoadmapEdges.size(); }           // num_edges(full_g)
+  size_t edgeSlots() const { return mEdges.size(); }                         // edge ids are 0 .. edgeSlots()-1
+  const EProps& edgeProps(Edge e) const { return mEdges[e]; }                // g[e]; .removed: cleared by pruning
+  size_t outDegree(Vertex v) const { return mOut[v].size(); }
+  bool beliefEmpty() const { return mBeliefEmpty; }
 
   unsigned int getDimension() const { return mDim; }
   size_t numVertices() const { return mOut.size(); }
@@ -290,6 +309,9 @@ private:
   unsigned int mNumEdgeChecks, mNumCollChecks, mNumSearches, mNumLookups;
   double mLookupTime, mCollCheckTime, mSearchTime;
   double mDeviceTime, mSearchHostTime;
+  int mBeliefK;
+  double mBeliefPrior, mBeliefPriorWeight;
 };
 
+}  // namespace core
 }  // namespace batching_pomp

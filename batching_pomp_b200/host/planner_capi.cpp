@@ -7,8 +7,8 @@
 #include "bpomp_planner.h"
 #include "graphml.hpp"
 
-using batching_pomp::BatchingPOMP;
-using batching_pomp::SpaceInformation;
+using batching_pomp::core::BatchingPOMP;
+using batching_pomp::core::SpaceInformation;
 
 struct bpomp_planner {
   std::unique_ptr<BatchingPOMP> planner;
@@ -22,7 +22,7 @@ static int guarded(bpomp_planner* p, F&& f) {
   try {
     f();
     return 0;
-  } catch (const batching_pomp::Exception& e) {
+  } catch (const batching_pomp::core::Exception& e) {
     (p ? p->error : g_error) = e.what();
     return -1;
   } catch (const std::invalid_argument& e) {
@@ -120,7 +120,7 @@ extern "C" int bpomp_planner_solve(bpomp_planner* p, long max_iterations, double
       --budget;
       return false;
     };
-    batching_pomp::PlannerStatus st = p->planner->solve(ptc);
+    batching_pomp::core::PlannerStatus st = p->planner->solve(ptc);
     if (status) *status = (int)st;
   });
 }

@@ -1,5 +1,6 @@
-// Compiles batching_pomp_b200/host/ompl_adapter.hpp against the OMPL API stand-ins of tests/stubs and drives it
-// the way an OMPL application drives the reference planner (README.md:54-67 of the reference): params through
+// Compiles include/batching_pomp/BatchingPOMP.hpp — the drop-in batching_pomp::BatchingPOMP, included and named
+// exactly as the reference's (BatchingPOMP.hpp:52,68) — against the OMPL API stand-ins of tests/stubs and drives it
+// the way an OMPL application drives the reference planner (README.md:43-67 of the reference): params through
 // the ParamSet by name, a GraphML roadmap file, a ProblemDefinition with one start and a GoalState, solve(ptc),
 // solution read back from the ProblemDefinition.  Linked with the test double of the CUDA C ABI
 // (tests/mock/mock_cuda.cpp) — TEST INFRASTRUCTURE ONLY.
@@ -9,13 +10,13 @@
 #include <string>
 #include <vector>
 
-#include "ompl_adapter.hpp"
+#include <batching_pomp/BatchingPOMP.hpp>
 #include "graphml.hpp"
 
 extern "C" void orc_halton(int64_t first_index, int64_t count, int d, double* out);
 
 namespace ob = ompl::base;
-using batching_pomp::ompl_adapter::DeviceWorldValidityChecker;
+using batching_pomp::DeviceWorldValidityChecker;
 
 class WallWorld : public DeviceWorldValidityChecker {
 public:
@@ -30,8 +31,8 @@ public:
     int col = std::min(255, (int)std::floor(v[0] * 256)), row = std::min(255, (int)std::floor(v[1] * 256));
     return pix_[row * 256 + col] >= 128;
   }
-  void describe(batching_pomp::SpaceInformation& si) const override {
-    si.world = batching_pomp::SpaceInformation::World::IMAGE;
+  void describe(batching_pomp::core::SpaceInformation& si) const override {
+    si.world = batching_pomp::core::SpaceInformation::World::IMAGE;
     si.image = pix_;
     si.imageWidth = 256; si.imageHeight = 256; si.imageThreshold = 128;
   }
@@ -58,7 +59,7 @@ int main(int argc, char** argv) {
   si->setStateValidityCheckingResolution(2e-3);
   si->setup();
 
-  batching_pomp::ompl_adapter::BatchingPOMP planner(si);
+  batching_pomp::BatchingPOMP planner(si);
   REQUIRE(planner.getName() == "BatchingPOMP");
   REQUIRE(planner.params().size() == 7);  // BP.cpp:313-319
   REQUIRE(planner.params().setParam("roadmap_filename", roadmap_file));
@@ -118,7 +119,7 @@ int main(int argc, char** argv) {
   // error paths keep the reference's exception type
   bool threw = false;
   try {
-    batching_pomp::ompl_adapter::BatchingPOMP p2(si);
+    batching_pomp::BatchingPOMP p2(si);
     p2.params().setParam("batching_type", "bogus");
     p2.params().setParam("roadmap_filename", roadmap_file);
     p2.setup();
@@ -126,6 +127,91 @@ int main(int argc, char** argv) {
     threw = std::string(e.what()).find("Invalid batching type") != std::string::npos;
   }
   REQUIRE(threw);
+  // ---- the reference's public members (BatchingPOMP.hpp:116-131) as views ----
+  REQUIRE(planner.mSpace.get() == space.get());
+  REQUIRE(num_vertices(planner.full_g) == N);                    // the roadmap as loaded
+  REQUIRE(num_vertices(planner.g) >= 2 && num_vertices(planner.g) <= N + 2);  // start, goal and the admitted batches
+  REQUIRE(num_edges(planner.g) > 0 && num_edges(planner.g) <= planner.g.edgeSlots());
+  REQUIRE(planner.g[planner.getStartVertex()].v_state[0] == 0.1 && planner.g[planner.getGoalVertex()].v_state[1] == 0.9);
+  REQUIRE(planner.full_g[5].v_state[0] == pts[10] && planner.full_g[5].dim == 2);
+  REQUIRE(planner.mBatchingPtr->getNumBatches() >= 1 && planner.mBatchingPtr->getType() == "hybrid");
+  REQUIRE(planner.mBatchingPtr->getNumVertices() == N && planner.mBatchingPtr->getCurrentRadius() > 0.0);
+  REQUIRE(planner.getSelector() && planner.getSelector()->getType() == "normal");
+  {
+    std::size_t blocked = 0, known = 0;
+    for (uint32_t e = 0; e < planner.g.edgeSlots(); ++e) {
+      if (planner.g.removed(e)) continue;
+      auto ep = planner.g.edge(e);
+      REQUIRE(ep.numStates >= 2 && ep.distance >= 0.0);
+      REQUIRE(std::fabs(planner.vertexDistFun(ep.source, ep.target) - ep.distance) == 0.0);
+      if (ep.blockedStatus != batching_pomp::BatchingPOMP::UNKNOWN) {
+        ++known;
+        const bool isBlocked = ep.blockedStatus == batching_pomp::BatchingPOMP::BLOCKED;
+        blocked += isBlocked;
+        if (known <= 40) REQUIRE(planner.checkAndSetEdgeBlocked(e) == isBlocked);  // re-evaluation agrees
+      }
+    }
+    REQUIRE(known == planner.getNumEdgeChecks() && blocked > 0);
+  }
+  // mBeliefModel is the device-resident model: the planner's checks are in it, estimates come from the device
+  auto knn = std::dynamic_pointer_cast<batching_pomp::cspacebelief::KNNModel>(planner.mBeliefModel);
+  REQUIRE(knn && knn->bound() && knn->getK() == 15 && knn->size() == planner.getNumCollChecks());
+  {
+    ob::ScopedState<> q(space);
+    q[0] = 0.5; q[1] = 0.3;  // inside the wall
+    batching_pomp::BeliefPoint bq(q.get(), 2, 0.0);
+    const double inWall = planner.mBeliefModel->estimate(bq);
+    q[0] = 0.1; q[1] = 0.1;
+    const double atStart = planner.mBeliefModel->estimate(batching_pomp::BeliefPoint(q.get(), 2, 0.0));
+    REQUIRE(inWall > 0.0 && inWall < 1.0 && atStart >= 0.0 && atStart < inWall);
+    const std::size_t before = knn->size();
+    planner.mBeliefModel->addPoint(batching_pomp::BeliefPoint(q.get(), 2, 1.0));
+    REQUIRE(knn->size() == before + 1);
+    REQUIRE(planner.mBeliefModel->estimate(batching_pomp::BeliefPoint(q.get(), 2, 0.0)) > atStart);
+    const double pf = planner.computeAndSetEdgeFreeProbability(0);
+    REQUIRE(pf > 0.0 && pf <= 1.0);
+  }
+
+  // ---- the 8-argument constructor (BatchingPOMP.hpp:147-154) ----
+  {
+    typedef batching_pomp::BatchingPOMP BP;
+    auto model = std::make_shared<batching_pomp::cspacebelief::KNNModel>(7, 0.4, 0.5);
+    std::unique_ptr<batching_pomp::util::Selector<BP::Graph>> sel(new batching_pomp::util::Selector<BP::Graph>("failfast"));
+    BP p8(si, std::shared_ptr<BP::BatchingManagerType>(), model, std::move(sel), roadmap_file, 0.3, 0.5, 1.1);
+    REQUIRE(p8.params().size() == 0);  // BP.cpp:221-267 declares no parameters
+    REQUIRE(p8.getRoadmapFileName() == roadmap_file && p8.getStartGoalRadius() == 0.3 && p8.getIncrement() == 0.5 &&
+            p8.getPruneThreshold() == 1.1);
+    REQUIRE(p8.core().getBeliefK() == 7 && p8.core().getBeliefPrior() == 0.4 && p8.core().getBeliefPriorWeight() == 0.5);
+    bool threw8 = false;
+    try {
+      p8.setup();  // batching_type is still "" -> the reference throws here too (BP.cpp:740-742)
+    } catch (const ompl::Exception& e) {
+      threw8 = std::string(e.what()).find("Invalid batching type") != std::string::npos;
+    }
+    REQUIRE(threw8);
+    p8.setBatchingType("vertex");
+    p8.setSelectorType("failfast");
+    auto pdef8 = std::make_shared<ob::ProblemDefinition>(si);
+    pdef8->setStartAndGoalStates(start, goal);
+    p8.setProblemDefinition(pdef8);
+    p8.setup();
+    REQUIRE(p8.getSelector()->getType() == "failfast" && p8.mBatchingPtr->getType() == "vertex");
+    long b8 = 200;
+    ob::PlannerTerminationCondition ptc8([&b8]() { return --b8 < 0; });
+    bool solved = false;
+    for (int call = 0; call < 20 && !solved; ++call) {
+      p8.solve(ptc8);
+      solved = pdef8->getSolutionCount() > 0;
+    }
+    REQUIRE(solved && model->bound() && model->size() == p8.getNumCollChecks());
+    bool bad = false;
+    try {
+      batching_pomp::util::Selector<BP::Graph> s2("bogus");
+    } catch (const std::invalid_argument&) {
+      bad = true;  // Selector.hpp:74
+    }
+    REQUIRE(bad);
+  }
   printf("ompl adapter ok: %d improving solutions, cost %.6f, %u searches\n", improved, last_cost,
          planner.getNumSearches());
   return 0;

@@ -12,8 +12,8 @@
 
 #include "BatchingPOMP.hpp"
 
-using batching_pomp::BatchingPOMP;
-using batching_pomp::SpaceInformation;
+using batching_pomp::core::BatchingPOMP;
+using batching_pomp::core::SpaceInformation;
 
 template <typename T>
 static std::vector<T> slurp(const char* path, size_t count) {
@@ -55,12 +55,12 @@ int main(int argc, char** argv) {
     auto st = p.solve([&]() { return --left < 0; });
     searches += p.getNumSearches() - before;
     double t = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    if (st == batching_pomp::PlannerStatus::APPROXIMATE_SOLUTION && p.getNumSolutions() > (size_t)solutions) {
+    if (st == batching_pomp::core::PlannerStatus::APPROXIMATE_SOLUTION && p.getNumSolutions() > (size_t)solutions) {
       solutions = (int)p.getNumSolutions();
       printf("t=%.2fs solution %d cost %.6f searches %u edges %zu\n", t, solutions, p.getCurrentBestCost(),
              p.getNumSearches(), p.numEdges());
     }
-    if (st == batching_pomp::PlannerStatus::EXACT_SOLUTION || st == batching_pomp::PlannerStatus::TIMEOUT) break;
+    if (st == batching_pomp::core::PlannerStatus::EXACT_SOLUTION || st == batching_pomp::core::PlannerStatus::TIMEOUT) break;
   }
   double total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   printf("total %.2fs, searches %u, search_s %.2f lookup_s %.2f collcheck_s %.2f, vertices %zu edges %zu\n", total,

@@ -396,12 +396,76 @@ def test_belief_edge_pfree_one_launch_path(capi, orc, wl, d, K, M, L):
         ctx.belief_config(K, 0.5, 0.25)
         ctx.set_option("fused_pfree", fused)
         ctx.belief_append(base, vals)
+        ctx.belief_estimate(frm[:1])  # dim <= 3: builds the model's spatial index (its own launches)
         n0 = ctx.launches
         pf, nl = ctx.belief_edge_pfree(frm, to)
         if fused and resident:
             assert ctx.launches - n0 == 1
         np.testing.assert_array_equal(nl, want_nl)
         np.testing.assert_array_equal(pf, want_pf)
+        ctx.close()
+
+
+def _clustered_points(wl, d, M, seed):
+    """Belief-like point sets: states strung along segments (checked edges), plus duplicates and a far outlier."""
+    rng = np.random.default_rng(seed)
+    nseg = max(1, M // 12)
+    a = rng.random((nseg, d)) * 0.6 + 0.2
+    b = a + (rng.random((nseg, d)) - 0.5) * 0.1
+    t = rng.random((M, 1))
+    k = rng.integers(0, nseg, M)
+    pts = a[k] + (b[k] - a[k]) * t
+    pts[M // 3: M // 3 + M // 10] = pts[: M // 10]  # duplicates: equal distances, the earlier index must win
+    pts[-1] = 3.0  # far outside everything else: stretches the bounding box
+    return np.ascontiguousarray(pts)
+
+
+@pytest.mark.parametrize("d,K,M", [(2, 15, 6000), (2, 15, 40000), (1, 15, 3000), (3, 15, 20000), (2, 1, 5000), (3, 32, 4000),
+                                   (2, 15, 600)])
+def test_belief_grid_index_equals_scan_and_oracle(capi, orc, wl, d, K, M):
+    """f4: the belief model's spatial index (KNNModel's GNAT, KNNModel.hpp:65, :108-111) for dim <= 3.  Estimates
+    through the grid, through the plain scan and from the oracle are bit-equal: clustered points, duplicates,
+    queries on points (distance 0), inside clusters, in empty regions and outside the bounding box; the model grows
+    between queries (tail of unindexed points, rebuilds)."""
+    L = wl.segment_length(d)
+    pts = _clustered_points(wl, d, M, seed=11 + d)
+    vals = (wl.uniform(12, (M,)) < 0.4).astype(np.float64)
+    rng = np.random.default_rng(5)
+    q = np.concatenate([pts[rng.integers(0, M, 300)],                                     # on points
+                        pts[rng.integers(0, M, 600)] + (rng.random((600, d)) - 0.5) * 0.01,  # near clusters
+                        rng.random((600, d)) * 1.4 - 0.2,                                   # anywhere, also outside
+                        np.full((3, d), -5.0), np.full((3, d), 9.0)])
+    ctxs = []
+    for grid in (1, 0):
+        ctx = capi.Context(d, L)
+        ctx.belief_config(K, 0.5, 0.25)
+        ctx.set_option("belief_grid", grid)
+        ctxs.append(ctx)
+    steps = [M // 2, M // 2 + 100, M // 2 + 700, M]  # first build, a short tail, a longer tail, a rebuild
+    prev = 0
+    for m in steps:
+        for ctx in ctxs:
+            ctx.belief_append(pts[prev:m], vals[prev:m])
+        prev = m
+        want = orc.belief_estimate(pts[:m], vals[:m], q, K=K, nthreads=orc.max_threads())
+        got = [ctx.belief_estimate(q) for ctx in ctxs]
+        np.testing.assert_array_equal(got[1], want)
+        np.testing.assert_array_equal(got[0], want)
+    if M >= 1024:
+        assert ctxs[0].counter("belief_grid_builds") >= 2 and ctxs[0].counter("belief_grid_points") > 0
+    assert ctxs[1].counter("belief_grid_builds") == 0
+    # edge free-probabilities (the planner's call) through the index
+    frm, to = wl.random_edges(500, d, seed=21, max_len=0.3)
+    want_pf, want_nl = orc.belief_edge_pfree(frm, to, L, pts, vals, K=K, nthreads=orc.max_threads())
+    for ctx in ctxs:
+        pf, nl = ctx.belief_edge_pfree(frm, to)
+        np.testing.assert_array_equal(nl, want_nl)
+        np.testing.assert_array_equal(pf, want_pf)
+    # a cleared model forgets its index
+    ctxs[0].belief_clear()
+    ctxs[0].belief_append(pts[:700], vals[:700])
+    np.testing.assert_array_equal(ctxs[0].belief_estimate(q), orc.belief_estimate(pts[:700], vals[:700], q, K=K))
+    for ctx in ctxs:
         ctx.close()
 
 

@@ -55,7 +55,8 @@ def test_host_planner_fuzz_against_oracle_planner(mock_dir):
 
 
 def test_ompl_adapter_compiles_and_plans(tmp_path):
-    """batching_pomp_b200/host/ompl_adapter.hpp (the drop-in ompl::base::Planner) compiled against the OMPL API
+    """include/batching_pomp/BatchingPOMP.hpp (the drop-in batching_pomp::BatchingPOMP: both constructors, the public
+    members g / full_g / mBatchingPtr / mBeliefModel as views) compiled against the OMPL API
     stand-ins of tests/stubs and driven like an OMPL application: ParamSet by name, GraphML roadmap file,
     ProblemDefinition + GoalState, solve(ptc), anytime solutions through addSolutionPath, ompl::Exception on a
     bad parameter (tests/cpp/ompl_adapter_check.cpp).  Device side = the test double."""
