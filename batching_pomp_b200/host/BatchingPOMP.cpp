@@ -61,7 +61,12 @@ inline double now() {
 // short query.  A context is only reused for the same device, dimension, segment length and world.
 struct CtxPool {
   std::mutex mu;
-  std::map<std::string, std::vector<bpomp_ctx*>> idle;
+  struct Entry {
+    std::vector<double> boxLo, boxHi;  // the world the contexts of this key were created with: compared on
+    std::vector<uint8_t> image;        // every hit, so a hash collision can never hand out the wrong world
+    std::vector<bpomp_ctx*> ctxs;
+  };
+  std::map<std::string, Entry> idle;
   // idle contexts are deliberately not destroyed at process exit: the CUDA runtime may already be
   // unloading when static destructors run, and the driver reclaims the memory with the process
 };
@@ -153,15 +158,15 @@ bpomp_ctx* BatchingPOMP::dev() {
   {
     std::lock_guard<std::mutex> lk(pool().mu);
     auto it = pool().idle.find(mCtxKey);
-    if (it != pool().idle.end() && !it->second.empty()) {
-      mCtx = it->second.back();
-      it->second.pop_back();
+    if (it != pool().idle.end() && !it->second.ctxs.empty() && it->second.boxLo == si.boxLo &&
+        it->second.boxHi == si.boxHi && it->second.image == si.image) {
+      mCtx = it->second.ctxs.back();
+      it->second.ctxs.pop_back();
     }
   }
   if (mCtx) {  // recycled: same device / dim / L / world, emptied when it was returned
     mLaunchBase = bpomp_launch_count(mCtx);
     check(bpomp_belief_config(mCtx, mBeliefK, mBeliefPrior, mBeliefPriorWeight));
-    mSpace.reset();
     return mCtx;
   }
   int rc = bpomp_create(si.device, (int)mDim, mL, &mCtx);
@@ -183,7 +188,6 @@ bpomp_ctx* BatchingPOMP::dev() {
     mCtx = nullptr;
     throw;
   }
-  mSpace.reset();
   return mCtx;
 }
 
@@ -200,9 +204,15 @@ BatchingPOMP::~BatchingPOMP() {
   // hand the emptied context back for the next planner instance (at most 4 idle per configuration)
   if (bpomp_vertices_clear(mCtx) == BPOMP_OK && bpomp_belief_clear(mCtx) == BPOMP_OK && bpomp_sync(mCtx) == BPOMP_OK) {
     std::lock_guard<std::mutex> lk(pool().mu);
-    std::vector<bpomp_ctx*>& v = pool().idle[mCtxKey];
-    if (v.size() < 4) {
-      v.push_back(mCtx);
+    CtxPool::Entry& en = pool().idle[mCtxKey];
+    const bool same = mSpace && en.boxLo == mSpace->boxLo && en.boxHi == mSpace->boxHi && en.image == mSpace->image;
+    if (mSpace && en.ctxs.empty() && !same) {  // first context of this key (or a colliding key whose slots are free)
+      en.boxLo = mSpace->boxLo;
+      en.boxHi = mSpace->boxHi;
+      en.image = mSpace->image;
+    }
+    if (mSpace && (same || en.ctxs.empty()) && en.ctxs.size() < 4) {
+      en.ctxs.push_back(mCtx);
       return;
     }
   }

@@ -218,7 +218,7 @@ private:
   double mL, mMaxExtent, mSpaceMeasure;
   bpomp_ctx* mCtx;
   bpomp_ctx* dev();                         // acquires the context on first use; throws without CUDA
-  std::unique_ptr<SpaceInformation> mSpace; // world description, held until the context exists
+  std::unique_ptr<SpaceInformation> mSpace; // world description (upload, and the context pool compares it on reuse)
   std::string mCtxKey;  // device contexts are recycled between planner instances (BatchingPOMP.cpp, CtxPool)
 
   // ---- parameters ----

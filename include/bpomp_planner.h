@@ -71,7 +71,9 @@ BPOMP_PAPI uint64_t bpomp_planner_gpu_launches(const bpomp_planner* p);
 /* GraphML helpers (the roadmap boundary format, util/RoadmapFromFile.hpp). */
 BPOMP_PAPI int bpomp_graphml_write(const char* filename, int dim, const double* states, uint32_t n,
                                    const uint32_t* edges, uint32_t nedges);
-/* Two-call protocol: states == NULL returns the counts only. */
+/* Two-call protocol: states == NULL / edges == NULL returns the counts only.  With buffers, *n and *nedges hold
+ * their capacities (in nodes / edges) on entry and the file's counts on return; a buffer that is too small is an
+ * error and nothing is written to it. */
 BPOMP_PAPI int bpomp_graphml_read(const char* filename, int dim, double* states, uint32_t* n, uint32_t* edges,
                                   uint32_t* nedges);
 

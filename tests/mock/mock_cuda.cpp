@@ -34,6 +34,8 @@ void orc_neighbors_radius(const double* verts, const uint8_t* active, int64_t N,
                           int64_t nq, double r, uint64_t* row_ptr, uint32_t* col, double* dist, int nthreads);
 void orc_vertices_inadmissible(const double* states, int64_t count, int d, const double* start, const double* goal,
                                double best_cost, uint8_t* out);
+void orc_belief_estimate(const double* pts, const double* vals, int64_t M, int d, const double* queries, int64_t nq,
+                         int K, double prior, double prior_weight, double* out, int nthreads);
 void orc_belief_edge_pfree(const double* from, const double* to, int64_t count, int d, double L, const double* pts,
                            const double* vals, int64_t M, int K, double prior, double prior_weight, double* pfree,
                            uint32_t* nlookups, int nthreads);
@@ -266,6 +268,24 @@ BPOMP_API int bpomp_belief_clear(bpomp_ctx* c) {
   if (!c) return BPOMP_ERR_INVALID;
   c->bel_pts.clear();
   c->bel_vals.clear();
+  return BPOMP_OK;
+}
+BPOMP_API int bpomp_belief_append(bpomp_ctx* c, const double* states, const double* values, int64_t count) {
+  if (!c || count < 0 || (count > 0 && (!states || !values))) return BPOMP_ERR_INVALID;
+  c->bel_pts.insert(c->bel_pts.end(), states, states + (size_t)count * c->dim);
+  c->bel_vals.insert(c->bel_vals.end(), values, values + count);
+  return BPOMP_OK;
+}
+BPOMP_API int bpomp_belief_size(bpomp_ctx* c, uint64_t* count) {
+  if (!c || !count) return BPOMP_ERR_INVALID;
+  *count = c->bel_vals.size();
+  return BPOMP_OK;
+}
+BPOMP_API int bpomp_belief_estimate(bpomp_ctx* c, const double* queries, int64_t nq, double* out) {
+  if (!c || nq < 0 || (nq > 0 && (!queries || !out))) return BPOMP_ERR_INVALID;
+  c->launches++;
+  orc_belief_estimate(c->bel_pts.data(), c->bel_vals.data(), (int64_t)c->bel_vals.size(), c->dim, queries, nq, c->knn,
+                      c->prior, c->prior_weight, out, 1);
   return BPOMP_OK;
 }
 // checkAndSetEdgeBlocked's addPoint calls (BP.cpp:523-537), replayed from the first-invalid slot.
