@@ -383,7 +383,7 @@ void BatchingPOMP::setup() {
     // RoadmapFromFile::generateVertices (util/RoadmapFromFile.hpp:136-147)
     std::vector<double> states;
     std::vector<std::pair<uint32_t, uint32_t>> edges;
-    util::readGraphml(mRoadmapName, mDim, states, edges);
+    util::readGraphmlCached(mRoadmapName, mDim, states, edges);  // parsed once, then read from the binary cache
     mRoadmapOwned.swap(states);
     mRoadmap = mRoadmapOwned.data();
     mRoadmapEdges.swap(edges);

@@ -12,6 +12,8 @@
 #include <stdexcept>
 #include <unordered_map>
 
+#include <sys/stat.h>
+
 namespace batching_pomp {
 namespace util {
 
@@ -190,6 +192,90 @@ void readGraphml(const std::string& filename, unsigned int dim, std::vector<doub
       edges.emplace_back(a->second, b2->second);
     }
   }
+}
+
+namespace {
+struct CacheHeader {
+  char magic[8];          // "BPOMPRM1"
+  uint32_t dim;
+  uint32_t reserved;
+  uint64_t n, nedges;
+  uint64_t src_size;      // the GraphML file the cache was made from
+  int64_t src_mtime_ns;
+  uint64_t checksum;      // FNV-1a over the payload
+};
+uint64_t fnv1a(const void* data, size_t n, uint64_t h) {
+  const unsigned char* b = static_cast<const unsigned char*>(data);
+  for (size_t i = 0; i < n; ++i) {
+    h ^= b[i];
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+bool sourceStamp(const std::string& filename, uint64_t& size, int64_t& mtime_ns) {
+  struct stat st;
+  if (stat(filename.c_str(), &st) != 0) return false;
+  size = (uint64_t)st.st_size;
+  mtime_ns = (int64_t)st.st_mtim.tv_sec * 1000000000ll + (int64_t)st.st_mtim.tv_nsec;
+  return true;
+}
+}  // namespace
+
+bool readGraphmlCached(const std::string& filename, unsigned int dim, std::vector<double>& states,
+                       std::vector<std::pair<uint32_t, uint32_t>>& edges) {
+  const char* env = std::getenv("BPOMP_ROADMAP_CACHE");
+  const bool enabled = !(env && env[0] == '0');
+  const std::string cache = filename + ".bpomp-cache";
+  uint64_t size = 0;
+  int64_t mtime = 0;
+  const bool stamped = enabled && sourceStamp(filename, size, mtime);
+  if (stamped) {
+    if (FILE* f = std::fopen(cache.c_str(), "rb")) {
+      CacheHeader h;
+      bool ok = std::fread(&h, sizeof(h), 1, f) == 1 && std::memcmp(h.magic, "BPOMPRM1", 8) == 0 && h.dim == dim &&
+                h.src_size == size && h.src_mtime_ns == mtime && h.n < (1ull << 32) && h.nedges < (1ull << 32);
+      if (ok) {
+        std::vector<double> s((size_t)h.n * dim);
+        std::vector<std::pair<uint32_t, uint32_t>> e((size_t)h.nedges);
+        ok = (s.empty() || std::fread(s.data(), sizeof(double), s.size(), f) == s.size()) &&
+             (e.empty() || std::fread(e.data(), sizeof(e[0]), e.size(), f) == e.size());
+        if (ok) {
+          uint64_t c = fnv1a(s.data(), s.size() * sizeof(double), 1469598103934665603ull);
+          c = fnv1a(e.data(), e.size() * sizeof(e[0]), c);
+          ok = c == h.checksum;
+        }
+        if (ok) {
+          std::fclose(f);
+          states.swap(s);
+          edges.swap(e);
+          return true;
+        }
+      }
+      std::fclose(f);
+    }
+  }
+  readGraphml(filename, dim, states, edges);
+  if (stamped) {  // best effort: a read-only directory just means no cache
+    const std::string tmp = cache + ".tmp";
+    if (FILE* f = std::fopen(tmp.c_str(), "wb")) {
+      CacheHeader h;
+      std::memset(&h, 0, sizeof(h));
+      std::memcpy(h.magic, "BPOMPRM1", 8);
+      h.dim = dim;
+      h.n = states.size() / dim;
+      h.nedges = edges.size();
+      h.src_size = size;
+      h.src_mtime_ns = mtime;
+      h.checksum = fnv1a(states.data(), states.size() * sizeof(double), 1469598103934665603ull);
+      h.checksum = fnv1a(edges.data(), edges.size() * sizeof(edges[0]), h.checksum);
+      bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1 &&
+                (states.empty() || std::fwrite(states.data(), sizeof(double), states.size(), f) == states.size()) &&
+                (edges.empty() || std::fwrite(edges.data(), sizeof(edges[0]), edges.size(), f) == edges.size());
+      ok = (std::fclose(f) == 0) && ok;
+      if (!ok || std::rename(tmp.c_str(), cache.c_str()) != 0) std::remove(tmp.c_str());
+    }
+  }
+  return false;
 }
 
 void writeGraphml(const std::string& filename, unsigned int dim, const std::vector<double>& states,

@@ -197,3 +197,27 @@ extern "C" int bpomp_graphml_read(const char* filename, int dim, double* states,
       }
   });
 }
+
+extern "C" int bpomp_graphml_read_cached(const char* filename, int dim, double* states, uint32_t* n,
+                                         uint32_t* edges, uint32_t* nedges, int* from_cache) {
+  return guarded(nullptr, [&] {
+    std::vector<double> s;
+    std::vector<std::pair<uint32_t, uint32_t>> e;
+    const bool hit = batching_pomp::util::readGraphmlCached(filename, (unsigned)dim, s, e);
+    if (from_cache) *from_cache = hit ? 1 : 0;
+    // in: capacities of the caller's buffers (when given), out: the counts in the file
+    const uint32_t cap_n = n ? *n : 0, cap_e = nedges ? *nedges : 0;
+    if (n) *n = (uint32_t)(s.size() / dim);
+    if (nedges) *nedges = (uint32_t)e.size();
+    if (states && (!n || cap_n < s.size() / dim))
+      throw batching_pomp::core::Exception("bpomp_graphml_read_cached: the states buffer is too small for the file's nodes");
+    if (edges && (!nedges || cap_e < e.size()))
+      throw batching_pomp::core::Exception("bpomp_graphml_read_cached: the edges buffer is too small for the file's edges");
+    if (states) std::memcpy(states, s.data(), s.size() * sizeof(double));
+    if (edges)
+      for (size_t i = 0; i < e.size(); ++i) {
+        edges[2 * i] = e[i].first;
+        edges[2 * i + 1] = e[i].second;
+      }
+  });
+}

@@ -41,6 +41,8 @@ SIGNATURES = {
     "bpomp_planner_gpu_launches": (C.c_uint64, [vp]),
     "bpomp_graphml_write": (C.c_int, [C.c_char_p, C.c_int, vp, C.c_uint32, vp, C.c_uint32]),
     "bpomp_graphml_read": (C.c_int, [C.c_char_p, C.c_int, vp, C.POINTER(C.c_uint32), vp, C.POINTER(C.c_uint32)]),
+    "bpomp_graphml_read_cached": (C.c_int, [C.c_char_p, C.c_int, vp, C.POINTER(C.c_uint32), vp, C.POINTER(C.c_uint32),
+                                            C.POINTER(C.c_int)]),
 }
 
 STATUS = {0: "UNKNOWN", 1: "INVALID_START", 2: "INVALID_GOAL", 3: "UNRECOGNIZED_GOAL_TYPE", 4: "TIMEOUT",
@@ -225,3 +227,20 @@ def read_graphml(filename, dim):
     if rc != 0:
         raise PlannerError(rc, lib.bpomp_planner_error(None).decode())
     return s, e[:ne.value]
+
+
+def read_graphml_cached(filename, dim):
+    """read_graphml through the binary cache beside the file (the path the planner's setup() takes).
+    Returns (states, edges, from_cache)."""
+    lib = load()
+    n, ne, hit = C.c_uint32(0), C.c_uint32(0), C.c_int(0)
+    rc = lib.bpomp_graphml_read_cached(filename.encode(), dim, None, C.byref(n), None, C.byref(ne), C.byref(hit))
+    if rc != 0:
+        raise PlannerError(rc, lib.bpomp_planner_error(None).decode())
+    s = np.zeros((n.value, dim), dtype=np.float64)
+    e = np.zeros((max(ne.value, 1), 2), dtype=np.uint32)
+    ne.value = max(ne.value, 1)
+    rc = lib.bpomp_graphml_read_cached(filename.encode(), dim, _p(s), C.byref(n), _p(e), C.byref(ne), C.byref(hit))
+    if rc != 0:
+        raise PlannerError(rc, lib.bpomp_planner_error(None).decode())
+    return s, e[:ne.value], bool(hit.value)

@@ -76,6 +76,11 @@ BPOMP_PAPI int bpomp_graphml_write(const char* filename, int dim, const double* 
  * error and nothing is written to it. */
 BPOMP_PAPI int bpomp_graphml_read(const char* filename, int dim, double* states, uint32_t* n, uint32_t* edges,
                                   uint32_t* nedges);
+/* The same through the binary cache `<filename>.bpomp-cache` that the planner's setup() uses (host/graphml.hpp:
+ * keyed by the source file's size, modification time and dimension; rewritten when stale).  *from_cache = 1 when
+ * the roadmap was read from the cache instead of being parsed. */
+BPOMP_PAPI int bpomp_graphml_read_cached(const char* filename, int dim, double* states, uint32_t* n, uint32_t* edges,
+                                         uint32_t* nedges, int* from_cache);
 
 #ifdef __cplusplus
 }

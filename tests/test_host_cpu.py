@@ -56,6 +56,59 @@ def test_graphml_reads_networkx_files(planner_mod, tmp_path):
     assert e2.tolist() == [[3, 7], [7, 9]]
 
 
+def test_graphml_binary_cache(planner_mod, tmp_path, monkeypatch):
+    """f3: the binary roadmap cache beside the GraphML file (RoadmapFromFile.hpp:136-147 is a text parse every
+    time): first read parses and writes the cache, later reads come from it bit for bit; a changed source file,
+    a different dimension or a corrupted cache fall back to parsing; a read-only directory is not an error."""
+    import os
+    from batching_pomp_b200 import workloads
+    st = workloads.halton(3000, 7)
+    edges = np.array([[0, 1], [5, 2999]], dtype=np.uint32)
+    f = str(tmp_path / "r.graphml")
+    planner_mod.write_graphml(f, st, edges)
+    s1, e1, hit1 = planner_mod.read_graphml_cached(f, 7)   # two calls inside: counts (parse + write), then data (cache)
+    assert os.path.exists(f + ".bpomp-cache")
+    s2, e2, hit2 = planner_mod.read_graphml_cached(f, 7)
+    assert hit2
+    for s, e in ((s1, e1), (s2, e2)):
+        np.testing.assert_array_equal(s, st)
+        np.testing.assert_array_equal(e, edges)
+    # the planner's setup() takes the same path
+    p = planner_mod.Planner(7, boxes=(np.zeros((1, 7)), np.full((1, 7), 0.1)))
+    p.set_param("roadmap_filename", f)
+    p.set_param("batching_type", "vertex")
+    p.setup()
+    # stale: the source changes (other contents, other size / mtime) -> parsed again, cache rewritten
+    st2 = workloads.halton(2000, 7) * 0.5
+    planner_mod.write_graphml(f, st2)
+    os.utime(f, ns=(1, 1))
+    s3, e3, _ = planner_mod.read_graphml_cached(f, 7)
+    np.testing.assert_array_equal(s3, st2)
+    assert e3.shape[0] == 0
+    assert planner_mod.read_graphml_cached(f, 7)[2]
+    # corrupted payload: checksum mismatch -> parse
+    with open(f + ".bpomp-cache", "r+b") as c:
+        c.seek(200)
+        c.write(b"\xff\xff\xff\xff")
+    lib = planner_mod.load()
+    import ctypes as C
+    n, ne, hit = C.c_uint32(0), C.c_uint32(0), C.c_int(1)
+    assert lib.bpomp_graphml_read_cached(f.encode(), 7, None, C.byref(n), None, C.byref(ne), C.byref(hit)) == 0
+    assert hit.value == 0 and n.value == 2000
+    # disabled by the environment
+    monkeypatch.setenv("BPOMP_ROADMAP_CACHE", "0")
+    os.remove(f + ".bpomp-cache")
+    s4, _, hit4 = planner_mod.read_graphml_cached(f, 7)
+    assert not hit4 and not os.path.exists(f + ".bpomp-cache")
+    np.testing.assert_array_equal(s4, st2)
+    # too-small buffers are refused (capacities travel in *n / *nedges)
+    monkeypatch.delenv("BPOMP_ROADMAP_CACHE")
+    small = np.zeros((10, 7))
+    n = C.c_uint32(10)
+    assert lib.bpomp_graphml_read(f.encode(), 7, small.ctypes.data_as(C.c_void_p), C.byref(n), None, None) != 0
+    assert n.value == 2000 and not small.any()
+
+
 def test_graphml_errors(planner_mod, tmp_path):
     with pytest.raises(planner_mod.PlannerError):
         planner_mod.read_graphml(str(tmp_path / "missing.graphml"), 2)
