@@ -327,6 +327,181 @@ __global__ void __launch_bounds__(BK_QB) bk_knn_partial(const double* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------
+// The same partial top-k with the prefilter in FP32 (dimensions >= 4, where there is no spatial index and the
+// FP64 pipe was the limiter: 45 % active, profiles/r2_belief_summary.md).  The tile holds the points rounded to
+// float plus |p|^2/2 (computed in FP64, then rounded); a thread owns BKS_QT queries rounded to float, so a point
+// read from the tile (two 16-byte broadcasts at D = 7) serves BKS_QT fused-multiply-add chains on the FP32 pipe.
+//   a = |p|^2/2 - q.p  (FP32)   rejects the point iff   a > (thr - |q|^2)/2 + E
+// where E = 2^-20 (|q|^2 + max|p|^2) bounds the error of a: inputs rounded to float (2^-24 relative each),
+// D <= 8 roundings of the chain and the rounding of |p|^2/2 add up to less than 11 * 2^-24 (|q|^2 + |p|^2), so a
+// rejected point is beyond thr in exact arithmetic — and thr already pads the reference's own rounding.  The
+// survivors (about k ln(M/k) per query, plus the few inside the error band) are evaluated by the reference's
+// unfused FP64 arithmetic on the original coordinates, read from global memory.
+// ---------------------------------------------------------------------------
+#ifndef BKS_QT
+#define BKS_QT 4
+#endif
+__host__ __device__ constexpr int bks_ds(int D) { return (D + 4) & ~3; }  // floats per tile point: D coords + norm, x4
+
+template <int D>
+__device__ __forceinline__ void bks_consider(const double* __restrict__ q, const double* __restrict__ pt, uint32_t idx,
+                                             int K, double* kd, uint32_t* ki, int& cnt, double& worst, double& thr) {
+  constexpr int LS = BKS_QT * BK_QB;
+  double d2 = 0.0;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    double diff = __dsub_rn(__ldg(q + j), __ldg(pt + j));
+    d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
+  }
+  if (cnt == K && d2 > thr) return;
+  double dist = __dsqrt_rn(d2);
+  if (cnt == K && !(dist < worst)) return;  // an equidistant later point never displaces (GNAT)
+  int pos = cnt < K ? cnt : K - 1;
+  while (pos > 0 && kd[(pos - 1) * LS] > dist) {
+    kd[pos * LS] = kd[(pos - 1) * LS];
+    ki[pos * LS] = ki[(pos - 1) * LS];
+    --pos;
+  }
+  kd[pos * LS] = dist;
+  ki[pos * LS] = idx;
+  if (cnt < K) ++cnt;
+  if (cnt == K) {
+    worst = kd[(K - 1) * LS];
+    thr = __dmul_rn(__dmul_rn(worst, worst), 1.0 + 9.094947017729282e-13);  // conservative (2^-40)
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(BK_QB) bk_knn_partial_f32(const double* __restrict__ queries, int64_t nq_total,
+                                                            const double* __restrict__ pts, uint64_t M, uint64_t chunk,
+                                                            int K, double* __restrict__ part_d,
+                                                            uint32_t* __restrict__ part_i) {
+  constexpr int DS = bks_ds(D);
+  constexpr int LS = BKS_QT * BK_QB;
+  extern __shared__ __align__(16) unsigned char smem[];
+  float* s_pts = reinterpret_cast<float*>(smem);                                               // [BK_TILE][DS]
+  double* s_kd = reinterpret_cast<double*>(smem + (size_t)BK_TILE * DS * sizeof(float));       // [K][BKS_QT][BK_QB]
+  uint32_t* s_ki = reinterpret_cast<uint32_t*>(s_kd + (size_t)K * LS);
+  __shared__ unsigned long long s_pnmax;
+  const int tid = threadIdx.x;
+  const uint64_t p_begin = (uint64_t)blockIdx.y * chunk;
+  const uint64_t p_end = p_begin + chunk < M ? p_begin + chunk : M;
+  float nqf[BKS_QT][D];  // -query, rounded to float
+  double qn[BKS_QT];     // |q|^2
+  double worst[BKS_QT], thr[BKS_QT];
+  float thrp[BKS_QT];
+  int cnt[BKS_QT];
+  const double* qptr[BKS_QT];
+#pragma unroll
+  for (int s = 0; s < BKS_QT; ++s) {
+    int64_t qi = (int64_t)blockIdx.x * LS + s * BK_QB + tid;
+    if (qi >= nq_total) qi = 0;  // out-of-range slots scan as query 0 and are not written
+    qptr[s] = queries + qi * D;
+    qn[s] = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      const double v = qptr[s][j];
+      nqf[s][j] = -(float)v;
+      qn[s] = fma(v, v, qn[s]);
+    }
+    cnt[s] = 0;
+    worst[s] = DBL_MAX;
+    thr[s] = DBL_MAX;
+    thrp[s] = __int_as_float(0x7f800000);  // +inf: nothing is rejected while the list is filling
+  }
+  auto approx = [&](const float4* pp, int s) {
+    float v[DS];
+#pragma unroll
+    for (int h = 0; h < DS / 4; ++h) {
+      const float4 t = pp[h];
+      v[4 * h] = t.x; v[4 * h + 1] = t.y; v[4 * h + 2] = t.z; v[4 * h + 3] = t.w;
+    }
+    float acc = v[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) acc = fmaf(nqf[s][j], v[j], acc);
+    return acc;
+  };
+
+  for (uint64_t base = p_begin; base < p_end; base += BK_TILE) {
+    const uint32_t tn = (uint32_t)((p_end - base) < BK_TILE ? (p_end - base) : BK_TILE);
+    __syncthreads();
+    if (tid == 0) s_pnmax = 0ull;
+    __syncthreads();
+    for (uint32_t p = tid; p < tn; p += BK_QB) {
+      double pn = 0.0;
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        const double v = pts[(base + p) * D + j];
+        s_pts[p * DS + j] = (float)v;
+        pn = fma(v, v, pn);
+      }
+      s_pts[p * DS + D] = (float)(0.5 * pn);
+      atomicMax(&s_pnmax, (unsigned long long)__double_as_longlong(pn));  // NaN bits exceed +inf: stays NaN
+    }
+    __syncthreads();
+    const double pnmax = __longlong_as_double((long long)s_pnmax);
+    double pad[BKS_QT];
+#pragma unroll
+    for (int s = 0; s < BKS_QT; ++s) {
+      pad[s] = 9.5367431640625e-07 * (qn[s] + pnmax);  // 2^-20
+      thrp[s] = cnt[s] == K ? __double2float_ru(0.5 * (thr[s] - qn[s]) + pad[s]) : __int_as_float(0x7f800000);
+    }
+    uint32_t p = 0;
+    while (p < tn) {
+      if (!(p & (BK_G - 1u)) && p + BK_G <= tn) {
+        float acc[BK_G][BKS_QT];
+        bool far = true;
+#pragma unroll
+        for (int u = 0; u < BK_G; ++u) {
+          const float4* pp = reinterpret_cast<const float4*>(s_pts + (p + u) * DS);
+#pragma unroll
+          for (int s = 0; s < BKS_QT; ++s) {
+            acc[u][s] = approx(pp, s);
+            far = far && acc[u][s] > thrp[s];
+          }
+        }
+        if (!far) {
+#pragma unroll
+          for (int u = 0; u < BK_G; ++u) {
+#pragma unroll
+            for (int s = 0; s < BKS_QT; ++s) {
+              if (!(acc[u][s] > thrp[s])) {  // a stale (looser) bound after an insertion stays conservative
+                bks_consider<D>(qptr[s], pts + (base + p + u) * D, (uint32_t)(base + p + u), K, s_kd + s * BK_QB + tid,
+                                s_ki + s * BK_QB + tid, cnt[s], worst[s], thr[s]);
+                if (cnt[s] == K) thrp[s] = __double2float_ru(0.5 * (thr[s] - qn[s]) + pad[s]);
+              }
+            }
+          }
+        }
+        p += BK_G;
+      } else {
+        const float4* pp = reinterpret_cast<const float4*>(s_pts + p * DS);
+#pragma unroll
+        for (int s = 0; s < BKS_QT; ++s) {
+          if (!(approx(pp, s) > thrp[s])) {
+            bks_consider<D>(qptr[s], pts + (base + p) * D, (uint32_t)(base + p), K, s_kd + s * BK_QB + tid,
+                            s_ki + s * BK_QB + tid, cnt[s], worst[s], thr[s]);
+            if (cnt[s] == K) thrp[s] = __double2float_ru(0.5 * (thr[s] - qn[s]) + pad[s]);
+          }
+        }
+        ++p;
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < BKS_QT; ++s) {
+    const int64_t qi = (int64_t)blockIdx.x * LS + s * BK_QB + tid;
+    if (qi >= nq_total) continue;
+    double* od = part_d + ((size_t)blockIdx.y * nq_total + qi) * K;
+    uint32_t* oi = part_i + ((size_t)blockIdx.y * nq_total + qi) * K;
+    for (int k = 0; k < K; ++k) {
+      od[k] = k < cnt[s] ? s_kd[k * LS + s * BK_QB + tid] : DBL_MAX;
+      oi[k] = k < cnt[s] ? s_ki[k * LS + s * BK_QB + tid] : 0xFFFFFFFFu;
+    }
+  }
+}
+
 // Merge the P partial lists of each query and evaluate KNNModel::estimate (KNNModel.hpp:101-134).
 __global__ void __launch_bounds__(128) bk_merge_estimate(int64_t nq, int P, int K, uint64_t M,
                                                          const double* __restrict__ part_d,
@@ -636,7 +811,10 @@ static int knn_estimate_dev(bpomp_ctx* ctx, const double* d_queries, int64_t nq,
   int P = 1;
   uint64_t chunk = M ? M : 1;
   if (M > 0) {
-    int64_t qblocks = (nq + BK_QB * BK_QT - 1) / (BK_QB * BK_QT);
+    // dimensions >= 4: prefilter on the FP32 pipe, BKS_QT queries per thread; else the FP64 prefilter
+    const bool f32 = D >= 4 && ctx->belief_f32;
+    const int qt = f32 ? BKS_QT : BK_QT;
+    int64_t qblocks = (nq + BK_QB * qt - 1) / (BK_QB * qt);
     int64_t want = 2 * (int64_t)ctx->num_sms;
     while (qblocks * P < want && P < 64 && (M + (2 * P) - 1) / (2 * P) >= 1024) P *= 2;
     chunk = (M + P - 1) / P;
@@ -644,12 +822,20 @@ static int knn_estimate_dev(bpomp_ctx* ctx, const double* d_queries, int64_t nq,
     P = (int)((M + chunk - 1) / chunk);
     BP_TRY(bp_reserve(ctx, bd, (size_t)P * nq * K * sizeof(double), false));
     BP_TRY(bp_reserve(ctx, bi, (size_t)P * nq * K * sizeof(uint32_t), false));
-    size_t sm = (size_t)BK_TILE * bk_ds(D) * sizeof(double) + (size_t)K * BK_QT * BK_QB * (sizeof(double) + sizeof(uint32_t));
-    auto kern = bk_knn_partial<D>;
-    BP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     dim3 grid((unsigned)qblocks, (unsigned)P);
-    kern<<<grid, BK_QB, sm, ctx->stream>>>(d_queries, nq, ctx->d_bel_pts.as<double>(), M, chunk, K, bd.as<double>(),
-                                           bi.as<uint32_t>());
+    if (f32) {
+      size_t sm = (size_t)BK_TILE * bks_ds(D) * sizeof(float) + (size_t)K * BKS_QT * BK_QB * (sizeof(double) + sizeof(uint32_t));
+      auto kern = bk_knn_partial_f32<D>;
+      BP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      kern<<<grid, BK_QB, sm, ctx->stream>>>(d_queries, nq, ctx->d_bel_pts.as<double>(), M, chunk, K, bd.as<double>(),
+                                             bi.as<uint32_t>());
+    } else {
+      size_t sm = (size_t)BK_TILE * bk_ds(D) * sizeof(double) + (size_t)K * BK_QT * BK_QB * (sizeof(double) + sizeof(uint32_t));
+      auto kern = bk_knn_partial<D>;
+      BP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      kern<<<grid, BK_QB, sm, ctx->stream>>>(d_queries, nq, ctx->d_bel_pts.as<double>(), M, chunk, K, bd.as<double>(),
+                                             bi.as<uint32_t>());
+    }
     ctx->launches++;
     BP_CUDA(ctx, cudaGetLastError());
   }

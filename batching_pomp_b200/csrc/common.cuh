@@ -91,6 +91,19 @@ struct ImageWorldView {
   const unsigned long long* bits;  // [tiles_y][tiles_x] 8x8 tile, bit (r&7)*8+(c&7) = pixel >= threshold
 };
 
+// Neighbour grid over the first NB_MAXG dimensions of the active vertices (neighbors.cu).
+#define NB_MAXG 3
+struct GridView {
+  int gd;                      // gridded dimensions (<= NB_MAXG)
+  int G[NB_MAXG];              // cells per gridded dim
+  double lo[NB_MAXG], inv[NB_MAXG];
+  const uint32_t* cell_start;  // [ncells+1]
+  const uint32_t* ids;         // [nactive] vertex ids in cell order
+  const double* pts;           // SoA [D][nactive] in cell order
+  uint32_t nactive;
+  uint32_t ncells;
+};
+
 enum WorldKind { WORLD_NONE = 0, WORLD_BOXES = 1, WORLD_IMAGE = 2 };
 
 // ---------------------------------------------------------------------------
@@ -138,6 +151,7 @@ struct bpomp_ctx {
   DevBuf d_slow_list[4];                    // per pipeline lane: indices of the edges the fast kernel left over
   int fused_pfree = 1;                      // 0: never use the one-launch free-probability kernel (testing)
   int fast_mode = 1;                        // 0: never use the fast kernel (testing / tuning)
+  int reserve_sms = -1;                     // SMs the fast kernel leaves free (-1: 4 with a communicator, else 0)
   int fast_warps = 0;                       // > 0: cap on the warps per CTA of the fast kernel (tuning)
   int64_t fast_min_edges = 4096;            // smaller batches go to the general kernel alone (one launch)
 
@@ -152,7 +166,10 @@ struct bpomp_ctx {
   uint32_t nb_nq = 0;
   // neighbour grid
   DevBuf d_grid_cell_start, d_grid_ids, d_grid_pts, d_grid_keys;
-  bool grid_valid = false;
+  bool grid_valid = false;   // grid_view describes the current vertex table / active flags for radius grid_r
+  GridView grid_view{};
+  double grid_r = 0.0;
+  uint32_t nactive = 0;      // number of active vertices
 
   // belief model
   int knn = 15;
@@ -164,6 +181,7 @@ struct bpomp_ctx {
   uint64_t bg_count = 0;
   uint32_t bg_bits = 0;
   uint64_t bg_builds = 0;
+  int belief_f32 = 1;                       // 0: FP64 prefilter in the brute-force kNN for every dimension (testing)
   int belief_grid = 1;                      // 0: always scan the whole model (testing)
 
   // pipelined host-buffer edge checks (edge_check.cu)

@@ -309,7 +309,7 @@ extern "C" void bpomp_destroy(bpomp_ctx* ctx) {
 int bp_read_flags(bpomp_ctx* ctx) {
   BP_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (ctx->h_flags[0] || ctx->h_flags[1])
+  if (ctx->h_flags[0] || ctx->h_flags[1] || ctx->h_flags[2])
     BP_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), ctx->stream));
   return BPOMP_OK;
 }
@@ -347,7 +347,9 @@ extern "C" int bpomp_set_option(bpomp_ctx* ctx, const char* name, int64_t value)
   if (!strcmp(name, "fast_edge_kernel")) ctx->fast_mode = value ? 1 : 0;
   else if (!strcmp(name, "fast_edge_min_edges")) ctx->fast_min_edges = value < 0 ? 0 : value;
   else if (!strcmp(name, "fast_edge_warps")) ctx->fast_warps = (int)value;
+  else if (!strcmp(name, "reserve_sms")) ctx->reserve_sms = (int)value;
   else if (!strcmp(name, "fused_pfree")) ctx->fused_pfree = value ? 1 : 0;
+  else if (!strcmp(name, "belief_f32")) ctx->belief_f32 = value ? 1 : 0;
   else if (!strcmp(name, "belief_grid")) { ctx->belief_grid = value ? 1 : 0; ctx->bg_count = 0; }
   else return bp_fail(ctx, BPOMP_ERR_INVALID, "unknown option '%s'", name);
   return BPOMP_OK;
@@ -403,6 +405,7 @@ extern "C" int bpomp_vertices_append(bpomp_ctx* ctx, const double* states, uint3
   BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->h_active.resize(n1, 1);
   ctx->nverts = (uint32_t)n1;
+  ctx->nactive += count;
   ctx->grid_valid = false;
   return BPOMP_OK;
 }
@@ -414,7 +417,13 @@ extern "C" int bpomp_vertices_set_active(bpomp_ctx* ctx, const uint32_t* ids, ui
   if (!ids) return bp_fail(ctx, BPOMP_ERR_INVALID, "ids is NULL");
   for (uint32_t i = 0; i < count; ++i)
     if (ids[i] >= ctx->nverts) return bp_fail(ctx, BPOMP_ERR_RANGE, "vertex id %u out of range", ids[i]);
-  for (uint32_t i = 0; i < count; ++i) ctx->h_active[ids[i]] = flag ? 1 : 0;
+  for (uint32_t i = 0; i < count; ++i) {
+    const uint8_t nv = flag ? 1 : 0;
+    if (ctx->h_active[ids[i]] != nv) {
+      ctx->h_active[ids[i]] = nv;
+      if (nv) ++ctx->nactive; else --ctx->nactive;
+    }
+  }
   BP_CUDA(ctx, cudaMemcpyAsync(ctx->d_active.p, ctx->h_active.data(), ctx->nverts, cudaMemcpyHostToDevice,
                                ctx->stream));
   BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -433,6 +442,7 @@ extern "C" int bpomp_vertices_clear(bpomp_ctx* ctx) {
   if (!ctx) return BPOMP_ERR_INVALID;
   bp_enter(ctx);
   ctx->nverts = 0;
+  ctx->nactive = 0;
   ctx->h_active.clear();
   ctx->grid_valid = false;
   return BPOMP_OK;

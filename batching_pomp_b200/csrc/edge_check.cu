@@ -619,6 +619,31 @@ extern "C" int bpomp_edges_check_indexed_dev(bpomp_ctx* ctx, const uint32_t* d_f
 
 // After a pass: if some edges met a non-resident sample order, upload the missing rows and
 // re-run the kernel on exactly those edges.
+// Vertex ids of a host-buffer call are validated on the device, on the staged copies: an id beyond the vertex
+// table is replaced by 0 (so that the edge kernel never reads out of bounds) and counted in flags[2]; the call
+// then fails with BPOMP_ERR_RANGE.  (A host loop over the ids cost more than the H2D copy of a large batch.)
+__global__ void __launch_bounds__(256) ids_validate_kernel(uint32_t* __restrict__ a, uint32_t* __restrict__ b,
+                                                           int64_t count, uint32_t nverts, int* __restrict__ flags) {
+  bool bad = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    if (a[i] >= nverts) { a[i] = 0; bad = true; }
+    if (b[i] >= nverts) { b[i] = 0; bad = true; }
+  }
+  if (bad) atomicAdd(flags + 2, 1);
+}
+static int launch_ids_validate(bpomp_ctx* ctx, uint32_t* d_a, uint32_t* d_b, int64_t count, cudaStream_t s) {
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((count + 255) / 256, (int64_t)ctx->num_sms * 8));
+  ids_validate_kernel<<<grid, 256, 0, s>>>(d_a, d_b, count, ctx->nverts, ctx->d_flags);
+  ctx->launches++;
+  BP_CUDA(ctx, cudaGetLastError());
+  return BPOMP_OK;
+}
+static int ids_flag_result(bpomp_ctx* ctx) {  // after bp_read_flags
+  if (!ctx->h_flags[2]) return BPOMP_OK;
+  ctx->h_flags[2] = 0;
+  return bp_fail(ctx, BPOMP_ERR_RANGE, "an edge references a vertex id out of range");
+}
+
 static int resolve_deferred(bpomp_ctx* ctx, const double* d_from, const double* d_to, const uint32_t* d_fi,
                             const uint32_t* d_ti, int64_t count, uint8_t* d_valid, int32_t* d_first,
                             uint32_t* d_nstates) {
@@ -694,7 +719,9 @@ static int edges_check_pipelined(bpomp_ctx* ctx, const double* from, const doubl
     uint32_t* dn = reinterpret_cast<uint32_t*>(dv + (size_t)EC_PIPE_CHUNK * 5);
     ctx->stream = s;
     ctx->work_slot = 1 + l;
-    rc = bp_launch_edge_check(ctx, indexed ? nullptr : ctx->lane_a[l].as<double>(),
+    if (indexed) rc = launch_ids_validate(ctx, ctx->lane_a[l].as<uint32_t>(), ctx->lane_b[l].as<uint32_t>(), m, s);
+    if (rc == BPOMP_OK)
+      rc = bp_launch_edge_check(ctx, indexed ? nullptr : ctx->lane_a[l].as<double>(),
                               indexed ? nullptr : ctx->lane_b[l].as<double>(),
                               indexed ? ctx->lane_a[l].as<uint32_t>() : nullptr,
                               indexed ? ctx->lane_b[l].as<uint32_t>() : nullptr, m, dv, dfirst, dn, false);
@@ -718,6 +745,7 @@ static int edges_check_pipelined(bpomp_ctx* ctx, const double* from, const doubl
   cudaEventDestroy(ev);
   BP_TRY(rc);
   BP_TRY(bp_read_flags(ctx));
+  BP_TRY(ids_flag_result(ctx));
   if (ctx->h_flags[1]) {
     ctx->h_flags[1] = 0;
     ctx->h_flags[0] = 0;
@@ -732,11 +760,7 @@ static int edges_check_host(bpomp_ctx* ctx, const double* from, const double* to
   if (ctx->world == WORLD_NONE) return bp_fail(ctx, BPOMP_ERR_NO_WORLD, "no collision world set");
   if (count == 0) return BPOMP_OK;
   const bool indexed = fi != nullptr;
-  if (indexed) {
-    for (int64_t e = 0; e < count; ++e)
-      if (fi[e] >= ctx->nverts || ti[e] >= ctx->nverts)
-        return bp_fail(ctx, BPOMP_ERR_RANGE, "edge %lld references a vertex id out of range", (long long)e);
-  }
+  if (indexed && ctx->nverts == 0) return bp_fail(ctx, BPOMP_ERR_RANGE, "an edge references a vertex id out of range");
   if (count >= 2 * (int64_t)EC_PIPE_CHUNK) {
     int rc = edges_check_pipelined(ctx, from, to, fi, ti, count, valid, first, nstates);
     if (rc <= 0) return rc;
@@ -760,8 +784,13 @@ static int edges_check_host(bpomp_ctx* ctx, const double* from, const double* to
   uint8_t* dv = ctx->s_c.as<uint8_t>();
   int32_t* dfirst = ctx->s_d.as<int32_t>();
   uint32_t* dn = ctx->s_e.as<uint32_t>();
+  if (indexed) BP_TRY(launch_ids_validate(ctx, ctx->s_a.as<uint32_t>(), ctx->s_b.as<uint32_t>(), count, ctx->stream));
   BP_TRY(bp_launch_edge_check(ctx, df, dt, dfi, dti, count, dv, dfirst, dn, false));
-  BP_TRY(resolve_deferred(ctx, df, dt, dfi, dti, count, dv, dfirst, dn));
+  {
+    const int rc = resolve_deferred(ctx, df, dt, dfi, dti, count, dv, dfirst, dn);
+    BP_TRY(ids_flag_result(ctx));  // the flags were read by resolve_deferred
+    BP_TRY(rc);
+  }
   BP_CUDA(ctx, cudaMemcpyAsync(valid, dv, (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
   BP_CUDA(ctx, cudaMemcpyAsync(first, dfirst, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   if (nstates)

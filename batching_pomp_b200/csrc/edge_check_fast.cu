@@ -569,7 +569,10 @@ static int launch_fast(bpomp_ctx* ctx, FastArgs& a) {
   auto k = edge_check_fast_kernel<D, INDEXED>;
   BP_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ntiles = (a.count + 31) / 32;
-  const int grid = (int)std::min<int64_t>((ntiles + nwarps - 1) / nwarps, ctx->num_sms);
+  // With a communicator, a few SMs are left free: this kernel's CTAs take a whole SM each (shared memory), and
+  // NCCL's all-gather of the previous step's flags could otherwise only start when they exit.
+  const int sms = std::max(1, ctx->num_sms - (ctx->reserve_sms >= 0 ? ctx->reserve_sms : (ctx->comm ? 4 : 0)));
+  const int grid = (int)std::min<int64_t>((ntiles + nwarps - 1) / nwarps, sms);
   k<<<grid, nwarps * 32, smem, ctx->stream>>>(a, w);
   return 1;
 }

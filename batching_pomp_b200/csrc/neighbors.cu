@@ -16,21 +16,10 @@
 
 #include "common.cuh"
 
-#define NB_MAXG 3
 #ifndef NB_U
 #define NB_U(D) ((D) <= 3 ? 1 : 2)  // point groups in flight per lane
 #endif
 
-struct GridView {
-  int gd;                      // gridded dimensions (<= NB_MAXG)
-  int G[NB_MAXG];              // cells per gridded dim
-  double lo[NB_MAXG], inv[NB_MAXG];
-  const uint32_t* cell_start;  // [ncells+1]
-  const uint32_t* ids;         // [nactive] vertex ids in cell order
-  const double* pts;           // SoA [D][nactive] in cell order
-  uint32_t nactive;
-  uint32_t ncells;
-};
 
 __host__ __device__ __forceinline__ int nb_cell(double x, double lo, double inv, int G) {
 #ifdef __CUDA_ARCH__
@@ -662,6 +651,13 @@ static int neighbors_all_dense(bpomp_ctx* ctx, const GridView& g, double r, doub
 template <int D>
 static int build_grid(bpomp_ctx* ctx, double r, GridView& g) {
   const uint32_t n = ctx->nverts;
+  // The grid of the last call stands while the vertex table, the active flags and the radius (which sets the cell
+  // size) are unchanged: the planner asks for one row per expanded vertex when the whole CSR exceeds its budget,
+  // and must not pay a rebuild (bounding box, histogram, scan, scatter and a wait) per expansion.
+  if (ctx->grid_valid && ctx->grid_r == r) {
+    g = ctx->grid_view;
+    return BPOMP_OK;
+  }
   memset(&g, 0, sizeof(g));
   // bounding box of the active vertices over the gridded dims
   const int blocks = 64;
@@ -673,8 +669,7 @@ static int build_grid(bpomp_ctx* ctx, double r, GridView& g) {
   BP_CUDA(ctx, cudaMemcpyAsync(part.data(), ctx->d_nb_tmp.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost,
                                ctx->stream));
   BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  uint32_t nactive = 0;
-  for (uint32_t i = 0; i < n; ++i) nactive += ctx->h_active[i];
+  const uint32_t nactive = ctx->nactive;  // kept by the vertex-table calls (ctx.cu)
   g.gd = D < NB_MAXG ? D : NB_MAXG;
   // cell budget: ~2^21 cells in total, and never more cells than ~4x the points
   double budget = std::min(2097152.0, std::max(1.0, 4.0 * (double)nactive));
@@ -726,6 +721,9 @@ static int build_grid(bpomp_ctx* ctx, double r, GridView& g) {
   g.cell_start = ctx->d_grid_cell_start.as<uint32_t>();
   g.ids = ctx->d_grid_ids.as<uint32_t>();
   g.pts = ctx->d_grid_pts.as<double>();
+  ctx->grid_view = g;
+  ctx->grid_r = r;
+  ctx->grid_valid = true;
   return BPOMP_OK;
 }
 

@@ -61,21 +61,47 @@ def config_dict(edges, n_gpus, extra=None):
     return cfg
 
 
+MERGE_TEXT = ("bpomp_edges_check_sharded_dev: the status flags packed to 2 bits/edge and merged with one "
+              "ncclAllGather per step on the library's communicator stream, overlapped with the next step's "
+              "kernel (double-buffered results); first-invalid slots stay with the shard owner, which "
+              "replays the belief inserts")
+
+
+def full_config(edges_per_gpu, world, strong):
+    """The `config` object of both arms (the driver compares them key by key)."""
+    return config_dict(edges_per_gpu, world, {
+        "scaling_mode": ("strong: %d edges in total" % (edges_per_gpu * world)) if strong else "weak: %d edges per GPU" % edges_per_gpu,
+        "merge": MERGE_TEXT if world > 1 else "none (single GPU)"})
+
+
 # --------------------------------------------------------------------------------------------
 # CPU baseline (the oracle is test infrastructure; this and --impl reference are the only
 # places bench.py executes it)
 # --------------------------------------------------------------------------------------------
-def cpu_baseline_run(L, lo, hi, frm, to, target_s=12.0, steps=1, warmup=0):
+def cpu_baseline_run(L, lo, hi, frm, to, target_s=12.0, steps=1, warmup=0, prefer_reference=True, parity_edges=0):
+    """Times the CPU arm on all host cores on a bounded sample of the batch.  kind "reference": the reference's own
+    initializeEdgePoints + checkAndSetEdgeBlocked (src/BatchingPOMP.cpp:435-461, 496-544) compiled from
+    /root/reference into oracle/_ref (one planner instance per thread: the reference is single-threaded); kind
+    "port" (no oracle/_ref on this machine): the oracle's restatement with OpenMP over edges.  `parity_edges` > 0
+    additionally returns the oracle port's outputs for that many edges (the in-run parity gate; not timed)."""
     from oracle import oracle
     # all host cores this process may use; torchrun exports OMP_NUM_THREADS=1, which must not throttle the
-    # CPU arm, so the thread count is passed explicitly (OpenMP num_threads clause) instead of read from it
+    # CPU arm, so the thread count is passed explicitly instead of read from it
     try:
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
         cores = os.cpu_count() or 1
+    use_ref = prefer_reference and oracle.ref_edges_available()
+    frac = L / workloads.max_extent(DIM)
+
+    def run(f, t, threads):
+        if use_ref:
+            return oracle.ref_edges_check_boxes(f, t, frac, lo, hi, nthreads=threads)
+        return oracle.edges_check_boxes(f, t, L, lo, hi, nthreads=threads)
+
     probe = min(20000, frm.shape[0])
     t0 = time.perf_counter()
-    oracle.edges_check_boxes(frm[:probe], to[:probe], L, lo, hi, nthreads=cores)
+    run(frm[:probe], to[:probe], cores)
     dt = max(time.perf_counter() - t0, 1e-6)
     per_step = target_s / max(steps + warmup, 1)
     sample = int(min(frm.shape[0], max(probe, probe * per_step / dt)))
@@ -83,20 +109,28 @@ def cpu_baseline_run(L, lo, hi, frm, to, target_s=12.0, steps=1, warmup=0):
     outputs = None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        outputs = oracle.edges_check_boxes(frm[:sample], to[:sample], L, lo, hi, nthreads=cores)
+        outputs = run(frm[:sample], to[:sample], cores)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     total = sum(times)
     # single-thread figure on a smaller sample (the reference itself is single-threaded)
     s1 = max(1000, sample // (4 * cores))
     t0 = time.perf_counter()
-    oracle.edges_check_boxes(frm[:s1], to[:s1], L, lo, hi, nthreads=1)
+    run(frm[:s1], to[:s1], 1)
     v1 = s1 / max(time.perf_counter() - t0, 1e-9)
-    return {"value": sample * len(times) / total, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "first %d edges of the same batch, %d timed pass(es), OpenMP over edges; "
-                      "single-thread: %.4g edges/s" % (sample, len(times), v1),
-            "single_thread_value": v1, "ms_per_step": 1e3 * total / len(times),
-            "outputs": outputs, "sample_edges": sample}
+    res = {"value": sample * len(times) / total, "unit": UNIT, "cores": cores, "kind": "reference" if use_ref else "port",
+           "sample": "first %d edges of the same batch, %d timed pass(es), %s; single-thread: %.4g edges/s"
+                     % (sample, len(times),
+                        "the reference's own edge code (oracle/_ref), one planner instance per thread" if use_ref
+                        else "oracle port, OpenMP over edges", v1),
+           "single_thread_value": v1, "ms_per_step": 1e3 * total / len(times),
+           "outputs": outputs, "sample_edges": sample}
+    if parity_edges > 0:  # the oracle port on a larger share of the batch: checker only, not timed
+        m = int(min(frm.shape[0], parity_edges))
+        t0 = time.perf_counter()
+        res["port_outputs"] = oracle.edges_check_boxes(frm[:m], to[:m], L, lo, hi, nthreads=cores)
+        res["port_value"] = m / max(time.perf_counter() - t0, 1e-9)
+    return res
 
 
 def parity_check(tag, got, want):
@@ -120,15 +154,21 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    L, lo, hi, frm, to = make_workload(min(args.edges, 2_000_000))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    strong = args.scaling == "strong"
+    E = args.edges if not strong else (args.edges // world) // 16 * 16
+    L, lo, hi, frm, to = make_workload(min(E, 2_000_000))
     cb = cpu_baseline_run(L, lo, hi, frm, to, target_s=60.0, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(args.edges, args.gpus, {"note": "CPU oracle port of the reference loop (the reference "
-                                                      "needs OMPL/Boost/Eigen and cannot be built here); each step is "
-                                                      "a bounded sample of the batch"}),
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": full_config(E, world, strong),
+        "note": ("the reference's own edge evaluation (src/BatchingPOMP.cpp:435-461, 496-544, compiled from /root/reference "
+                 "against API stand-ins into oracle/_ref), one planner instance per host thread; each step is a bounded "
+                 "sample of the batch" if cb["kind"] == "reference" else
+                 "CPU oracle port of the reference loop (oracle/_ref is not present on this machine); each step is a "
+                 "bounded sample of the batch"),
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -418,6 +458,8 @@ def run_gpu(args):
         ids = [capi.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         ctx.comm_init_rank(world, rank, ids[0])
+        if args.reserve_sms >= 0:
+            ctx.set_option("reserve_sms", args.reserve_sms)
 
     # pinned host copies (e2e) and device-resident copies (value)
     h_from = torch.from_numpy(frm).pin_memory()
@@ -527,9 +569,9 @@ def run_gpu(args):
     # parity gate on every rank: the oracle outputs of the cpu_baseline sample (rank 0, N = 1) or of a short oracle
     # pass against what the device-resident step and the end-to-end call produced in this very run
     cores = len(os.sched_getaffinity(0))
-    cb = cpu_baseline_run(L, lo, hi, frm, to, target_s=12.0) if (not args.no_cpu and world == 1) else None
+    cb = cpu_baseline_run(L, lo, hi, frm, to, target_s=12.0, parity_edges=7_000_000) if (not args.no_cpu and world == 1) else None
     if cb:
-        want = cb["outputs"]
+        want = cb["port_outputs"]
     else:
         from oracle import oracle
         m = min(E, 200000)
@@ -537,6 +579,10 @@ def run_gpu(args):
     ns_dev = d_ns.cpu().numpy().view(np.uint32)
     checked = parity_check("device-resident step", (d_valid[last].cpu().numpy(), d_first[last].cpu().numpy(), ns_dev), want)
     parity_check("end-to-end call", (v_np, fi_np, ns_dev), want)
+    ref_checked = 0
+    if cb and cb["kind"] == "reference":  # and against the reference's own code on its timed sample
+        ref_checked = parity_check("device-resident step vs the reference's own code",
+                                   (d_valid[last].cpu().numpy(), d_first[last].cpu().numpy(), ns_dev), cb["outputs"])
 
     if rank == 0:
         peak, peak_src = peak_hbm()
@@ -561,12 +607,7 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(E, world, {
-                "scaling_mode": ("strong: %d edges in total" % (E * world)) if strong else "weak: %d edges per GPU" % E,
-                "merge": ("bpomp_edges_check_sharded_dev: the status flags packed to 2 bits/edge and merged with one "
-                          "ncclAllGather per step on the library's communicator stream, overlapped with the next step's "
-                          "kernel (double-buffered results); first-invalid slots stay with the shard owner, which "
-                          "replays the belief inserts") if world > 1 else "none (single GPU)"}),
+            "config": full_config(E, world, strong),
             "kernel_ms_per_step": kern_ms_per_step,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
@@ -587,10 +628,14 @@ def run_gpu(args):
             "blocked_fraction": float((fi_np >= 1).mean()),
             "parity_checked_edges": int(checked),
             "parity": "valid, first_invalid_slot and nstates of the first %d edges bit-equal to the CPU oracle, "
-                      "device-resident step and end-to-end call, checked in this run before printing" % checked,
+                      "device-resident step and end-to-end call%s, checked in this run before printing"
+                      % (checked, (", and of the first %d edges bit-equal to the reference's own edge code (oracle/_ref)"
+                                   % ref_checked) if ref_checked else ""),
+            "parity_checked_edges_reference": int(ref_checked),
         }
         if cb:
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["oracle_port_value"] = cb.get("port_value")
         if world == 1 and not args.no_extras:
             from oracle import oracle
             extras = {}
@@ -614,6 +659,8 @@ def main():
     ap.add_argument("--edges", type=int, default=10 ** 7)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --edges per GPU (default); strong: --edges in total")
+    ap.add_argument("--reserve-sms", type=int, default=-1,
+                    help="SMs the edge kernel leaves free for NCCL when N > 1 (-1: library default, 4)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra legs (indexed / image edges, planner times)")
     args = ap.parse_args()

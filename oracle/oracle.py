@@ -500,6 +500,28 @@ def ref_knn_estimate(pts, vals, queries, K=15, prior=0.5, prior_weight=0.25):
     return out
 
 
+def ref_edges_available():
+    return ref_available() and hasattr(_reflib(), "ref_edges_check_boxes")
+
+
+def ref_edges_check_boxes(frm, to, fraction, lo, hi, nthreads=1):
+    """The reference's own initializeEdgePoints + checkAndSetEdgeBlocked (src/BatchingPOMP.cpp:435-461, 496-544) on
+    arbitrary edges of the unit hypercube against a box world: (valid, first_invalid_slot, nstates).  `fraction` is
+    the state space's longestValidSegmentFraction (the planner derives L = maxExtent * fraction itself)."""
+    frm, to, lo, hi = _f64(frm), _f64(to), _f64(lo), _f64(hi)
+    n, d = frm.shape
+    valid = np.empty(n, dtype=np.uint8)
+    first = np.empty(n, dtype=np.int32)
+    ns = np.empty(n, dtype=np.uint32)
+    rc = _reflib().ref_edges_check_boxes(C.c_int(d), C.c_double(fraction), _p(lo, c_dp), _p(hi, c_dp),
+                                         C.c_int(lo.shape[0]), _p(frm, c_dp), _p(to, c_dp), C.c_int64(n),
+                                         valid.ctypes.data_as(C.c_void_p), first.ctypes.data_as(C.c_void_p),
+                                         ns.ctypes.data_as(C.c_void_p), C.c_int(nthreads))
+    if rc != 0:
+        raise RuntimeError("ref_edges_check_boxes failed")
+    return valid, first, ns
+
+
 def ref_selector(sel_type, prob_free):
     """util::Selector<Graph>::selectEdges of the reference: evaluation order of a path's edges (positions)."""
     p = _f64(prob_free)

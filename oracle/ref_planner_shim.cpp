@@ -17,6 +17,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "batching_pomp/BatchingPOMP.hpp"
@@ -179,6 +180,73 @@ REF_API uint64_t refp_solution_count(void* h) {
   RefPlanner* r = (RefPlanner*)h;
   return r->pdef ? r->pdef->getSolutionCount() : 0;
 }
+
+// ---- BatchingPOMP::initializeEdgePoints + checkAndSetEdgeBlocked (src/BatchingPOMP.cpp:435-461, 496-544) ----
+// The reference's own edge evaluation on arbitrary edges: every edge gets two vertices and an edge record in the
+// planner's public graph `g`, its states are materialised by initializeEdgePoints and marched by
+// checkAndSetEdgeBlocked (belief inserts included), exactly as the planner does for a candidate-path edge.
+// first_invalid is recovered from the planner's own isValid counter (getNumCollChecks).  The reference is
+// single-threaded; `nthreads` independent planner instances each take a contiguous slice of the edges (a fresh
+// instance every 2048 edges, so the affected-edge set and the belief model stay as small as in a short query).
+// Used to pin the oracle's edge operator to the reference and as bench.py's reference arm.
+namespace {
+void ref_edges_slice(int d, double fraction, const double* blo, const double* bhi, int nb, const double* from,
+                     const double* to, int64_t begin, int64_t end, uint8_t* valid, int32_t* first, uint32_t* nstates) {
+  typedef batching_pomp::BatchingPOMP BP;
+  for (int64_t c0 = begin; c0 < end; c0 += 2048) {
+    const int64_t c1 = c0 + 2048 < end ? c0 + 2048 : end;
+    auto space = std::make_shared<ob::RealVectorStateSpace>((unsigned)d);
+    space->setBounds(0.0, 1.0);
+    ob::SpaceInformationPtr si = std::make_shared<ob::SpaceInformation>(space);
+    si->setStateValidityCheckingResolution(fraction);
+    auto checker = std::make_shared<WorldChecker>(si, d);
+    checker->kind = 1;
+    checker->nb = nb;
+    checker->lo.assign(blo, blo + (size_t)nb * d);
+    checker->hi.assign(bhi, bhi + (size_t)nb * d);
+    si->setStateValidityChecker(checker);
+    si->setup();
+    BP planner(si);
+    for (int64_t e = c0; e < c1; ++e) {
+      BP::Vertex uv[2];
+      for (int k = 0; k < 2; ++k) {
+        uv[k] = boost::add_vertex(planner.g);
+        batching_pomp::StateConPtr st = std::make_shared<batching_pomp::StateCon>(space);
+        double* v = st->state->as<ob::RealVectorStateSpace::StateType>()->values;
+        const double* src = (k == 0 ? from : to) + (size_t)e * d;
+        for (int j = 0; j < d; ++j) v[j] = src[j];
+        planner.g[uv[k]].v_state = st;
+      }
+      std::pair<BP::Edge, bool> ne = boost::add_edge(uv[0], uv[1], planner.g);
+      planner.g[ne.first].distance = planner.vertexDistFun(uv[0], uv[1]);  // BP.cpp:162-166
+      planner.g[ne.first].blockedStatus = BP::UNKNOWN;
+      planner.initializeEdgePoints(ne.first);
+      const unsigned int before = planner.getNumCollChecks();
+      const bool blocked = planner.checkAndSetEdgeBlocked(ne.first);
+      valid[e] = blocked ? 0 : 1;
+      first[e] = blocked ? (int32_t)(planner.getNumCollChecks() - before) : -1;
+      nstates[e] = (uint32_t)planner.g[ne.first].edgeStates.size();
+    }
+  }
+}
+}  // namespace
+REF_API int ref_edges_check_boxes(int d, double fraction, const double* blo, const double* bhi, int nb, const double* from,
+                                  const double* to, int64_t count, uint8_t* valid, int32_t* first, uint32_t* nstates,
+                                  int nthreads) {
+  try {
+    if (nthreads < 1) nthreads = 1;
+    std::vector<std::thread> ts;
+    for (int t = 0; t < nthreads; ++t) {
+      const int64_t b = count * t / nthreads, e = count * (t + 1) / nthreads;
+      if (e > b) ts.emplace_back(ref_edges_slice, d, fraction, blo, bhi, nb, from, to, b, e, valid, first, nstates);
+    }
+    for (auto& t : ts) t.join();
+    return 0;
+  } catch (...) {
+    return -1;
+  }
+}
+
 
 // ---- cspacebelief::KNNModel (KNNModel.hpp:56-134) with the planner's distance function
 // (beliefDistanceFunction, src/BatchingPOMP.cpp:213-219: the Eigen norm of the difference) ------------------

@@ -406,6 +406,35 @@ def test_belief_edge_pfree_one_launch_path(capi, orc, wl, d, K, M, L):
         ctx.close()
 
 
+def test_indexed_edges_reject_bad_vertex_ids(capi, orc, wl):
+    """Vertex ids of a host-buffer call are validated on the device (no host loop over the ids): one bad id fails
+    the call with BPOMP_ERR_RANGE — small batch and pipelined batch — and the context stays usable."""
+    d, N = 7, 1000
+    ctx, L, lo, hi = _ctx_boxes(capi, wl, d, 500, seed=3)
+    verts = wl.halton(N, d)
+    ctx.vertices_append(verts)
+    rng = np.random.default_rng(3)
+    for E in (5000, (1 << 21) + 12345):
+        fi = rng.integers(0, N, E).astype(np.uint32)
+        ti = rng.integers(0, N, E).astype(np.uint32)
+        good = ctx.edges_check_indexed(fi, ti)
+        for arr, pos in ((fi, E // 2), (ti, E - 1)):
+            keep = arr[pos]
+            arr[pos] = N  # first id beyond the table
+            with pytest.raises(capi.BpompError) as ei:
+                ctx.edges_check_indexed(fi, ti)
+            assert "out of range" in str(ei.value)
+            arr[pos] = keep
+        again = ctx.edges_check_indexed(fi, ti)
+        for a, b in zip(good, again):
+            np.testing.assert_array_equal(a, b)
+    m = 20000
+    ov, of, on = orc.edges_check_boxes(verts[fi[:m]], verts[ti[:m]], L, lo, hi, nthreads=orc.max_threads())
+    np.testing.assert_array_equal(again[0][:m], ov)
+    np.testing.assert_array_equal(again[1][:m], of)
+    ctx.close()
+
+
 def _clustered_points(wl, d, M, seed):
     """Belief-like point sets: states strung along segments (checked edges), plus duplicates and a far outlier."""
     rng = np.random.default_rng(seed)

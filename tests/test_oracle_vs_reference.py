@@ -206,3 +206,47 @@ def test_gpu_belief_estimates_match_reference_knn_model():
         ctx.belief_append(pts, vals)
         np.testing.assert_allclose(ctx.belief_estimate(q), want, rtol=1e-12, atol=0)
         ctx.close()
+
+
+@pytest.mark.parametrize("d,nb,fraction,max_len", [(7, 500, 0.01, None), (2, 40, 0.002, 0.4), (3, 200, 0.01, 1.2)])
+def test_oracle_edge_operator_equals_reference_code(orc, d, nb, fraction, max_len):
+    """initializeEdgePoints + checkAndSetEdgeBlocked of the reference itself (src/BatchingPOMP.cpp:435-461, 496-544,
+    driven on arbitrary edges through oracle/ref_planner_shim.cpp: ref_edges_check_boxes) against the oracle's edge
+    operator: validity, first invalid slot and nStates bit for bit — short edges (2 states), long edges (hundreds
+    of states), zero-length edges, both orientations."""
+    if not orc.ref_edges_available():
+        pytest.skip("oracle/_ref/libbpomp_ref.so with ref_edges_check_boxes is not built here")
+    from batching_pomp_b200 import workloads as wl
+    L = wl.segment_length(d, fraction)
+    lo, hi = wl.box_world(d, nb, seed=3)
+    frm, to = wl.random_edges(30000, d, seed=4, max_len=max_len or wl.halton_radius(10 ** 6, d))
+    frm[:10] = to[:10]                       # zero length
+    frm[10:5000], to[10:5000] = to[10:5000].copy(), frm[10:5000].copy()  # other orientation
+    rv, rf, rn = orc.ref_edges_check_boxes(frm, to, fraction, lo, hi, nthreads=orc.max_threads())
+    ov, of, on = orc.edges_check_boxes(frm, to, L, lo, hi, nthreads=orc.max_threads())
+    np.testing.assert_array_equal(on, rn)
+    np.testing.assert_array_equal(ov, rv)
+    np.testing.assert_array_equal(of, rf)
+    assert 0.02 < (rv == 0).mean() < 0.98 and rn.max() > (20 if max_len else 8)
+
+
+@pytest.mark.gpu
+def test_gpu_edge_operator_equals_reference_code(orc):
+    """The CUDA edge kernels against the reference's own edge code (not the oracle): config-4 style edges."""
+    if not orc.ref_edges_available():
+        pytest.skip("oracle/_ref/libbpomp_ref.so with ref_edges_check_boxes is not built here")
+    from batching_pomp_b200 import capi, workloads as wl
+    d = 7
+    L = wl.segment_length(d)
+    lo, hi = wl.box_world(d, 500, seed=3)
+    frm, to = wl.random_edges(120000, d, seed=9, max_len=wl.halton_radius(10 ** 6, d))
+    frm[:2000], to[:2000] = wl.random_edges(2000, d, seed=10, max_len=2.0)  # long edges: the general kernel's share
+    ctx = capi.Context(d, L)
+    ctx.set_bounds(0.0, 1.0)
+    ctx.set_world_boxes(lo, hi)
+    gv, gf, gn = ctx.edges_check(frm, to)
+    rv, rf, rn = orc.ref_edges_check_boxes(frm, to, 0.01, lo, hi, nthreads=orc.max_threads())
+    np.testing.assert_array_equal(gn, rn)
+    np.testing.assert_array_equal(gv, rv)
+    np.testing.assert_array_equal(gf, rf)
+    ctx.close()
