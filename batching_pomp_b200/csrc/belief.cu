@@ -328,30 +328,41 @@ __global__ void __launch_bounds__(BK_QB) bk_knn_partial(const double* __restrict
 }
 
 // ---------------------------------------------------------------------------
-// The same partial top-k with the prefilter in FP32 (dimensions >= 4, where there is no spatial index and the
-// FP64 pipe was the limiter: 45 % active, profiles/r2_belief_summary.md).  The tile holds the points rounded to
-// float plus |p|^2/2 (computed in FP64, then rounded); a thread owns BKS_QT queries rounded to float, so a point
-// read from the tile (two 16-byte broadcasts at D = 7) serves BKS_QT fused-multiply-add chains on the FP32 pipe.
-//   a = |p|^2/2 - q.p  (FP32)   rejects the point iff   a > (thr - |q|^2)/2 + E
-// where E = 2^-20 (|q|^2 + max|p|^2) bounds the error of a: inputs rounded to float (2^-24 relative each),
-// D <= 8 roundings of the chain and the rounding of |p|^2/2 add up to less than 11 * 2^-24 (|q|^2 + |p|^2), so a
-// rejected point is beyond thr in exact arithmetic — and thr already pads the reference's own rounding.  The
-// survivors (about k ln(M/k) per query, plus the few inside the error band) are evaluated by the reference's
-// unfused FP64 arithmetic on the original coordinates, read from global memory.
+// The same partial top-k for dimensions >= 4 (no spatial index there), restructured around the two things the
+// FP64 version above was bound by (profiles/r2_belief_summary.md: FP64 pipe 45 % active at 16 % warps active, and
+// list insertions running with one or two active lanes):
+//  * the prefilter runs on the FP32 pipe.  The tile holds the points rounded to float plus |p|^2/2 (computed in
+//    FP64, then rounded); a thread owns BKS_QT queries rounded to float, so a point read from the tile (two
+//    16-byte broadcasts at D = 7) serves BKS_QT fused-multiply-add chains.
+//        a = |p|^2/2 - q.p  (FP32)   rejects the point iff   a > (thr - |q|^2)/2 + E,
+//    E = 2^-20 (|q|^2 + max|p|^2): the error of a — inputs rounded to float (2^-24 relative each), D <= 8
+//    roundings of the chain, the rounding of |p|^2/2 — is below 11 * 2^-24 (|q|^2 + |p|^2), so a rejected point
+//    is beyond thr in exact arithmetic (and thr already pads the reference's own rounding);
+//  * survivors are not inserted on the spot: a thread pushes them (tile position, query slot) to its own small
+//    queue in shared memory, and the queues are drained together — at the end of a tile, or when one is about to
+//    overflow — so that the exact evaluation (the reference's unfused FP64 arithmetic on the original coordinates,
+//    kept beside the float tile) and the ordered insertion run with most lanes of a warp busy.  A queue is
+//    drained in push order, i.e. ascending insertion index per list, which the tie rule relies on.
 // ---------------------------------------------------------------------------
 #ifndef BKS_QT
 #define BKS_QT 4
 #endif
+#define BKS_TILE 128
+#define BKS_QCAP 8
 __host__ __device__ constexpr int bks_ds(int D) { return (D + 4) & ~3; }  // floats per tile point: D coords + norm, x4
+__host__ __device__ constexpr size_t bks_smem(int D, int K) {
+  return (size_t)BKS_TILE * bks_ds(D) * sizeof(float) + (size_t)BKS_TILE * D * sizeof(double) +
+         (size_t)K * BKS_QT * BK_QB * (sizeof(double) + sizeof(uint32_t)) + (size_t)BKS_QCAP * BK_QB * sizeof(uint16_t);
+}
 
 template <int D>
-__device__ __forceinline__ void bks_consider(const double* __restrict__ q, const double* __restrict__ pt, uint32_t idx,
-                                             int K, double* kd, uint32_t* ki, int& cnt, double& worst, double& thr) {
+__device__ __forceinline__ void bks_consider(const double* __restrict__ q, const double* pt, uint32_t idx, int K,
+                                             double* kd, uint32_t* ki, int& cnt, double& worst, double& thr) {
   constexpr int LS = BKS_QT * BK_QB;
   double d2 = 0.0;
 #pragma unroll
   for (int j = 0; j < D; ++j) {
-    double diff = __dsub_rn(__ldg(q + j), __ldg(pt + j));
+    double diff = __dsub_rn(__ldg(q + j), pt[j]);
     d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
   }
   if (cnt == K && d2 > thr) return;
@@ -380,16 +391,18 @@ __global__ void __launch_bounds__(BK_QB) bk_knn_partial_f32(const double* __rest
   constexpr int DS = bks_ds(D);
   constexpr int LS = BKS_QT * BK_QB;
   extern __shared__ __align__(16) unsigned char smem[];
-  float* s_pts = reinterpret_cast<float*>(smem);                                               // [BK_TILE][DS]
-  double* s_kd = reinterpret_cast<double*>(smem + (size_t)BK_TILE * DS * sizeof(float));       // [K][BKS_QT][BK_QB]
+  float* s_pts = reinterpret_cast<float*>(smem);                                                  // [BKS_TILE][DS]
+  double* s_ptd = reinterpret_cast<double*>(smem + (size_t)BKS_TILE * DS * sizeof(float));        // [BKS_TILE][D]
+  double* s_kd = s_ptd + (size_t)BKS_TILE * D;                                                    // [K][BKS_QT][BK_QB]
   uint32_t* s_ki = reinterpret_cast<uint32_t*>(s_kd + (size_t)K * LS);
+  uint16_t* s_q = reinterpret_cast<uint16_t*>(s_ki + (size_t)K * LS) + threadIdx.x;               // [BKS_QCAP][BK_QB]
   __shared__ unsigned long long s_pnmax;
   const int tid = threadIdx.x;
   const uint64_t p_begin = (uint64_t)blockIdx.y * chunk;
   const uint64_t p_end = p_begin + chunk < M ? p_begin + chunk : M;
   float nqf[BKS_QT][D];  // -query, rounded to float
   double qn[BKS_QT];     // |q|^2
-  double worst[BKS_QT], thr[BKS_QT];
+  double worst[BKS_QT], thr[BKS_QT], pad[BKS_QT];
   float thrp[BKS_QT];
   int cnt[BKS_QT];
   const double* qptr[BKS_QT];
@@ -408,24 +421,36 @@ __global__ void __launch_bounds__(BK_QB) bk_knn_partial_f32(const double* __rest
     cnt[s] = 0;
     worst[s] = DBL_MAX;
     thr[s] = DBL_MAX;
+    pad[s] = 0.0;
     thrp[s] = __int_as_float(0x7f800000);  // +inf: nothing is rejected while the list is filling
   }
-  auto approx = [&](const float4* pp, int s) {
-    float v[DS];
+  int qlen = 0;
+  uint64_t base = p_begin;  // first point of the current tile (the drain needs it)
+
+  auto drain = [&]() {  // every lane empties its queue, oldest entry first
+    int i = 0;
+    while (__any_sync(0xffffffffu, i < qlen)) {
+      if (i < qlen) {
+        const uint32_t code = s_q[i * BK_QB];
+        const uint32_t p = code & 0xfffu;
+        const int s = (int)(code >> 12);
 #pragma unroll
-    for (int h = 0; h < DS / 4; ++h) {
-      const float4 t = pp[h];
-      v[4 * h] = t.x; v[4 * h + 1] = t.y; v[4 * h + 2] = t.z; v[4 * h + 3] = t.w;
+        for (int t = 0; t < BKS_QT; ++t)
+          if (t == s)
+            bks_consider<D>(qptr[t], s_ptd + p * D, (uint32_t)(base + p), K, s_kd + t * BK_QB + tid,
+                            s_ki + t * BK_QB + tid, cnt[t], worst[t], thr[t]);
+      }
+      ++i;
     }
-    float acc = v[D];
+    qlen = 0;
 #pragma unroll
-    for (int j = 0; j < D; ++j) acc = fmaf(nqf[s][j], v[j], acc);
-    return acc;
+    for (int s = 0; s < BKS_QT; ++s)
+      thrp[s] = cnt[s] == K ? __double2float_ru(0.5 * (thr[s] - qn[s]) + pad[s]) : __int_as_float(0x7f800000);
   };
 
-  for (uint64_t base = p_begin; base < p_end; base += BK_TILE) {
-    const uint32_t tn = (uint32_t)((p_end - base) < BK_TILE ? (p_end - base) : BK_TILE);
-    __syncthreads();
+  for (; base < p_end; base += BKS_TILE) {
+    const uint32_t tn = (uint32_t)((p_end - base) < BKS_TILE ? (p_end - base) : BKS_TILE);
+    __syncthreads();  // every thread has drained the previous tile
     if (tid == 0) s_pnmax = 0ull;
     __syncthreads();
     for (uint32_t p = tid; p < tn; p += BK_QB) {
@@ -433,6 +458,7 @@ __global__ void __launch_bounds__(BK_QB) bk_knn_partial_f32(const double* __rest
 #pragma unroll
       for (int j = 0; j < D; ++j) {
         const double v = pts[(base + p) * D + j];
+        s_ptd[p * D + j] = v;
         s_pts[p * DS + j] = (float)v;
         pn = fma(v, v, pn);
       }
@@ -441,53 +467,61 @@ __global__ void __launch_bounds__(BK_QB) bk_knn_partial_f32(const double* __rest
     }
     __syncthreads();
     const double pnmax = __longlong_as_double((long long)s_pnmax);
-    double pad[BKS_QT];
 #pragma unroll
     for (int s = 0; s < BKS_QT; ++s) {
       pad[s] = 9.5367431640625e-07 * (qn[s] + pnmax);  // 2^-20
       thrp[s] = cnt[s] == K ? __double2float_ru(0.5 * (thr[s] - qn[s]) + pad[s]) : __int_as_float(0x7f800000);
     }
-    uint32_t p = 0;
-    while (p < tn) {
-      if (!(p & (BK_G - 1u)) && p + BK_G <= tn) {
-        float acc[BK_G][BKS_QT];
-        bool far = true;
+    for (uint32_t p = 0; p < tn; p += BK_G) {
+      // hit mask of this group: bit u*BKS_QT+s = point p+u survives the prefilter of query s
+      uint32_t hits = 0;
 #pragma unroll
-        for (int u = 0; u < BK_G; ++u) {
+      for (int u = 0; u < BK_G; ++u) {
+        if (p + u < tn) {
           const float4* pp = reinterpret_cast<const float4*>(s_pts + (p + u) * DS);
+          float v[DS];
+#pragma unroll
+          for (int h = 0; h < DS / 4; ++h) {
+            const float4 t = pp[h];
+            v[4 * h] = t.x; v[4 * h + 1] = t.y; v[4 * h + 2] = t.z; v[4 * h + 3] = t.w;
+          }
 #pragma unroll
           for (int s = 0; s < BKS_QT; ++s) {
-            acc[u][s] = approx(pp, s);
-            far = far && acc[u][s] > thrp[s];
+            float acc = v[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) acc = fmaf(nqf[s][j], v[j], acc);
+            if (!(acc > thrp[s])) hits |= 1u << (u * BKS_QT + s);
           }
         }
-        if (!far) {
+      }
+      if (__any_sync(0xffffffffu, hits != 0u)) {
+        const int nh = __popc(hits);
+        if (__any_sync(0xffffffffu, qlen + nh > BKS_QCAP)) drain();
+        if (nh > BKS_QCAP) {  // a list that is still filling: evaluate this group in place
+          while (hits) {
+            const int b = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const int u = b / BKS_QT, s = b % BKS_QT;
 #pragma unroll
-          for (int u = 0; u < BK_G; ++u) {
+            for (int t = 0; t < BKS_QT; ++t)
+              if (t == s)
+                bks_consider<D>(qptr[t], s_ptd + (p + u) * D, (uint32_t)(base + p + u), K, s_kd + t * BK_QB + tid,
+                                s_ki + t * BK_QB + tid, cnt[t], worst[t], thr[t]);
+          }
 #pragma unroll
-            for (int s = 0; s < BKS_QT; ++s) {
-              if (!(acc[u][s] > thrp[s])) {  // a stale (looser) bound after an insertion stays conservative
-                bks_consider<D>(qptr[s], pts + (base + p + u) * D, (uint32_t)(base + p + u), K, s_kd + s * BK_QB + tid,
-                                s_ki + s * BK_QB + tid, cnt[s], worst[s], thr[s]);
-                if (cnt[s] == K) thrp[s] = __double2float_ru(0.5 * (thr[s] - qn[s]) + pad[s]);
-              }
-            }
+          for (int s = 0; s < BKS_QT; ++s)
+            thrp[s] = cnt[s] == K ? __double2float_ru(0.5 * (thr[s] - qn[s]) + pad[s]) : __int_as_float(0x7f800000);
+        } else {
+          while (hits) {  // ascending bit = ascending point, so a list's candidates stay in index order
+            const int b = __ffs(hits) - 1;
+            hits &= hits - 1;
+            s_q[qlen * BK_QB] = (uint16_t)(((uint32_t)(b % BKS_QT) << 12) | (p + (uint32_t)(b / BKS_QT)));
+            ++qlen;
           }
         }
-        p += BK_G;
-      } else {
-        const float4* pp = reinterpret_cast<const float4*>(s_pts + p * DS);
-#pragma unroll
-        for (int s = 0; s < BKS_QT; ++s) {
-          if (!(approx(pp, s) > thrp[s])) {
-            bks_consider<D>(qptr[s], pts + (base + p) * D, (uint32_t)(base + p), K, s_kd + s * BK_QB + tid,
-                            s_ki + s * BK_QB + tid, cnt[s], worst[s], thr[s]);
-            if (cnt[s] == K) thrp[s] = __double2float_ru(0.5 * (thr[s] - qn[s]) + pad[s]);
-          }
-        }
-        ++p;
       }
     }
+    drain();
   }
 #pragma unroll
   for (int s = 0; s < BKS_QT; ++s) {
@@ -824,7 +858,7 @@ static int knn_estimate_dev(bpomp_ctx* ctx, const double* d_queries, int64_t nq,
     BP_TRY(bp_reserve(ctx, bi, (size_t)P * nq * K * sizeof(uint32_t), false));
     dim3 grid((unsigned)qblocks, (unsigned)P);
     if (f32) {
-      size_t sm = (size_t)BK_TILE * bks_ds(D) * sizeof(float) + (size_t)K * BKS_QT * BK_QB * (sizeof(double) + sizeof(uint32_t));
+      size_t sm = bks_smem(D, K);
       auto kern = bk_knn_partial_f32<D>;
       BP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
       kern<<<grid, BK_QB, sm, ctx->stream>>>(d_queries, nq, ctx->d_bel_pts.as<double>(), M, chunk, K, bd.as<double>(),
