@@ -17,7 +17,9 @@
 #include "common.cuh"
 #include "belief_grid.cuh"
 
+#ifndef BK_QB
 #define BK_QB 128    // threads per block
+#endif
 #ifndef BK_QT
 #define BK_QT 2      // queries per thread
 #endif
@@ -331,27 +333,31 @@ __global__ void __launch_bounds__(BK_QB) bk_knn_partial(const double* __restrict
 // The same partial top-k for dimensions >= 4 (no spatial index there), restructured around the two things the
 // FP64 version above was bound by (profiles/r2_belief_summary.md: FP64 pipe 45 % active at 16 % warps active, and
 // list insertions running with one or two active lanes):
-//  * the prefilter runs on the FP32 pipe.  The tile holds the points rounded to float plus |p|^2/2 (computed in
-//    FP64, then rounded); a thread owns BKS_QT queries rounded to float, so a point read from the tile (two
-//    16-byte broadcasts at D = 7) serves BKS_QT fused-multiply-add chains.
-//        a = |p|^2/2 - q.p  (FP32)   rejects the point iff   a > (thr - |q|^2)/2 + E,
-//    E = 2^-20 (|q|^2 + max|p|^2): the error of a — inputs rounded to float (2^-24 relative each), D <= 8
-//    roundings of the chain, the rounding of |p|^2/2 — is below 11 * 2^-24 (|q|^2 + |p|^2), so a rejected point
-//    is beyond thr in exact arithmetic (and thr already pads the reference's own rounding);
+//  * the prefilter runs on the FP32 pipe with the packed two-lane instructions of sm_100 (FFMA2).  The tile holds
+//    the points rounded to float, two points interleaved per record ((x_j of point 2i, x_j of point 2i+1) pairs,
+//    then the pair of |p|^2/2 values, computed in FP64 and rounded), so one 16-byte broadcast load feeds two
+//    packed fused multiply-adds; a thread owns BKS_QT queries (each coordinate duplicated into a float2).
+//        a = |p|^2/2 - q.p - t   (FP32),   t = (thr - |q|^2)/2 + E rounded up,   rejects the point iff a > 0.
+//    E = 2^-20 (|q|^2 + max|p|^2) bounds the error of a — inputs rounded to float (2^-24 relative each), D + 1 <= 9
+//    roundings of the chain, the rounding of |p|^2/2: below 12 * 2^-24 (|q|^2 + |p|^2) — so a rejected point is
+//    beyond thr in exact arithmetic (and thr already pads the reference's own rounding).  The rejection test of a
+//    group of 8 points is one OR over the sign bits of its accumulators;
 //  * survivors are not inserted on the spot: a thread pushes them (tile position, query slot) to its own small
 //    queue in shared memory, and the queues are drained together — at the end of a tile, or when one is about to
 //    overflow — so that the exact evaluation (the reference's unfused FP64 arithmetic on the original coordinates,
 //    kept beside the float tile) and the ordered insertion run with most lanes of a warp busy.  A queue is
 //    drained in push order, i.e. ascending insertion index per list, which the tie rule relies on.
+// While a list is still filling (the first k points of a chunk) every point is a survivor.
 // ---------------------------------------------------------------------------
 #ifndef BKS_QT
-#define BKS_QT 4
+#define BKS_QT 2
 #endif
 #define BKS_TILE 128
 #define BKS_QCAP 8
-__host__ __device__ constexpr int bks_ds(int D) { return (D + 4) & ~3; }  // floats per tile point: D coords + norm, x4
+#define BKS_G 8  // points per group (4 pair records)
+__host__ __device__ constexpr int bks_pp(int D) { return (D + 2) & ~1; }  // float2 entries per pair record
 __host__ __device__ constexpr size_t bks_smem(int D, int K) {
-  return (size_t)BKS_TILE * bks_ds(D) * sizeof(float) + (size_t)BKS_TILE * D * sizeof(double) +
+  return (size_t)(BKS_TILE / 2) * bks_pp(D) * sizeof(float2) + (size_t)BKS_TILE * D * sizeof(double) +
          (size_t)K * BKS_QT * BK_QB * (sizeof(double) + sizeof(uint32_t)) + (size_t)BKS_QCAP * BK_QB * sizeof(uint16_t);
 }
 
@@ -388,23 +394,24 @@ __global__ void __launch_bounds__(BK_QB) bk_knn_partial_f32(const double* __rest
                                                             const double* __restrict__ pts, uint64_t M, uint64_t chunk,
                                                             int K, double* __restrict__ part_d,
                                                             uint32_t* __restrict__ part_i) {
-  constexpr int DS = bks_ds(D);
+  constexpr int PP = bks_pp(D);
   constexpr int LS = BKS_QT * BK_QB;
+  static_assert(BKS_G * BKS_QT <= 32, "hit mask is 32 bits");
   extern __shared__ __align__(16) unsigned char smem[];
-  float* s_pts = reinterpret_cast<float*>(smem);                                                  // [BKS_TILE][DS]
-  double* s_ptd = reinterpret_cast<double*>(smem + (size_t)BKS_TILE * DS * sizeof(float));        // [BKS_TILE][D]
-  double* s_kd = s_ptd + (size_t)BKS_TILE * D;                                                    // [K][BKS_QT][BK_QB]
+  float* s_pts = reinterpret_cast<float*>(smem);                                                       // [TILE/2][PP] float2
+  double* s_ptd = reinterpret_cast<double*>(smem + (size_t)(BKS_TILE / 2) * PP * sizeof(float2));      // [TILE][D]
+  double* s_kd = s_ptd + (size_t)BKS_TILE * D;                                                         // [K][QT][QB]
   uint32_t* s_ki = reinterpret_cast<uint32_t*>(s_kd + (size_t)K * LS);
-  uint16_t* s_q = reinterpret_cast<uint16_t*>(s_ki + (size_t)K * LS) + threadIdx.x;               // [BKS_QCAP][BK_QB]
+  uint16_t* s_q = reinterpret_cast<uint16_t*>(s_ki + (size_t)K * LS) + threadIdx.x;                    // [QCAP][QB]
   __shared__ unsigned long long s_pnmax;
   const int tid = threadIdx.x;
   const uint64_t p_begin = (uint64_t)blockIdx.y * chunk;
   const uint64_t p_end = p_begin + chunk < M ? p_begin + chunk : M;
-  float nqf[BKS_QT][D];  // -query, rounded to float
-  double qn[BKS_QT];     // |q|^2
+  float2 nq2[BKS_QT][D];  // (-q_j, -q_j)
+  float2 nthr2[BKS_QT];   // (-t, -t)
+  double qn[BKS_QT];      // |q|^2
   double worst[BKS_QT], thr[BKS_QT], pad[BKS_QT];
-  float thrp[BKS_QT];
-  int cnt[BKS_QT];
+  int cnt[BKS_QT];        // the same in every thread and slot: min(points scanned, K)
   const double* qptr[BKS_QT];
 #pragma unroll
   for (int s = 0; s < BKS_QT; ++s) {
@@ -415,102 +422,124 @@ __global__ void __launch_bounds__(BK_QB) bk_knn_partial_f32(const double* __rest
 #pragma unroll
     for (int j = 0; j < D; ++j) {
       const double v = qptr[s][j];
-      nqf[s][j] = -(float)v;
+      const float f = -(float)v;
+      nq2[s][j] = make_float2(f, f);
       qn[s] = fma(v, v, qn[s]);
     }
     cnt[s] = 0;
     worst[s] = DBL_MAX;
     thr[s] = DBL_MAX;
     pad[s] = 0.0;
-    thrp[s] = __int_as_float(0x7f800000);  // +inf: nothing is rejected while the list is filling
+    nthr2[s] = make_float2(0.f, 0.f);
   }
   int qlen = 0;
   uint64_t base = p_begin;  // first point of the current tile (the drain needs it)
 
+  auto refresh = [&]() {
+#pragma unroll
+    for (int s = 0; s < BKS_QT; ++s) {
+      const float t = -__double2float_ru(0.5 * (thr[s] - qn[s]) + pad[s]);
+      nthr2[s] = make_float2(t, t);
+    }
+  };
+  auto consider_slot = [&](int s, uint32_t p) {
+#pragma unroll
+    for (int t = 0; t < BKS_QT; ++t)
+      if (t == s)
+        bks_consider<D>(qptr[t], s_ptd + p * D, (uint32_t)(base + p), K, s_kd + t * BK_QB + tid, s_ki + t * BK_QB + tid,
+                        cnt[t], worst[t], thr[t]);
+  };
   auto drain = [&]() {  // every lane empties its queue, oldest entry first
     int i = 0;
     while (__any_sync(0xffffffffu, i < qlen)) {
       if (i < qlen) {
         const uint32_t code = s_q[i * BK_QB];
-        const uint32_t p = code & 0xfffu;
-        const int s = (int)(code >> 12);
-#pragma unroll
-        for (int t = 0; t < BKS_QT; ++t)
-          if (t == s)
-            bks_consider<D>(qptr[t], s_ptd + p * D, (uint32_t)(base + p), K, s_kd + t * BK_QB + tid,
-                            s_ki + t * BK_QB + tid, cnt[t], worst[t], thr[t]);
+        consider_slot((int)(code >> 12), code & 0xfffu);
       }
       ++i;
     }
     qlen = 0;
-#pragma unroll
-    for (int s = 0; s < BKS_QT; ++s)
-      thrp[s] = cnt[s] == K ? __double2float_ru(0.5 * (thr[s] - qn[s]) + pad[s]) : __int_as_float(0x7f800000);
+    refresh();
   };
 
   for (; base < p_end; base += BKS_TILE) {
     const uint32_t tn = (uint32_t)((p_end - base) < BKS_TILE ? (p_end - base) : BKS_TILE);
+    const uint32_t tn_pad = (tn + BKS_G - 1) & ~(uint32_t)(BKS_G - 1);
     __syncthreads();  // every thread has drained the previous tile
     if (tid == 0) s_pnmax = 0ull;
     __syncthreads();
-    for (uint32_t p = tid; p < tn; p += BK_QB) {
-      double pn = 0.0;
+    for (uint32_t p = tid; p < tn_pad; p += BK_QB) {
+      float* rec = s_pts + (size_t)(p >> 1) * 2 * PP + (p & 1u);
+      if (p < tn) {
+        double pn = 0.0;
 #pragma unroll
-      for (int j = 0; j < D; ++j) {
-        const double v = pts[(base + p) * D + j];
-        s_ptd[p * D + j] = v;
-        s_pts[p * DS + j] = (float)v;
-        pn = fma(v, v, pn);
+        for (int j = 0; j < D; ++j) {
+          const double v = pts[(base + p) * D + j];
+          s_ptd[p * D + j] = v;
+          rec[2 * j] = (float)v;
+          pn = fma(v, v, pn);
+        }
+        rec[2 * D] = (float)(0.5 * pn);
+        atomicMax(&s_pnmax, (unsigned long long)__double_as_longlong(pn));  // NaN bits exceed +inf: stays NaN
+      } else {  // padding up to a whole group: a point that is never a survivor
+#pragma unroll
+        for (int j = 0; j < D; ++j) rec[2 * j] = 0.f;
+        rec[2 * D] = __int_as_float(0x7f800000);
       }
-      s_pts[p * DS + D] = (float)(0.5 * pn);
-      atomicMax(&s_pnmax, (unsigned long long)__double_as_longlong(pn));  // NaN bits exceed +inf: stays NaN
     }
     __syncthreads();
     const double pnmax = __longlong_as_double((long long)s_pnmax);
 #pragma unroll
-    for (int s = 0; s < BKS_QT; ++s) {
-      pad[s] = 9.5367431640625e-07 * (qn[s] + pnmax);  // 2^-20
-      thrp[s] = cnt[s] == K ? __double2float_ru(0.5 * (thr[s] - qn[s]) + pad[s]) : __int_as_float(0x7f800000);
-    }
-    for (uint32_t p = 0; p < tn; p += BK_G) {
-      // hit mask of this group: bit u*BKS_QT+s = point p+u survives the prefilter of query s
+    for (int s = 0; s < BKS_QT; ++s) pad[s] = 9.5367431640625e-07 * (qn[s] + pnmax);  // 2^-20
+    refresh();
+    for (uint32_t p = 0; p < tn; p += BKS_G) {
       uint32_t hits = 0;
+      if (cnt[0] < K) {  // lists still filling (block-uniform): every real point of the group is a survivor
 #pragma unroll
-      for (int u = 0; u < BK_G; ++u) {
-        if (p + u < tn) {
-          const float4* pp = reinterpret_cast<const float4*>(s_pts + (p + u) * DS);
-          float v[DS];
+        for (int u = 0; u < BKS_G; ++u)
+          if (p + u < tn) hits |= ((1u << BKS_QT) - 1u) << (u * BKS_QT);
+      } else {
+        const float4* g4 = reinterpret_cast<const float4*>(s_pts) + (size_t)(p >> 1) * (PP / 2);
+        float2 acc[BKS_G / 2][BKS_QT];
+        uint32_t sign = 0;
 #pragma unroll
-          for (int h = 0; h < DS / 4; ++h) {
-            const float4 t = pp[h];
-            v[4 * h] = t.x; v[4 * h + 1] = t.y; v[4 * h + 2] = t.z; v[4 * h + 3] = t.w;
+        for (int u = 0; u < BKS_G / 2; ++u) {
+          float2 x2[PP];
+#pragma unroll
+          for (int h = 0; h < PP / 2; ++h) {
+            const float4 t = g4[u * (PP / 2) + h];
+            x2[2 * h] = make_float2(t.x, t.y);
+            x2[2 * h + 1] = make_float2(t.z, t.w);
           }
 #pragma unroll
           for (int s = 0; s < BKS_QT; ++s) {
-            float acc = v[D];
+            float2 a = __fadd2_rn(x2[D], nthr2[s]);
 #pragma unroll
-            for (int j = 0; j < D; ++j) acc = fmaf(nqf[s][j], v[j], acc);
-            if (!(acc > thrp[s])) hits |= 1u << (u * BKS_QT + s);
+            for (int j = 0; j < D; ++j) a = __ffma2_rn(nq2[s][j], x2[j], a);
+            acc[u][s] = a;
+            sign |= __float_as_uint(a.x) | __float_as_uint(a.y);
           }
+        }
+        if (sign >> 31) {  // some accumulator is not positive: collect the survivors of this group
+#pragma unroll
+          for (int u = 0; u < BKS_G / 2; ++u)
+#pragma unroll
+            for (int s = 0; s < BKS_QT; ++s) {
+              if (!(acc[u][s].x > 0.f)) hits |= 1u << ((2 * u) * BKS_QT + s);
+              if (!(acc[u][s].y > 0.f)) hits |= 1u << ((2 * u + 1) * BKS_QT + s);
+            }
         }
       }
       if (__any_sync(0xffffffffu, hits != 0u)) {
         const int nh = __popc(hits);
         if (__any_sync(0xffffffffu, qlen + nh > BKS_QCAP)) drain();
-        if (nh > BKS_QCAP) {  // a list that is still filling: evaluate this group in place
+        if (nh > BKS_QCAP) {  // more than a queue holds (lists filling): evaluate this group in place
           while (hits) {
             const int b = __ffs(hits) - 1;
             hits &= hits - 1;
-            const int u = b / BKS_QT, s = b % BKS_QT;
-#pragma unroll
-            for (int t = 0; t < BKS_QT; ++t)
-              if (t == s)
-                bks_consider<D>(qptr[t], s_ptd + (p + u) * D, (uint32_t)(base + p + u), K, s_kd + t * BK_QB + tid,
-                                s_ki + t * BK_QB + tid, cnt[t], worst[t], thr[t]);
+            consider_slot(b % BKS_QT, p + (uint32_t)(b / BKS_QT));
           }
-#pragma unroll
-          for (int s = 0; s < BKS_QT; ++s)
-            thrp[s] = cnt[s] == K ? __double2float_ru(0.5 * (thr[s] - qn[s]) + pad[s]) : __int_as_float(0x7f800000);
+          refresh();
         } else {
           while (hits) {  // ascending bit = ascending point, so a list's candidates stay in index order
             const int b = __ffs(hits) - 1;

@@ -132,7 +132,7 @@ BatchingPOMP::BatchingPOMP(const SpaceInformation& si)
       bmExhausted(false), bmCurrRadius(0.0), bmNumVerticesAdded(0), bmNextVertexTarget(0), bmVertInfl(2.0),
       bmRadiusInfl(1.0), bmInitRadius(0.0), bmMaxRadius(0.0), bmCurrVertex(0), bmEdgeMode(false), mNumSolutions(0),
       mBeliefEmpty(true), mNumEdgeChecks(0), mNumCollChecks(0), mNumSearches(0), mNumLookups(0), mLookupTime(0.0),
-      mCollCheckTime(0.0), mSearchTime(0.0), mDeviceTime(0.0), mSearchHostTime(0.0), mBeliefK(15), mBeliefPrior(0.5),
+      mCollCheckTime(0.0), mSearchTime(0.0), mDeviceTime(0.0), mSearchHostTime(0.0), mNumSpeculativeChecks(0), mBeliefK(15), mBeliefPrior(0.5),
       mBeliefPriorWeight(0.25) {
   if (mDim == 0 || si.low.size() != mDim || si.high.size() != mDim)
     throw Exception("SpaceInformation: bounds must have `dim` entries");
@@ -839,16 +839,39 @@ bool BatchingPOMP::checkAndUpdatePathBlocked(const std::vector<Edge>& ePath) {
     if (mEdges[e].blockedStatus == UNKNOWN) unknown.push_back(e);
   if (unknown.empty()) return false;
   double t0 = now();
-  size_t m = unknown.size();
-  std::vector<uint32_t> from(m), to(m), ns(m);
-  std::vector<uint8_t> valid(m);
-  std::vector<int32_t> first(m);
-  for (size_t i = 0; i < m; ++i) {
-    from[i] = mEdges[unknown[i]].source;
-    to[i] = mEdges[unknown[i]].target;
+  const size_t m = unknown.size();
+  // Speculative edge evaluation.  Every still-unknown edge of the candidate path is evaluated in
+  // ONE device call, although with a selector the reference stops at the first blocked edge (BP.cpp:591-593):
+  // the collision world is static, so the result of an edge never changes, and the results of the edges behind
+  // the stopping point are kept (mSpecStatus / mSpecFirst) until the reference's order gets to them — consecutive
+  // candidate paths share most of their edges.  They are COMMITTED (status, counters, belief inserts) only then,
+  // in the reference's order, so statuses, counters and the belief model are those of the sequential reference.
+  if (mSpecStatus.size() < mEdges.size()) {
+    mSpecStatus.resize(mEdges.size(), 0);
+    mSpecFirst.resize(mEdges.size(), 0);
   }
-  flushVertices();
-  BP_DEV(bpomp_edges_check_indexed(dev(), from.data(), to.data(), (int64_t)m, valid.data(), first.data(), ns.data()));
+  std::vector<uint32_t> from, to;
+  std::vector<Edge> fresh;
+  for (Edge e : unknown)
+    if (!mSpecStatus[e]) {
+      fresh.push_back(e);
+      from.push_back(mEdges[e].source);
+      to.push_back(mEdges[e].target);
+    }
+  if (!fresh.empty()) {
+    const size_t k = fresh.size();
+    std::vector<uint32_t> ns(k);
+    std::vector<uint8_t> valid(k);
+    std::vector<int32_t> first(k);
+    flushVertices();
+    BP_DEV(bpomp_edges_check_indexed(dev(), from.data(), to.data(), (int64_t)k, valid.data(), first.data(), ns.data()));
+    for (size_t i = 0; i < k; ++i) {
+      if (ns[i] != mEdges[fresh[i]].nStates) throw Exception("internal: device and host disagree on nStates");
+      mSpecStatus[fresh[i]] = valid[i] ? 1 : 2;
+      mSpecFirst[fresh[i]] = first[i];
+    }
+    mNumSpeculativeChecks += k;
+  }
   bool pathBlocked = false;
   size_t committed = 0;
   for (size_t i = 0; i < m; ++i) {
@@ -862,11 +885,10 @@ bool BatchingPOMP::checkAndUpdatePathBlocked(const std::vector<Edge>& ePath) {
           mEdgeMarked[oe.eid] = 1;
           mEdgesToUpdate.push_back(oe.eid);
         }
-    if (ns[i] != ep.nStates) throw Exception("internal: device and host disagree on nStates");
     committed = i + 1;
-    if (!valid[i]) {
-      mNumCollChecks += (unsigned int)first[i];  // one isValid per slot up to the invalid one, BP.cpp:516
-      ep.blockedStatus = BLOCKED;                 // BP.cpp:529-531
+    if (mSpecStatus[e] == 2) {
+      mNumCollChecks += (unsigned int)mSpecFirst[e];  // one isValid per slot up to the invalid one, BP.cpp:516
+      ep.blockedStatus = BLOCKED;                      // BP.cpp:529-531
       ep.distance = kInf;
       setProbFree(ep, 0.0);
       pathBlocked = true;
@@ -878,11 +900,20 @@ bool BatchingPOMP::checkAndUpdatePathBlocked(const std::vector<Edge>& ePath) {
     }
   }
   // belief inserts of the committed edges, in check order (BP.cpp:523-537), replayed on the device from the
-  // vertex ids and the nStates the check reported
+  // vertex ids, the first invalid slot and nStates
   uint64_t added = 0;
-  for (size_t i = 0; i < committed; ++i) added += valid[i] ? ns[i] - 2u : (uint32_t)first[i];
+  std::vector<uint32_t> cf(committed), ct(committed), cn(committed);
+  std::vector<int32_t> cfirst(committed);
+  for (size_t i = 0; i < committed; ++i) {
+    const EProps& ep = mEdges[unknown[i]];
+    cf[i] = ep.source;
+    ct[i] = ep.target;
+    cn[i] = ep.nStates;
+    cfirst[i] = mSpecStatus[unknown[i]] == 2 ? mSpecFirst[unknown[i]] : -1;
+    added += cfirst[i] >= 1 ? (uint32_t)cfirst[i] : ep.nStates - 2u;
+  }
   if (added > 0) {
-    BP_DEV(bpomp_belief_append_checked_indexed(dev(), from.data(), to.data(), first.data(), ns.data(), (int64_t)committed));
+    BP_DEV(bpomp_belief_append_checked_indexed(dev(), cf.data(), ct.data(), cfirst.data(), cn.data(), (int64_t)committed));
     mBeliefEmpty = false;
   }
   mCollCheckTime += now() - t0;

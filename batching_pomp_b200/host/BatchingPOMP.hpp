@@ -131,6 +131,9 @@ public:
   double getDeviceTime() const { return mDeviceTime; }
   /// Wall time of the searches (astar, including edge creation) outside the device library.
   double getSearchHostTime() const { return mSearchHostTime; }
+  /// Edges evaluated on the device so far, including those evaluated ahead of the reference's order whose
+  /// results are waiting to be committed (getNumEdgeChecks counts committed evaluations, as the reference does).
+  uint64_t getNumDeviceEdgeChecks() const { return mNumSpeculativeChecks; }
 
   // ---- OMPL required methods, BatchingPOMP.hpp:203-205 ----
   void setup();
@@ -309,6 +312,10 @@ private:
   unsigned int mNumEdgeChecks, mNumCollChecks, mNumSearches, mNumLookups;
   double mLookupTime, mCollCheckTime, mSearchTime;
   double mDeviceTime, mSearchHostTime;
+  // speculative edge evaluation: device results of edges not yet committed (0 none, 1 free, 2 blocked)
+  std::vector<uint8_t> mSpecStatus;
+  std::vector<int32_t> mSpecFirst;
+  uint64_t mNumSpeculativeChecks;
   int mBeliefK;
   double mBeliefPrior, mBeliefPriorWeight;
 };

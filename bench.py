@@ -249,7 +249,7 @@ def peak_hbm():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-def extra_indexed_leg(torch, capi, oracle, stream, dev, L, lo, hi, peak, cores):
+def extra_indexed_leg(torch, capi, oracle, stream, dev, L, lo, hi, peak, cores, rank=0, world=1, dist=None):
     """The planner's own edge path (BASELINE config 3): r-disk rows of the 10^6-vertex 7-D Halton roadmap as indexed
     edges (source = the expanded vertex) against the 500 boxes; vertex table resident, 8 B of ids per edge in."""
     N, nq = 10 ** 6, 4096
@@ -259,7 +259,8 @@ def extra_indexed_leg(torch, capi, oracle, stream, dev, L, lo, hi, peak, cores):
     ctx.set_bounds(0.0, 1.0)
     ctx.set_world_boxes(lo, hi)
     ctx.vertices_append(verts)
-    q = (np.arange(nq, dtype=np.uint64) * (N // nq)).astype(np.uint32)
+    # N > 1 (weak scaling): every rank takes the rows of different vertices; the vertex table is replicated
+    q = ((np.arange(nq, dtype=np.uint64) * (N // nq) + 17 * rank) % N).astype(np.uint32)
     t0 = time.perf_counter()
     rp, col, _ = ctx.neighbors_radius(q, r)
     nb_s = time.perf_counter() - t0
@@ -284,14 +285,25 @@ def extra_indexed_leg(torch, capi, oracle, stream, dev, L, lo, hi, peak, cores):
         ctx._ck(ctx.lib.bpomp_edges_check_indexed(ctx.h, capi._ptr(fi_p), capi._ptr(ti_p), E, capi._ptr(hv.numpy()),
                                                   capi._ptr(hf.numpy()), None))
     e2e()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     w0 = time.perf_counter()
     for _ in range(5):
         e2e()
     e2e_s = (time.perf_counter() - w0) / 5
+    E_all = E
+    if world > 1:  # max time over ranks, edges of all ranks
+        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+        n = torch.tensor([E], dtype=torch.int64, device=dev)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+        E_all = int(n[0])
     # parity + CPU column on a sample
     m = min(E, 1_000_000)
     t0 = time.perf_counter()
-    ov, of, on = oracle.edges_check_boxes(verts[fi[:m]], verts[ti[:m]], L, lo, hi, nthreads=cores)
+    ov, of, on = oracle.edges_check_boxes(verts[fi[:m]], verts[ti[:m]], L, lo, hi, nthreads=max(1, cores // world))
     cpu = m / (time.perf_counter() - t0)
     parity_check("indexed leg", (tv.cpu().numpy(), tf.cpu().numpy(), tn.cpu().numpy().view(np.uint32)), (ov, of, on))
     parity_check("indexed leg, end to end", (hv.numpy(), hf.numpy(), tn.cpu().numpy().view(np.uint32)), (ov, of, on))
@@ -299,14 +311,38 @@ def extra_indexed_leg(torch, capi, oracle, stream, dev, L, lo, hi, peak, cores):
     ctx.close()
     return {"workload": "config3 roadmap edges: %d r-disk rows (r = haltonRadius) of the 10^6-vertex 7-D Halton roadmap, "
                         "indexed endpoints, 500 boxes" % nq,
-            "edges": E, "value": E / ms * 1e3, "unit": UNIT, "ms": ms,
+            "edges": E_all, "n_gpus": world, "value": E_all / ms * 1e3, "unit": UNIT, "ms": ms,
             "roofline": {"bound": "hbm", "algorithmic_bytes": algo, "achieved": algo / ms * 1e-6, "peak": peak, "unit": "GB/s",
                          "frac": algo / ms * 1e-6 / peak,
-                         "note": "13 B per edge + the 56 MB vertex table once; instruction-issue bound like the headline"},
-            "e2e": {"value": E / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * E, "d2h_bytes_per_step": 5 * E,
-                    "call": "bpomp_edges_check_indexed (pinned host id arrays)"},
+                         "note": "per GPU: 13 B per edge + the 56 MB vertex table once; instruction-issue bound like the headline"},
+            "e2e": {"value": E_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * E, "d2h_bytes_per_step": 5 * E,
+                    "ms_per_step": 1e3 * e2e_s,
+                    "call": "bpomp_edges_check_indexed (pinned host id arrays; vertex table resident; max over ranks)"},
             "cpu_port_value": cpu, "cpu_cores": cores, "parity_checked_edges": m,
             "neighbor_rows_seconds": nb_s, "blocked_fraction": float((tv == 0).float().mean())}
+
+
+def h2d_roof(torch, dev, world, dist, mbytes=512, reps=5):
+    """What the host link moves: every rank copies a pinned buffer to its GPU at the same time (barrier on both
+    sides, max over ranks); the figure the end-to-end numbers are to be read against."""
+    h = torch.empty(mbytes << 20, dtype=torch.uint8).pin_memory()
+    d = torch.empty(mbytes << 20, dtype=torch.uint8, device=dev)
+    d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t[0])
+    per_rank = reps * (mbytes << 20) / dt / 1e9
+    return {"GBps_per_rank": per_rank, "GBps_aggregate": per_rank * world, "n_gpus": world,
+            "how": "%d MiB pinned -> device, %d copies per rank, all ranks at once, max time over ranks" % (mbytes, reps)}
 
 
 def extra_image_leg(torch, capi, oracle, stream, dev, peak, cores):
@@ -597,6 +633,13 @@ def run_gpu(args):
         ref_checked = parity_check("device-resident step vs the reference's own code",
                                    (d_valid[last].cpu().numpy(), d_first[last].cpu().numpy(), ns_dev), cb["outputs"])
 
+    # legs every rank takes part in (N > 1: the indexed end-to-end figure and the host link's roof)
+    multi_extras = None
+    if world > 1 and not args.no_extras:
+        from oracle import oracle as _orc
+        multi_extras = {"h2d_roof": h2d_roof(torch, dev, world, dist),
+                        "indexed_edges": extra_indexed_leg(torch, capi, _orc, stream, dev, L, lo, hi, peak_hbm()[0], cores,
+                                                           rank=rank, world=world, dist=dist)}
     if rank == 0:
         peak, peak_src = peak_hbm()
         achieved = ALGO_BYTES_PER_EDGE * edges_per_launch / (avg_launch_ms * 1e-3) / 1e9
@@ -651,11 +694,13 @@ def run_gpu(args):
             line["cpu_baseline"]["oracle_port_value"] = cb.get("port_value")
         if world == 1 and not args.no_extras:
             from oracle import oracle
-            extras = {}
+            extras = {"h2d_roof": h2d_roof(torch, dev, 1, None)}
             extras["indexed_edges"] = extra_indexed_leg(torch, capi, oracle, stream, dev, L, lo, hi, peak, cores)
             extras["image_edges"] = extra_image_leg(torch, capi, oracle, stream, dev, peak, cores)
             extras["planner"] = extra_planner_leg(oracle)
             line["extra"] = extras
+        if multi_extras:
+            line["extra"] = multi_extras
         print(json.dumps(line))
     ctx.close()
     if world > 1:
