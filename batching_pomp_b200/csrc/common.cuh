@@ -149,6 +149,8 @@ struct bpomp_ctx {
   bool work_dirty[4] = {true, true, true, true};
   const int* last_slow_count = nullptr;
   DevBuf d_slow_list[4];                    // per pipeline lane: indices of the edges the fast kernel left over
+  uint32_t* pack_out = nullptr;             // set around a sharded edge call: the fast kernel also writes the packed
+  bool pack_done = false;                   // status words there (and says so), saving the separate pack kernel
   int fused_pfree = 1;                      // 0: never use the one-launch free-probability kernel (testing)
   int fast_mode = 1;                        // 0: never use the fast kernel (testing / tuning)
   int reserve_sms = -1;                     // SMs the fast kernel leaves free (-1: 4 with a communicator, else 0)

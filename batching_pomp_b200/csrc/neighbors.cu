@@ -436,6 +436,194 @@ __global__ void __launch_bounds__(NB_TQ, 4) nb_tile_kernel(QueryArgs a, GridView
   }
 }
 
+// The tiled all-pairs scan for dimensions >= 4 and a finite radius, with the prefilter on the FP32 pipe — the
+// FP64 version above runs at 57 % of the FP64 pipe (profiles/r1_neighbors7d_tiled_v2_summary.md).  Same scheme as
+// the belief kNN kernel (belief.cu: bk_knn_partial_f32): the tile holds the points rounded to float, two points
+// interleaved per record plus their |p|^2/2, so a 16-byte broadcast load feeds two packed fused multiply-adds
+// (FFMA2);  a = |p|^2/2 - q.p - t  with  t = (r2pad - |q|^2)/2 + 2^-20 (|q|^2 + max|p|^2)  rounded up rejects a
+// point iff a > 0 (the pad bounds the FP32 error: inputs rounded to float, D + 1 <= 9 roundings of the chain, the
+// rounding of |p|^2/2), tested for 16 points at once by OR-ing the accumulators' sign bits.  Survivors go to a
+// small per-thread queue and are evaluated together — the reference's unfused FP64 distance on the original
+// coordinates, `dist <= r` inclusive as GNAT's nearestR — so that path runs with most lanes of a warp busy.
+#define NBS_G 16
+#define NBS_QCAP 8
+__host__ __device__ constexpr int nbs_pp(int D) { return (D + 2) & ~1; }  // float2 entries per pair record
+
+template <int D, bool FILL>
+__global__ void __launch_bounds__(NB_TQ, 4) nb_tile_kernel_f32(QueryArgs a, GridView g, uint32_t chunk) {
+  constexpr int PP = nbs_pp(D);
+  static_assert(NBS_G * NB_QT <= 32, "hit mask is 32 bits");
+  __shared__ __align__(16) float s_pf[(NB_TP / 2) * PP * 2];
+  __shared__ double s_pd[NB_TP * D];
+  __shared__ uint32_t s_ids[NB_TP];
+  __shared__ uint16_t s_queue[NBS_QCAP * NB_TQ];
+  __shared__ unsigned int s_pnhi;
+  const int tid = threadIdx.x;
+  uint16_t* s_q = s_queue + tid;
+  const uint32_t c = blockIdx.y;
+  const uint32_t p_begin = c * chunk;
+  const uint32_t p_end = min(p_begin + chunk, g.nactive);
+  bool have[NB_QT], skip[NB_QT];
+  float2 nq2[NB_QT][D];
+  float2 nthr2[NB_QT];
+  double qn[NB_QT];
+  const double* qptr[NB_QT];
+  uint64_t w[NB_QT], o[NB_QT];
+  uint32_t cnt[NB_QT];
+  bool skip_all = true;
+#pragma unroll
+  for (int s = 0; s < NB_QT; ++s) {
+    const uint32_t qi = (blockIdx.x * NB_QT + s) * NB_TQ + tid;
+    have[s] = qi < a.nq;
+    const uint32_t qid = have[s] ? (a.query ? __ldg(a.query + qi) : qi) : 0u;
+    skip[s] = !have[s] || (a.skip_inactive_query && !a.active[qid]);
+    skip_all = skip_all && skip[s];
+    qptr[s] = a.verts + (size_t)qid * D;
+    qn[s] = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      const double v = have[s] ? __ldg(qptr[s] + j) : 0.0;
+      const float f = -(float)v;
+      nq2[s][j] = make_float2(f, f);
+      qn[s] = fma(v, v, qn[s]);
+    }
+    w[s] = (uint64_t)qi * a.S + c;
+    o[s] = (FILL && have[s]) ? a.offs[w[s]] : 0;
+    cnt[s] = 0;
+  }
+  int qlen = 0;
+  auto exact = [&](int s, uint32_t t) {
+    double d2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      const double diff = __dsub_rn(__ldg(qptr[s] + j), s_pd[t * D + j]);
+      d2 = __dadd_rn(d2, __dmul_rn(diff, diff));
+    }
+    const double dist = __dsqrt_rn(d2);
+    if (dist <= a.r) {  // inclusive, as GNAT nearestR
+      if (FILL) {
+        a.out_dist[o[s] + cnt[s]] = dist;
+        a.out_id[o[s] + cnt[s]] = s_ids[t];
+      }
+      ++cnt[s];
+    }
+  };
+  auto exact_slot = [&](int s, uint32_t t) {
+#pragma unroll
+    for (int k = 0; k < NB_QT; ++k)
+      if (k == s) exact(k, t);
+  };
+  auto drain = [&]() {
+    int i = 0;
+    while (__any_sync(0xffffffffu, i < qlen)) {
+      if (i < qlen) {
+        const uint32_t code = s_q[i * NB_TQ];
+        exact_slot((int)(code >> 12), code & 0xfffu);
+      }
+      ++i;
+    }
+    qlen = 0;
+  };
+  for (uint32_t base = p_begin; base < p_end; base += NB_TP) {
+    const uint32_t tn = min((uint32_t)NB_TP, p_end - base);
+    const uint32_t tn_pad = (tn + NBS_G - 1) & ~(uint32_t)(NBS_G - 1);
+    __syncthreads();  // the previous tile has been drained by every thread
+    if (tid == 0) s_pnhi = 0u;
+    __syncthreads();
+    {
+      double pn = 0.0;
+      float* rec = s_pf + (size_t)(tid >> 1) * 2 * PP + (tid & 1);
+      if ((uint32_t)tid < tn) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          const double v = __ldg(g.pts + (size_t)j * g.nactive + base + tid);
+          s_pd[tid * D + j] = v;
+          rec[2 * j] = (float)v;
+          pn = fma(v, v, pn);
+        }
+        rec[2 * D] = (float)(0.5 * pn);
+        if (FILL) s_ids[tid] = __ldg(g.ids + base + tid);
+      } else if ((uint32_t)tid < tn_pad) {  // padding up to a whole group: never a survivor
+#pragma unroll
+        for (int j = 0; j < D; ++j) rec[2 * j] = 0.f;
+        rec[2 * D] = __int_as_float(0x7f800000);
+      }
+      const unsigned int hi = __reduce_max_sync(0xffffffffu, (unsigned int)__double2hiint(pn));
+      if ((tid & 31) == 0) atomicMax(&s_pnhi, hi);
+    }
+    __syncthreads();
+    if (skip_all) continue;
+    // upper bound of max |p|^2: next high word (inf / NaN high words stay non-finite -> nothing is rejected)
+    const double pnmax = __hiloint2double((int)(s_pnhi < 0x7ff00000u ? s_pnhi + 1u : 0x7ff80000u), 0);
+#pragma unroll
+    for (int s = 0; s < NB_QT; ++s) {
+      // a skipped slot never survives (t = -inf); a NaN bound makes every comparison fail -> everything survives
+      const float t = skip[s] ? __int_as_float(0x7f800000)
+                              : -__double2float_ru(0.5 * (a.r2pad - qn[s]) + 9.5367431640625e-07 * (qn[s] + pnmax));
+      nthr2[s] = make_float2(t, t);
+    }
+    for (uint32_t p = 0; p < tn; p += NBS_G) {
+      const float4* g4 = reinterpret_cast<const float4*>(s_pf) + (size_t)(p >> 1) * (PP / 2);
+      float2 acc[NBS_G / 2][NB_QT];
+      uint32_t sign = 0;
+#pragma unroll
+      for (int u = 0; u < NBS_G / 2; ++u) {
+        float2 x2[PP];
+#pragma unroll
+        for (int h = 0; h < PP / 2; ++h) {
+          const float4 t = g4[u * (PP / 2) + h];
+          x2[2 * h] = make_float2(t.x, t.y);
+          x2[2 * h + 1] = make_float2(t.z, t.w);
+        }
+#pragma unroll
+        for (int s = 0; s < NB_QT; ++s) {
+          float2 v = __fadd2_rn(x2[D], nthr2[s]);
+#pragma unroll
+          for (int j = 0; j < D; ++j) v = __ffma2_rn(nq2[s][j], x2[j], v);
+          acc[u][s] = v;
+          sign |= __float_as_uint(v.x) | __float_as_uint(v.y);
+        }
+      }
+      uint32_t hits = 0;
+      if (sign >> 31) {
+#pragma unroll
+        for (int u = 0; u < NBS_G / 2; ++u)
+#pragma unroll
+          for (int s = 0; s < NB_QT; ++s) {
+            if (!(acc[u][s].x > 0.f)) hits |= 1u << ((2 * u) * NB_QT + s);
+            if (!(acc[u][s].y > 0.f)) hits |= 1u << ((2 * u + 1) * NB_QT + s);
+          }
+      }
+      if (__any_sync(0xffffffffu, hits != 0u)) {
+        const int nh = __popc(hits);
+        if (__any_sync(0xffffffffu, qlen + nh > NBS_QCAP)) drain();
+        if (nh > NBS_QCAP) {  // more than a queue holds: evaluate this group in place
+          while (hits) {
+            const int b = __ffs(hits) - 1;
+            hits &= hits - 1;
+            if (p + (uint32_t)(b / NB_QT) < tn) exact_slot(b % NB_QT, p + (uint32_t)(b / NB_QT));
+          }
+        } else {
+          while (hits) {
+            const int b = __ffs(hits) - 1;
+            hits &= hits - 1;
+            if (p + (uint32_t)(b / NB_QT) < tn) {
+              s_q[qlen * NB_TQ] = (uint16_t)(((uint32_t)(b % NB_QT) << 12) | (p + (uint32_t)(b / NB_QT)));
+              ++qlen;
+            }
+          }
+        }
+      }
+    }
+    drain();
+  }
+  if (!FILL) {
+#pragma unroll
+    for (int s = 0; s < NB_QT; ++s)
+      if (have[s]) a.counts[w[s]] = cnt[s];
+  }
+}
+
 // row_ptr[q] = offs[q*S]
 __global__ void nb_rowptr_kernel(const uint64_t* __restrict__ offs, uint32_t nq, int S, uint64_t* __restrict__ row_ptr,
                                  unsigned long long* __restrict__ maxrow) {
@@ -773,7 +961,10 @@ static int neighbors_impl(bpomp_ctx* ctx, const uint32_t* d_query, uint32_t nq, 
   int grid = (int)std::min<uint64_t>((nw * 32 + 255) / 256, (uint64_t)ctx->num_sms * 8);
   if (grid < 1) grid = 1;
   const dim3 tgrid((unsigned)(((uint64_t)nq + NB_TQ * NB_QT - 1) / (NB_TQ * NB_QT)), (unsigned)S);
-  if (tiled) nb_tile_kernel<D, false><<<tgrid, NB_TQ, 0, ctx->stream>>>(a, g, chunk);
+  // dimensions >= 4 with a finite radius: prefilter on the FP32 pipe; else (every pair passes / low dimension) FP64
+  const bool tiled32 = tiled && D >= 4 && a.r2pad < DBL_MAX && ctx->belief_f32;
+  if (tiled32) nb_tile_kernel_f32<D, false><<<tgrid, NB_TQ, 0, ctx->stream>>>(a, g, chunk);
+  else if (tiled) nb_tile_kernel<D, false><<<tgrid, NB_TQ, 0, ctx->stream>>>(a, g, chunk);
   else nb_query_kernel<D, false><<<grid, 256, 0, ctx->stream>>>(a, g);
   ctx->launches++;
   BP_CUDA(ctx, cudaGetLastError());
@@ -800,7 +991,8 @@ static int neighbors_impl(bpomp_ctx* ctx, const uint32_t* d_query, uint32_t nq, 
   a.out_dist = ctx->d_nb_tmp.as<double>();
   a.out_id = ctx->s_f.as<uint32_t>();
   if (nnz > 0) {
-    if (tiled) nb_tile_kernel<D, true><<<tgrid, NB_TQ, 0, ctx->stream>>>(a, g, chunk);
+    if (tiled32) nb_tile_kernel_f32<D, true><<<tgrid, NB_TQ, 0, ctx->stream>>>(a, g, chunk);
+    else if (tiled) nb_tile_kernel<D, true><<<tgrid, NB_TQ, 0, ctx->stream>>>(a, g, chunk);
     else nb_query_kernel<D, true><<<grid, 256, 0, ctx->stream>>>(a, g);
     ctx->launches++;
     BP_CUDA(ctx, cudaGetLastError());

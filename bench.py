@@ -30,6 +30,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's banner (printed when NCCL_DEBUG=VERSION is exported) must not join it
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 from batching_pomp_b200 import workloads  # noqa: E402
 
@@ -506,9 +509,9 @@ def run_gpu(args):
     if world > 1:  # the library's own communicator (bpomp_comm_init_rank): the id travels through the process group
         ids = [capi.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
-        ctx.comm_init_rank(world, rank, ids[0])
-        if args.reserve_sms >= 0:
+        if args.reserve_sms >= 0:  # before the communicator exists: it also caps NCCL's CTAs
             ctx.set_option("reserve_sms", args.reserve_sms)
+        ctx.comm_init_rank(world, rank, ids[0])
 
     # pinned host copies (e2e) and device-resident copies (value)
     h_from = torch.from_numpy(frm).pin_memory()

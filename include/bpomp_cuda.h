@@ -240,7 +240,9 @@ BPOMP_API int bpomp_edges_check_sharded(bpomp_ctx* ctx, const double* from, cons
  * ranks merged in packed form (bpomp_edge_status_pack_dev layout per shard, shards in rank order:
  * d_packed_all holds nranks * ((shard_count+15)/16) words).  First-invalid slots stay with the shard owner
  * (it replays the belief inserts).  Asynchronous: the merge runs on the communicator's own stream and overlaps
- * the next batch's kernel; bpomp_comm_wait makes the ctx stream wait for it. */
+ * the next batch's kernel when consecutive calls alternate between two sets of d_packed_shard / d_packed_all
+ * buffers (a call that reuses the previous call's buffers first waits for that merge); bpomp_comm_wait makes the
+ * ctx stream wait for the last merge. */
 BPOMP_API int bpomp_edges_check_sharded_dev(bpomp_ctx* ctx, const double* d_from_shard, const double* d_to_shard,
                                             int64_t shard_count, uint8_t* d_valid_shard, int32_t* d_first_shard,
                                             uint32_t* d_nstates_shard, uint32_t* d_packed_shard,

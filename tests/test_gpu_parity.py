@@ -233,7 +233,9 @@ def test_states_valid_and_prune_parity(capi, orc, wl):
 @pytest.mark.parametrize("d,N,nq,rfun", [(2, 20000, 20000, "halton"), (7, 20000, 300, "halton"), (3, 5000, 5000, "halton"),
                                          (2, 3000, 50, "max"), (7, 2000, 20, "max"), (2, 1, 1, "halton"),
                                          # many queries in the brute-force regime -> tiled all-pairs kernel
-                                         (7, 20000, 2000, "halton"), (2, 3000, 1000, "max"), (5, 4000, 4000, "max")])
+                                         (7, 20000, 2000, "halton"), (2, 3000, 1000, "max"), (5, 4000, 4000, "max"),
+                                         # finite radius, dim >= 4: the packed-FP32 prefilter form of that kernel
+                                         (4, 30000, 3000, "halton"), (8, 5000, 1500, "halton"), (6, 777, 777, "halton")])
 def test_neighbors_parity(capi, orc, wl, d, N, nq, rfun):
     verts = wl.halton(N, d)
     r = wl.halton_radius(N, d) if rfun == "halton" else np.finfo(np.float64).max

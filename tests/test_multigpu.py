@@ -140,3 +140,50 @@ def test_sharded_device_edge_path_two_gpus(orc):
         np.testing.assert_array_equal(res[g][1], want[g][1])
     for c in ctxs:
         c.close()
+
+
+@pytest.mark.gpu
+def test_packed_status_written_by_the_edge_kernel_one_rank(orc):
+    """The sharded device path on a one-rank communicator (runs on a single GPU): the fast edge kernel writes the
+    2-bit status words itself, edges it leaves to the general kernel are patched in place, a ragged batch ends in
+    a partial word, and both buffer disciplines (alternating sets, the same set again) give the packed form of
+    exactly the status bytes — which equal the oracle's."""
+    import torch
+    from batching_pomp_b200 import capi, workloads as wl
+    d = 7
+    L = wl.segment_length(d)
+    lo, hi = wl.box_world(d, 500, seed=3)
+    ctx = capi.Context(d, L, device=0)
+    ctx.set_bounds(0.0, 1.0)
+    ctx.set_world_boxes(lo, hi)
+    capi.comm_init_all([ctx])
+    E = 100003  # not a multiple of 32: partial tile, partial word
+    frm, to = wl.random_edges(E, d, seed=4, max_len=0.35)
+    frm[::50], to[::50] = wl.random_edges(len(frm[::50]), d, seed=5, max_len=2.5)  # long edges: left to the general kernel
+    frm[7] = 1.5  # an endpoint outside the quantised zone: also the general kernel's
+    words = (E + 15) // 16
+    dev = torch.device("cuda", 0)
+    tf, tt = torch.from_numpy(frm).to(dev), torch.from_numpy(to).to(dev)
+    v = torch.empty(E, dtype=torch.uint8, device=dev)
+    f = torch.empty(E, dtype=torch.int32, device=dev)
+    n = torch.empty(E, dtype=torch.int32, device=dev)
+    sets = [(torch.full((words,), -1, dtype=torch.int32, device=dev), torch.full((words,), -1, dtype=torch.int32, device=dev))
+            for _ in range(2)]
+    want = orc.edges_check_boxes(frm, to, L, lo, hi, nthreads=orc.max_threads())
+    assert ctx.counter("fast_world") == 1
+    for k in (0, 1, 0, 0, 1):  # alternating sets, then the same set twice in a row
+        p, pa = sets[k]
+        ctx.edges_check_sharded_dev(tf.data_ptr(), tt.data_ptr(), E, v.data_ptr(), f.data_ptr(), n.data_ptr(),
+                                    p.data_ptr(), pa.data_ptr())
+        ctx.comm_wait()
+        out = torch.empty(E, dtype=torch.uint8, device=dev)
+        ctx.edge_status_unpack_dev(pa.data_ptr(), E, out.data_ptr())
+        ref = torch.empty(words, dtype=torch.int32, device=dev)
+        ctx.edge_status_pack_dev(v.data_ptr(), E, ref.data_ptr())
+        ctx.sync()
+        assert ctx.counter("slow_edges") > 1000
+        np.testing.assert_array_equal(v.cpu().numpy(), want[0])
+        np.testing.assert_array_equal(f.cpu().numpy(), want[1])
+        np.testing.assert_array_equal(out.cpu().numpy(), want[0])
+        assert torch.equal(pa, ref) and torch.equal(p, ref)  # word for word what the separate pack pass writes
+    ctx.close()
