@@ -491,6 +491,8 @@ __global__ void __launch_bounds__(NB_TQ, 4) nb_tile_kernel_f32(QueryArgs a, Grid
     o[s] = (FILL && have[s]) ? a.offs[w[s]] : 0;
     cnt[s] = 0;
   }
+  // a warp leaves a tile early only as a whole (a lane without queries keeps voting; its slots never survive)
+  const bool skip_warp = __all_sync(0xffffffffu, skip_all);
   int qlen = 0;
   auto exact = [&](int s, uint32_t t) {
     double d2 = 0.0;
@@ -552,7 +554,7 @@ __global__ void __launch_bounds__(NB_TQ, 4) nb_tile_kernel_f32(QueryArgs a, Grid
       if ((tid & 31) == 0) atomicMax(&s_pnhi, hi);
     }
     __syncthreads();
-    if (skip_all) continue;
+    if (skip_warp) continue;  // warp-uniform: the group loop below uses warp-wide votes
     // upper bound of max |p|^2: next high word (inf / NaN high words stay non-finite -> nothing is rejected)
     const double pnmax = __hiloint2double((int)(s_pnhi < 0x7ff00000u ? s_pnhi + 1u : 0x7ff80000u), 0);
 #pragma unroll
