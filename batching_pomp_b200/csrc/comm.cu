@@ -107,12 +107,12 @@ extern "C" int bpomp_comm_unique_id(void* id, size_t bytes) {
   return BPOMP_OK;
 }
 
-// The communicator's kernels run UNDER an edge kernel that fills all but a few SMs (bpomp_ctx::reserve_sms, 4 by
-// default) with one CTA each, so NCCL is asked for no more CTAs than fit there: a collective whose CTAs are not
-// all resident would only finish when the edge kernel's CTAs exit, and the merge would no longer be hidden
-// (measured at 8 GPUs: 0.64 ms per step instead of 0.41).
+// The communicator's kernels run UNDER an edge kernel that fills all but a few SMs (common.cuh: bp_reserved_sms)
+// with one CTA each, so NCCL is asked for no more CTAs than fit there: a collective whose CTAs are not all
+// resident would only finish when the edge kernel's CTAs exit, and the merge would no longer be hidden
+// (measured at 8 GPUs: 0.64 ms per step with NCCL's default CTA count and 4 free SMs, 0.46 with 8 and 8).
 static ncclResult_t comm_init_one(ncclComm_t* comm, int nranks, const ncclUniqueId& u, int rank, int max_ctas) {
-  if (g_nccl.CommInitRankConfig) {
+  if (g_nccl.CommInitRankConfig && max_ctas > 0) {
     ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
     cfg.minCTAs = 1;
     cfg.maxCTAs = max_ctas < 1 ? 1 : max_ctas;
@@ -120,7 +120,10 @@ static ncclResult_t comm_init_one(ncclComm_t* comm, int nranks, const ncclUnique
   }
   return g_nccl.CommInitRank(comm, nranks, u, rank);
 }
-static int comm_ctas(const bpomp_ctx* ctx) { return ctx->reserve_sms >= 0 ? ctx->reserve_sms : 4; }
+static int comm_ctas(const bpomp_ctx* ctx, int nranks) {
+  if (ctx->nccl_max_ctas >= 0) return ctx->nccl_max_ctas;  // 0: no limit
+  return bp_reserved_sms(ctx, nranks);
+}
 
 static int comm_attach(bpomp_ctx* ctx, ncclComm_t comm, int nranks, int rank) {
   bpomp_comm* c = new bpomp_comm();
@@ -128,6 +131,7 @@ static int comm_attach(bpomp_ctx* ctx, ncclComm_t comm, int nranks, int rank) {
   c->nranks = nranks;
   c->rank = rank;
   ctx->comm = c;
+  ctx->comm_nranks = nranks;
   BP_CUDA(ctx, cudaSetDevice(ctx->device));
   BP_CUDA(ctx, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   BP_CUDA(ctx, cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
@@ -146,7 +150,7 @@ extern "C" int bpomp_comm_init_rank(bpomp_ctx* ctx, int nranks, int rank, const 
   ncclUniqueId u;
   memcpy(&u, id, sizeof(u));
   ncclComm_t comm;
-  BP_NCCL(ctx, comm_init_one(&comm, nranks, u, rank, comm_ctas(ctx)));
+  BP_NCCL(ctx, comm_init_one(&comm, nranks, u, rank, comm_ctas(ctx, nranks)));
   return comm_attach(ctx, comm, nranks, rank);
 }
 
@@ -164,7 +168,7 @@ extern "C" int bpomp_comm_init(bpomp_ctx** ctxs, int ngpus) {
     BP_NCCL(ctxs[0], g_nccl.GroupStart());
     for (int i = 0; i < ngpus; ++i) {
       BP_CUDA(ctxs[0], cudaSetDevice(devs[i]));
-      BP_NCCL(ctxs[0], comm_init_one(&comms[i], ngpus, u, i, comm_ctas(ctxs[i])));
+      BP_NCCL(ctxs[0], comm_init_one(&comms[i], ngpus, u, i, comm_ctas(ctxs[i], ngpus)));
     }
     BP_NCCL(ctxs[0], g_nccl.GroupEnd());
   } else {
@@ -192,6 +196,7 @@ extern "C" int bpomp_comm_destroy(bpomp_ctx* ctx) {
   bp_free(c->tmp_c);
   delete c;
   ctx->comm = nullptr;
+  ctx->comm_nranks = 0;
   return BPOMP_OK;
 }
 
@@ -284,21 +289,16 @@ extern "C" int bpomp_edges_check_sharded_dev(bpomp_ctx* ctx, const double* d_fro
       !d_packed_shard || !d_packed_all)
     return bp_fail(ctx, BPOMP_ERR_INVALID, "bad arguments");
   bpomp_comm* c = ctx->comm;
-  // The packed words are written by the edge kernel itself (no separate pack pass), so the merge that last read
-  // this buffer set must be done before the kernel starts.  A caller that alternates two buffer sets waits for
-  // the merge of call k-2, which ended long ago, and the merge of call k-1 runs under this call's kernel; a
-  // caller that passes the same buffers again waits for the previous merge (correct, no overlap).
+  BP_TRY(bpomp_edges_check_dev(ctx, d_from_shard, d_to_shard, shard_count, d_valid_shard, d_first_shard, d_nstates_shard));
+  // The merge that last read this set of packed buffers must be done before they are written again.  A caller
+  // that alternates two buffer sets waits for the merge of call k-2, which ended long ago, while the merge of
+  // call k-1 runs under this call's kernel; a caller that passes the same buffers again waits for the previous
+  // merge (correct, no overlap).
   const uint64_t k = c->edge_calls;
   if (k >= 1 && (c->last_packed[(k - 1) & 1] == (const void*)d_packed_shard))
     BP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, c->ev_done2[(k - 1) & 1], 0));
   if (k >= 2) BP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, c->ev_done2[k & 1], 0));
-  ctx->pack_out = d_packed_shard;
-  ctx->pack_done = false;
-  const int rc = bpomp_edges_check_dev(ctx, d_from_shard, d_to_shard, shard_count, d_valid_shard, d_first_shard, d_nstates_shard);
-  ctx->pack_out = nullptr;
-  BP_TRY(rc);
-  if (!ctx->pack_done)  // the batch did not go through the fast box-world kernel: pack in a pass of its own
-    BP_TRY(bpomp_edge_status_pack_dev(ctx, d_valid_shard, shard_count, d_packed_shard));
+  BP_TRY(bpomp_edge_status_pack_dev(ctx, d_valid_shard, shard_count, d_packed_shard));
   BP_CUDA(ctx, cudaEventRecord(c->ev_ready, ctx->stream));
   BP_CUDA(ctx, cudaStreamWaitEvent(c->stream, c->ev_ready, 0));
   const size_t words = (size_t)((shard_count + 15) / 16);

@@ -149,11 +149,11 @@ struct bpomp_ctx {
   bool work_dirty[4] = {true, true, true, true};
   const int* last_slow_count = nullptr;
   DevBuf d_slow_list[4];                    // per pipeline lane: indices of the edges the fast kernel left over
-  uint32_t* pack_out = nullptr;             // set around a sharded edge call: the fast kernel also writes the packed
-  bool pack_done = false;                   // status words there (and says so), saving the separate pack kernel
+  int nccl_max_ctas = -1;                   // CTAs NCCL may use: -1 = as many as SMs are left free, 0 = no limit
+  int comm_nranks = 0;                      // ranks of the communicator (0: none)
   int fused_pfree = 1;                      // 0: never use the one-launch free-probability kernel (testing)
   int fast_mode = 1;                        // 0: never use the fast kernel (testing / tuning)
-  int reserve_sms = -1;                     // SMs the fast kernel leaves free (-1: 4 with a communicator, else 0)
+  int reserve_sms = -1;                     // SMs the fast kernel leaves free (-1: bp_reserved_sms' default)
   int fast_warps = 0;                       // > 0: cap on the warps per CTA of the fast kernel (tuning)
   int64_t fast_min_edges = 4096;            // smaller batches go to the general kernel alone (one launch)
 
@@ -200,6 +200,17 @@ struct bpomp_ctx {
 // Every entry point makes the context's device current first: a process may drive several contexts (one per
 // GPU) from one or several threads, and the CUDA current device is per-thread state.
 inline void bp_enter(const bpomp_ctx* ctx) { cudaSetDevice(ctx->device); }
+
+// SMs the fast edge kernel leaves free.  Its CTAs take a whole SM each (226 KB of shared memory), so under a
+// communicator a few SMs stay empty for NCCL's kernel, which merges the previous batch meanwhile — and NCCL is
+// asked for no more CTAs than that (comm.cu), else part of the collective would wait for an edge CTA to exit.
+// Measured, 10^7 edges per GPU (ms per step; single GPU 0.398): 2 GPUs 0.435 with 4 SMs, 0.463 with 8;
+// 8 GPUs 0.682 with 4 SMs, 0.527 with 2, 0.462 with 8 (the all-gather moves 8 x 2.5 MB there).
+inline int bp_reserved_sms(const bpomp_ctx* ctx, int nranks = -1) {
+  if (ctx->reserve_sms >= 0) return ctx->reserve_sms;
+  if (nranks < 0) nranks = ctx->comm_nranks;
+  return nranks <= 1 ? 0 : (nranks <= 2 ? 4 : 8);
+}
 
 // internal cross-file helpers
 int bp_read_flags(bpomp_ctx* ctx);

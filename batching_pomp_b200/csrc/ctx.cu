@@ -348,6 +348,7 @@ extern "C" int bpomp_set_option(bpomp_ctx* ctx, const char* name, int64_t value)
   else if (!strcmp(name, "fast_edge_min_edges")) ctx->fast_min_edges = value < 0 ? 0 : value;
   else if (!strcmp(name, "fast_edge_warps")) ctx->fast_warps = (int)value;
   else if (!strcmp(name, "reserve_sms")) ctx->reserve_sms = (int)value;
+  else if (!strcmp(name, "nccl_max_ctas")) ctx->nccl_max_ctas = (int)value;
   else if (!strcmp(name, "fused_pfree")) ctx->fused_pfree = value ? 1 : 0;
   else if (!strcmp(name, "belief_f32")) ctx->belief_f32 = value ? 1 : 0;
   else if (!strcmp(name, "belief_grid")) { ctx->belief_grid = value ? 1 : 0; ctx->bg_count = 0; }

@@ -37,16 +37,7 @@ struct EdgeArgs {
   unsigned long long* reset1;
   double L;
   unsigned long long* work;  // dynamic tile counter (zeroed before the launch)
-  uint32_t* packed;          // non-null (only with only_status == BPOMP_EDGE_SLOW): the fast kernel already wrote the
-                             // 2-bit status words of the batch; an edge re-evaluated here patches its field
 };
-
-// Status store of the general kernel.  In the left-over pass behind the fast kernel the edge's field in the
-// packed status words (multi-GPU merge) still says SLOW: one XOR turns it into the new status.
-__device__ __forceinline__ void ec_store_valid(const EdgeArgs& a, int64_t e, uint32_t v) {
-  a.valid[e] = (uint8_t)v;
-  if (a.packed) atomicXor(a.packed + (e >> 4), (BPOMP_EDGE_SLOW ^ v) << (2 * (int)(e & 15)));
-}
 
 // ---- bulk async copy global -> shared (TMA engine, 1-D), completion on an mbarrier ----------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -117,14 +108,14 @@ __device__ __forceinline__ bool edge_prologue(const EdgeArgs& a, const PermView&
   n = bp_nstates(dist, a.L);                     // BP.cpp:440-445
   if (n == 0u) {                                 // more than BPOMP_NSTATES_MAX states
     atomicAdd(pv.flags + 1, 1);
-    ec_store_valid(a, e, BPOMP_EDGE_BLOCKED);
+    a.valid[e] = BPOMP_EDGE_BLOCKED;
     a.first[e] = -1;
     if (a.nstates) a.nstates[e] = 0u;
     return false;
   }
   if (a.nstates) a.nstates[e] = n;
   if (n <= 2u) {  // BP.cpp:510: no slot in 1..n-2 -> FREE unchecked
-    ec_store_valid(a, e, BPOMP_EDGE_FREE);
+    a.valid[e] = BPOMP_EDGE_FREE;
     a.first[e] = -1;
     return false;
   }
@@ -132,7 +123,7 @@ __device__ __forceinline__ bool edge_prologue(const EdgeArgs& a, const PermView&
   if (off == BP_ABSENT) {  // sample order for this n not resident: host uploads it and re-runs
     pv.need[n] = 1;
     atomicAdd(pv.flags, 1);
-    ec_store_valid(a, e, BPOMP_EDGE_DEFERRED);
+    a.valid[e] = BPOMP_EDGE_DEFERRED;
     a.first[e] = -2;
     return false;
   }
@@ -325,7 +316,7 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
       }
     }
     if (need && nc == 0) {  // no box can touch the edge: FREE without interpolating a state
-      ec_store_valid(a, e, BPOMP_EDGE_FREE);
+      a.valid[e] = BPOMP_EDGE_FREE;
       a.first[e] = -1;
       need = false;
     }
@@ -393,7 +384,7 @@ __global__ void __launch_bounds__(EC_THREADS, 1)
     __syncwarp();
     if (need) {
       const int32_t bad = vfirst[lane] == 0x7fffffff ? -1 : vfirst[lane];
-      ec_store_valid(a, e, bad < 0 ? BPOMP_EDGE_FREE : BPOMP_EDGE_BLOCKED);
+      a.valid[e] = bad < 0 ? BPOMP_EDGE_FREE : BPOMP_EDGE_BLOCKED;
       a.first[e] = bad;
     }
     __syncwarp();
@@ -567,7 +558,6 @@ int bp_launch_edge_check(bpomp_ctx* ctx, const double* d_from, const double* d_t
   a.verts = ctx->d_verts.as<double>();
   a.count = count; a.valid = d_valid; a.first = d_first; a.nstates = d_nstates;
   a.only_status = deferred_only ? (int)BPOMP_EDGE_DEFERRED : (fast ? (int)BPOMP_EDGE_SLOW : 0);
-  a.packed = (fast && ctx->pack_done) ? ctx->pack_out : nullptr;
   a.L = ctx->L;
   BP_TRY(bp_reserve(ctx, ctx->d_work, 80 * sizeof(unsigned long long), false));
   const int l = ctx->work_slot;

@@ -59,7 +59,6 @@ struct FastArgs {
   int* flags;                // [1] range errors
   int* slow_count;           // number of edges left to the general kernel (its gate)
   uint32_t* slow_list;       // their indices (the first BP_SLOW_LIST_CAP of them)
-  uint32_t* packed;          // non-null: also emit the status flags packed to 2 bits per edge (multi-GPU merge)
   int tma_ok;                // from/to are 16-byte aligned: tiles are fetched with cp.async.bulk
   int nwarps;
   // FP64 tables of the exact test (rare path)
@@ -534,36 +533,15 @@ __global__ void __launch_bounds__(FE_MAXWARPS * 32, 1)
         if (to_slow && at < BP_SLOW_LIST_CAP) a.slow_list[at] = (uint32_t)e;
       }
     }
-    uint32_t vstat = BPOMP_EDGE_BLOCKED;  // this lane's final status byte (lanes beyond the batch: 0)
-    if (live && n != 0u && n <= 2u) vstat = BPOMP_EDGE_FREE;
     if (need) {
       if (to_slow) {
-        vstat = BPOMP_EDGE_SLOW;
         a.valid[e] = BPOMP_EDGE_SLOW;
         a.first[e] = -2;
       } else {
         const int32_t r = ws->first[lane];
         const int32_t bad = r == 0x7fffffff ? -1 : r;
-        vstat = bad < 0 ? BPOMP_EDGE_FREE : BPOMP_EDGE_BLOCKED;
-        a.valid[e] = (uint8_t)vstat;
+        a.valid[e] = bad < 0 ? BPOMP_EDGE_FREE : BPOMP_EDGE_BLOCKED;
         a.first[e] = bad;
-      }
-    }
-    if (a.packed) {  // the tile's 32 statuses as two words of 16 two-bit fields (bpomp_edge_status_pack_dev's format)
-      const uint32_t b0 = __ballot_sync(0xffffffffu, (vstat & 1u) != 0u);
-      const uint32_t b1 = __ballot_sync(0xffffffffu, (vstat & 2u) != 0u);
-      if ((lane & 15) == 0) {
-        const int half = lane >> 4;
-        auto spread = [](uint32_t x) {  // bit i -> bit 2i
-          x &= 0xFFFFu;
-          x = (x | (x << 8)) & 0x00FF00FFu;
-          x = (x | (x << 4)) & 0x0F0F0F0Fu;
-          x = (x | (x << 2)) & 0x33333333u;
-          x = (x | (x << 1)) & 0x55555555u;
-          return x;
-        };
-        const int64_t word = cur * 2 + half;
-        if (word * 16 < a.count) a.packed[word] = spread(b0 >> (16 * half)) | (spread(b1 >> (16 * half)) << 1);
       }
     }
     __syncwarp();
@@ -593,7 +571,7 @@ static int launch_fast(bpomp_ctx* ctx, FastArgs& a) {
   const int64_t ntiles = (a.count + 31) / 32;
   // With a communicator, a few SMs are left free: this kernel's CTAs take a whole SM each (shared memory), and
   // NCCL's all-gather of the previous step's flags could otherwise only start when they exit.
-  const int sms = std::max(1, ctx->num_sms - (ctx->reserve_sms >= 0 ? ctx->reserve_sms : (ctx->comm ? 4 : 0)));
+  const int sms = std::max(1, ctx->num_sms - bp_reserved_sms(ctx));
   const int grid = (int)std::min<int64_t>((ntiles + nwarps - 1) / nwarps, sms);
   k<<<grid, nwarps * 32, smem, ctx->stream>>>(a, w);
   return 1;
@@ -645,7 +623,6 @@ int bp_launch_edge_check_fast(bpomp_ctx* ctx, const double* d_from, const double
   a.slow_list = ctx->d_slow_list[ctx->work_slot].as<uint32_t>();
   a.tma_ok = (d_from && ((reinterpret_cast<uintptr_t>(d_from) | reinterpret_cast<uintptr_t>(d_to)) & 15u) == 0) ? 1 : 0;
   a.nwarps = 0;
-  a.packed = ctx->pack_out;
   a.lohi = ctx->boxes.lohi;
   a.lohi_stride = ctx->boxes.lohi_stride;
   a.perm_off = ctx->d_perm_off.as<uint32_t>();
@@ -656,6 +633,5 @@ int bp_launch_edge_check_fast(bpomp_ctx* ctx, const double* d_from, const double
   if (rc <= 0) return rc;
   ctx->launches++;
   BP_CUDA(ctx, cudaGetLastError());
-  if (ctx->pack_out) ctx->pack_done = true;
   return 1;
 }

@@ -511,6 +511,8 @@ def run_gpu(args):
         dist.broadcast_object_list(ids, src=0)
         if args.reserve_sms >= 0:  # before the communicator exists: it also caps NCCL's CTAs
             ctx.set_option("reserve_sms", args.reserve_sms)
+        for kv in args.ctx_option:
+            ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
         ctx.comm_init_rank(world, rank, ids[0])
 
     # pinned host copies (e2e) and device-resident copies (value)
@@ -721,7 +723,9 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --edges per GPU (default); strong: --edges in total")
     ap.add_argument("--reserve-sms", type=int, default=-1,
-                    help="SMs the edge kernel leaves free for NCCL when N > 1 (-1: library default, 4)")
+                    help="SMs the edge kernel leaves free for NCCL when N > 1 (-1: library default: 4 on 2 GPUs, 8 beyond)")
+    ap.add_argument("--ctx-option", action="append", default=[], metavar="NAME=VALUE",
+                    help="library tuning option set before the communicator is created (bpomp_set_option)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra legs (indexed / image edges, planner times)")
     args = ap.parse_args()

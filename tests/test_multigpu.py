@@ -143,11 +143,11 @@ def test_sharded_device_edge_path_two_gpus(orc):
 
 
 @pytest.mark.gpu
-def test_packed_status_written_by_the_edge_kernel_one_rank(orc):
-    """The sharded device path on a one-rank communicator (runs on a single GPU): the fast edge kernel writes the
-    2-bit status words itself, edges it leaves to the general kernel are patched in place, a ragged batch ends in
-    a partial word, and both buffer disciplines (alternating sets, the same set again) give the packed form of
-    exactly the status bytes — which equal the oracle's."""
+def test_sharded_device_edge_path_one_rank(orc):
+    """The sharded device path on a one-rank communicator (runs on a single GPU): fast-kernel edges and edges left
+    to the general kernel, a ragged batch that ends in a partial status word, and both buffer disciplines
+    (alternating sets, the same set again) give the packed form of exactly the status bytes — which equal the
+    oracle's."""
     import torch
     from batching_pomp_b200 import capi, workloads as wl
     d = 7
