@@ -3,12 +3,17 @@
 // beliefDistanceFunction src/BatchingPOMP.cpp:213-219) and computeAndSetEdgeFreeProbability
 // (src/BatchingPOMP.cpp:464-493) as batched device operators.
 //
-// kNN is exact brute force over the append-only point set, tiled through shared memory:
-// one thread per query, a (distance, insertion index)-ordered top-k list per thread in shared
-// memory, the point set split into chunks across blocks and merged afterwards.  Ordering and
-// summation are sequential in ascending (distance, insertion index), as the CPU oracle defines
-// them, so results are bit-equal to the oracle and within 1e-12 relative of
-// the reference's Eigen-packetised sums.
+// Exact kNN over the append-only point set, three ways:
+//   * dim <= 3: a Morton-ordered grid used as an implicit quadtree / octree, a warp per query with the k best in
+//     registers (belief_grid.cuh); rebuilt incrementally as the model grows;
+//   * dim >= 4, large batches: brute force tiled through shared memory with a packed-FP32 prefilter and deferred
+//     insertion (bk_knn_partial_f32); one thread per query slot, a (distance, insertion index)-ordered top-k list
+//     per query in shared memory, the point set split into chunks across blocks and merged afterwards;
+//   * small batches (the planner's per-expansion calls): one launch, a block per edge, a warp per query
+//     (bk_pfree_fused), through the index where there is one.
+// Ordering and summation are sequential in ascending (distance, insertion index), as the CPU oracle defines
+// them, so results are bit-equal to the oracle and within 1e-12 relative of the
+// reference's Eigen-packetised sums (checked against the reference's own KNNModel, tests/test_oracle_vs_reference.py).
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
