@@ -99,11 +99,23 @@ __device__ __forceinline__ void load_endpoints(const EdgeArgs& a, int64_t e, dou
 }
 
 // Phase A shared by both worlds.  Returns false when the edge is already decided (outputs written).
+template <int D>
+__device__ __forceinline__ bool edge_prologue_loaded(const EdgeArgs& a, const PermView& pv, int64_t e, const double* f,
+                                                     const double* t, uint32_t& n, uint32_t& off, int only_status);
+
 template <int D, bool INDEXED>
 __device__ __forceinline__ bool edge_prologue(const EdgeArgs& a, const PermView& pv, int64_t e, double* f, double* t,
                                               uint32_t& n, uint32_t& off, int only_status) {
   if (only_status && a.valid[e] != (uint8_t)only_status) return false;
   load_endpoints<D, INDEXED>(a, e, f, t);
+  return edge_prologue_loaded<D>(a, pv, e, f, t, n, off, 0);
+}
+
+// The same with the endpoints already in registers (the image kernel fetches them one round ahead).
+template <int D>
+__device__ __forceinline__ bool edge_prologue_loaded(const EdgeArgs& a, const PermView& pv, int64_t e, const double* f,
+                                                     const double* t, uint32_t& n, uint32_t& off, int only_status) {
+  if (only_status && a.valid[e] != (uint8_t)only_status) return false;
   double dist = __dsqrt_rn(bp_dist2<D>(f, t));  // BP.cpp:163 distance(source, target)
   n = bp_nstates(dist, a.L);                     // BP.cpp:440-445
   if (n == 0u) {                                 // more than BPOMP_NSTATES_MAX states
@@ -413,11 +425,38 @@ __global__ void __launch_bounds__(EC_IMG_THREADS) edge_check_image_kernel(EdgeAr
   const unsigned char* winb = reinterpret_cast<const unsigned char*>(win);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t rounds = (a.count + stride - 1) / stride;
+  const int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // Software pipeline over the rounds: the endpoints of round r+1 (and, for indexed endpoints, the ids of round
+  // r+2 they are gathered with) are requested before round r is evaluated, so the dependent id -> vertex-table
+  // loads are in flight during a whole round of arithmetic instead of being waited for at its start.
+  uint32_t idf = 0, idt = 0;  // ids of the round after next (indexed form)
+  double nf[2] = {0.0, 0.0}, nt[2] = {0.0, 0.0};  // endpoints of the next round
+  auto fetch_ids = [&](int64_t e) {
+    if (INDEXED && e < a.count) {
+      idf = __ldg(a.from_ids + e);
+      idt = __ldg(a.to_ids + e);
+    }
+  };
+  auto fetch_endpoints = [&](int64_t e) {  // uses idf / idt fetched for this very edge
+    if (e < a.count) {
+      const double* pf = INDEXED ? a.verts + (size_t)idf * 2 : a.from + (size_t)e * 2;
+      const double* pt = INDEXED ? a.verts + (size_t)idt * 2 : a.to + (size_t)e * 2;
+      const double2 vf = __ldg(reinterpret_cast<const double2*>(pf));
+      const double2 vt = __ldg(reinterpret_cast<const double2*>(pt));
+      nf[0] = vf.x; nf[1] = vf.y;
+      nt[0] = vt.x; nt[1] = vt.y;
+    }
+  };
+  fetch_ids(e0);
+  fetch_endpoints(e0);
+  fetch_ids(e0 + stride);
   for (int64_t rd = 0; rd < rounds; ++rd) {  // warp-uniform trip count: the lanes of a warp stay together
-    const int64_t e = rd * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double f[2] = {0.0, 0.0}, t[2] = {0.0, 0.0};
+    const int64_t e = rd * stride + e0;
+    const double f[2] = {nf[0], nf[1]}, t[2] = {nt[0], nt[1]};
+    fetch_endpoints(e + stride);   // round rd+1, with the ids requested a round ago
+    fetch_ids(e + 2 * stride);     // round rd+2
     uint32_t n = 0, off = 0;
-    const bool need = e < a.count && edge_prologue<2, INDEXED>(a, pv, e, f, t, n, off, a.only_status);
+    const bool need = e < a.count && edge_prologue_loaded<2>(a, pv, e, f, t, n, off, a.only_status);
     const double d0 = __dsub_rn(t[0], f[0]), d1 = __dsub_rn(t[1], f[1]);
     const double* tf = pv.tfrac + off;
     int32_t bad = 0x7fffffff;
