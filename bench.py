@@ -684,6 +684,20 @@ def run_gpu(args):
                     traffic_src = "no ncu capture of kernel build '%s' at %d edges/launch committed" % (KERNEL_TAG, int(edges_per_launch))
             except Exception:
                 traffic = None
+        # second ceiling (SURVEY.md 8d asks for the ALU one beside HBM): the kernel is instruction-issue bound, so the
+        # floor is its warp instructions (same ncu capture as `traffic`) at one instruction per scheduler per cycle
+        issue = None
+        try:
+            if traffic is not None and rec.get("warp_instructions_per_launch"):
+                import torch as _t
+                prop = _t.cuda.get_device_properties(dev)
+                sm_hz = (sampler.summary().get("sm_mhz") or sampler.max_mhz or 1965) * 1e6
+                floor_ms = rec["warp_instructions_per_launch"] / (prop.multi_processor_count * 4 * sm_hz) * 1e3
+                issue = {"warp_instructions_per_edge": rec["warp_instructions_per_launch"] / edges_per_launch,
+                         "floor_ms_per_launch": floor_ms, "frac": floor_ms / avg_launch_ms,
+                         "how": "smsp__inst_executed.sum of the committed capture / (SMs x 4 schedulers x SM clock)"}
+        except Exception:
+            issue = None
         value = world * E * args.steps / (elapsed_ms * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -696,7 +710,7 @@ def run_gpu(args):
                          "algorithmic_bytes_per_edge": ALGO_BYTES_PER_EDGE,
                          "kernel": "edge_check_fast_kernel<7,false> (+ the general kernel's launch for left-over edges: "
                                    "none on this workload, its CTAs exit at once)",
-                         "avg_launch_ms": avg_launch_ms,
+                         "avg_launch_ms": avg_launch_ms, "issue_ceiling": issue,
                          "note": "instruction-issue bound (DESIGN.md 4.1): ~32 warp instructions per edge at ~70% of the "
                                  "issue slots, shared-memory wavefronts ~64% of peak; DRAM at ~45% of the measured copy peak"},
             "e2e": {"value": world * E * e2e_steps / e2e_s, "unit": UNIT,
