@@ -888,7 +888,7 @@ static int knn_estimate_dev(bpomp_ctx* ctx, const double* d_queries, int64_t nq,
   uint64_t chunk = M ? M : 1;
   if (M > 0) {
     // dimensions >= 4: prefilter on the FP32 pipe, BKS_QT queries per thread; else the FP64 prefilter
-    const bool f32 = D >= 4 && ctx->belief_f32;
+    const bool f32 = D >= 4 && ctx->prefilter_f32;
     const int qt = f32 ? BKS_QT : BK_QT;
     int64_t qblocks = (nq + BK_QB * qt - 1) / (BK_QB * qt);
     int64_t want = 2 * (int64_t)ctx->num_sms;

@@ -183,7 +183,7 @@ struct bpomp_ctx {
   uint64_t bg_count = 0;
   uint32_t bg_bits = 0;
   uint64_t bg_builds = 0;
-  int belief_f32 = 1;                       // 0: FP64 prefilter in the brute-force kNN for every dimension (testing)
+  int prefilter_f32 = 1;                    // 0: FP64 prefilter in the tiled kNN / neighbour kernels for every dimension (testing)
   int belief_grid = 1;                      // 0: always scan the whole model (testing)
 
   // pipelined host-buffer edge checks (edge_check.cu)

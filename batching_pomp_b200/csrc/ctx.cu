@@ -350,7 +350,7 @@ extern "C" int bpomp_set_option(bpomp_ctx* ctx, const char* name, int64_t value)
   else if (!strcmp(name, "reserve_sms")) ctx->reserve_sms = (int)value;
   else if (!strcmp(name, "nccl_max_ctas")) ctx->nccl_max_ctas = (int)value;
   else if (!strcmp(name, "fused_pfree")) ctx->fused_pfree = value ? 1 : 0;
-  else if (!strcmp(name, "belief_f32")) ctx->belief_f32 = value ? 1 : 0;
+  else if (!strcmp(name, "fp32_prefilter")) ctx->prefilter_f32 = value ? 1 : 0;
   else if (!strcmp(name, "belief_grid")) { ctx->belief_grid = value ? 1 : 0; ctx->bg_count = 0; }
   else return bp_fail(ctx, BPOMP_ERR_INVALID, "unknown option '%s'", name);
   return BPOMP_OK;

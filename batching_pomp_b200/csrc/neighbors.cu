@@ -964,7 +964,7 @@ static int neighbors_impl(bpomp_ctx* ctx, const uint32_t* d_query, uint32_t nq, 
   if (grid < 1) grid = 1;
   const dim3 tgrid((unsigned)(((uint64_t)nq + NB_TQ * NB_QT - 1) / (NB_TQ * NB_QT)), (unsigned)S);
   // dimensions >= 4 with a finite radius: prefilter on the FP32 pipe; else (every pair passes / low dimension) FP64
-  const bool tiled32 = tiled && D >= 4 && a.r2pad < DBL_MAX && ctx->belief_f32;
+  const bool tiled32 = tiled && D >= 4 && a.r2pad < DBL_MAX && ctx->prefilter_f32;
   if (tiled32) nb_tile_kernel_f32<D, false><<<tgrid, NB_TQ, 0, ctx->stream>>>(a, g, chunk);
   else if (tiled) nb_tile_kernel<D, false><<<tgrid, NB_TQ, 0, ctx->stream>>>(a, g, chunk);
   else nb_query_kernel<D, false><<<grid, 256, 0, ctx->stream>>>(a, g);

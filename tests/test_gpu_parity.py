@@ -437,6 +437,40 @@ def test_indexed_edges_reject_bad_vertex_ids(capi, orc, wl):
     ctx.close()
 
 
+@pytest.mark.parametrize("d,K,M,nq", [(7, 15, 30000, 2500), (4, 32, 9000, 700), (8, 1, 20000, 1300), (5, 15, 300, 600)])
+def test_fp32_prefilter_paths_equal_fp64_and_oracle(capi, orc, wl, d, K, M, nq):
+    """dim >= 4: the packed-FP32 prefilter forms of the tiled kNN and neighbour kernels against their FP64-prefilter
+    forms and the oracle — bit for bit; duplicates (ties by insertion index), queries on points, ragged tiles."""
+    L = wl.segment_length(d)
+    pts = wl.uniform(81, (M, d))
+    pts[M // 2: M // 2 + M // 8] = pts[: M // 8]
+    vals = (wl.uniform(82, (M,)) < 0.35).astype(np.float64)
+    q = wl.uniform(83, (nq, d))
+    q[:100] = pts[:100]
+    want = orc.belief_estimate(pts, vals, q, K=K, nthreads=orc.max_threads())
+    r = 0.9 * wl.halton_radius(M, d)
+    qid = np.arange(0, M, max(1, M // 1100), dtype=np.uint32)
+    rows = None
+    for f32 in (1, 0):
+        ctx = capi.Context(d, L)
+        ctx.set_option("fp32_prefilter", f32)
+        ctx.belief_config(K, 0.5, 0.25)
+        ctx.belief_append(pts, vals)
+        np.testing.assert_array_equal(ctx.belief_estimate(q), want)
+        ctx.vertices_append(pts)
+        got = ctx.neighbors_radius(qid, r)
+        if rows is None:
+            rows = got
+            orp, ocol, odist = orc.neighbors_radius(pts, qid, r, nthreads=orc.max_threads())
+            np.testing.assert_array_equal(got[0], orp)
+            np.testing.assert_array_equal(got[1], ocol)
+            np.testing.assert_array_equal(got[2], odist)
+        else:
+            for a, b in zip(rows, got):
+                np.testing.assert_array_equal(a, b)
+        ctx.close()
+
+
 def _clustered_points(wl, d, M, seed):
     """Belief-like point sets: states strung along segments (checked edges), plus duplicates and a far outlier."""
     rng = np.random.default_rng(seed)
