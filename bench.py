@@ -11,12 +11,19 @@ One "step" = one pass of the hot path (checkAndSetEdgeBlocked's isValid loop,
   value        edge checks / s, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e          the same through the host-buffer C-ABI call bpomp_edges_check (pinned host inputs,
                H2D + kernel + D2H inside the timed region)
-  roofline     117 algorithmic bytes per edge (2*7*8 in + 1 + 4 out) / kernel time
-  cpu_baseline the CPU oracle (port of the reference loop) on all host cores, bounded sample
+  roofline     117 algorithmic bytes per edge (2*7*8 in + 1 + 4 out) / kernel time, the DRAM
+               traffic and the issue-slot ceiling from the committed ncu capture of the same kernel build
+  cpu_baseline the reference's own edge code (oracle/_ref, compiled from /root/reference) on all host cores,
+               bounded sample; the oracle port where that build is absent.  The GPU results are compared with
+               both in the run (exit code 3 on a mismatch, before any number is printed)
+  extra        N = 1: indexed box edges (config 3 rows), image edges (config 2), time to first / best path of
+               the planner for configs 1-3 beside the CPU oracle planner; N > 1: host-link roof with all ranks
+               copying, indexed end-to-end leg
 
 N > 1 (torchrun, one rank per GPU): every rank evaluates its own 10^7-edge shard (weak scaling, world
-replicated) and the edge status flags are merged with an NCCL all-gather that overlaps the next
-step's kernel.  --impl reference times the CPU oracle only (rank 0).
+replicated; --scaling strong splits 10^7 edges) through the library's communicator (bpomp_comm_init_rank): the
+edge status flags are packed to 2 bits and merged with an NCCL all-gather that overlaps the next step's kernel.
+--impl reference times the CPU arm only (rank 0; the other ranks exit at once).
 """
 import argparse
 import json
