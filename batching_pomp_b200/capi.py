@@ -39,6 +39,7 @@ SIGNATURES = {
     "bpomp_states_valid_dev": (C.c_int, [vp, vp, C.c_int64, vp]),
     "bpomp_states_prune": (C.c_int, [vp, vp, C.c_int64, vp, vp, C.c_double, C.c_int, vp]),
     "bpomp_vertices_prune": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_double, C.c_int, vp]),
+    "bpomp_roadmap_generate": (C.c_int, [vp, C.c_int, C.c_uint64, C.c_uint32, vp]),
     "bpomp_vertices_append": (C.c_int, [vp, vp, C.c_uint32, c_u32p]),
     "bpomp_vertices_set_active": (C.c_int, [vp, vp, C.c_uint32, C.c_int]),
     "bpomp_vertices_count": (C.c_int, [vp, c_u32p]),
@@ -206,6 +207,14 @@ class Context:
         return out
 
     # ---- vertices / neighbours -----------------------------------------------------------
+    def roadmap_generate(self, kind, first, count):
+        """Roadmap states generated on the device: kind "halton" (first = 1-based index of the first point) or
+        "uniform" (first = splitmix64 seed); bit-equal to workloads.halton / workloads.uniform."""
+        out = np.empty((int(count), self.dim), dtype=np.float64)
+        k = {"halton": 0, "uniform": 1}[kind]
+        self._ck(self.lib.bpomp_roadmap_generate(self.h, k, int(first), int(count), _ptr(out)))
+        return out
+
     def vertices_append(self, states):
         s = _f64(states).reshape(-1, self.dim)
         first = C.c_uint32(0)

@@ -387,6 +387,59 @@ extern "C" void* bpomp_get_stream(bpomp_ctx* ctx) { return ctx ? (void*)ctx->str
 extern "C" uint64_t bpomp_launch_count(const bpomp_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // ---------------------------------------------------------------------------
+// roadmap generation: the two sample sequences of this project, same arithmetic as
+// oracle/bpomp_oracle.cpp: orc_halton and batching_pomp_b200/workloads.py: uniform
+// ---------------------------------------------------------------------------
+__constant__ int c_primes[16] = {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53};
+
+__global__ void __launch_bounds__(256) roadmap_generate_kernel(int kind, unsigned long long first, uint32_t count,
+                                                               int dim, double* __restrict__ out) {
+  const uint64_t total = (uint64_t)count * dim;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t k = t / dim;
+    const int j = (int)(t - k * dim);
+    double r;
+    if (kind == BPOMP_ROADMAP_HALTON) {
+      unsigned long long idx = first + k;
+      const unsigned long long p = (unsigned long long)c_primes[j];
+      const double base = (double)c_primes[j];
+      double f = 1.0;
+      r = 0.0;
+      while (idx > 0) {
+        f = __ddiv_rn(f, base);
+        r = __dadd_rn(r, __dmul_rn(f, (double)(idx % p)));
+        idx /= p;
+      }
+    } else {
+      unsigned long long z = first + (t + 1ull) * 0x9E3779B97F4A7C15ull;
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+      z = z ^ (z >> 31);
+      r = __dmul_rn((double)(z >> 11), 1.0 / 9007199254740992.0);  // 53 bits: exact
+    }
+    out[t] = r;
+  }
+}
+
+extern "C" int bpomp_roadmap_generate(bpomp_ctx* ctx, int kind, uint64_t first, uint32_t count, double* host_out) {
+  if (!ctx) return BPOMP_ERR_INVALID;
+  bp_enter(ctx);
+  if (kind != BPOMP_ROADMAP_HALTON && kind != BPOMP_ROADMAP_UNIFORM) return bp_fail(ctx, BPOMP_ERR_INVALID, "unknown roadmap kind %d", kind);
+  if (count == 0) return BPOMP_OK;
+  if (!host_out) return bp_fail(ctx, BPOMP_ERR_INVALID, "host_out is NULL");
+  if (kind == BPOMP_ROADMAP_HALTON && ctx->dim > 16) return bp_fail(ctx, BPOMP_ERR_RANGE, "Halton roadmaps are defined for dim <= 16");
+  const size_t bytes = (size_t)count * ctx->dim * sizeof(double);
+  BP_TRY(bp_reserve(ctx, ctx->s_a, bytes, false));
+  const int grid = (int)std::min<uint64_t>(((uint64_t)count * ctx->dim + 255) / 256, (uint64_t)ctx->num_sms * 16);
+  roadmap_generate_kernel<<<grid, 256, 0, ctx->stream>>>(kind, first, count, ctx->dim, ctx->s_a.as<double>());
+  ctx->launches++;
+  BP_CUDA(ctx, cudaGetLastError());
+  BP_CUDA(ctx, cudaMemcpyAsync(host_out, ctx->s_a.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  BP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return BPOMP_OK;
+}
+
+// ---------------------------------------------------------------------------
 // vertex table
 // ---------------------------------------------------------------------------
 extern "C" int bpomp_vertices_append(bpomp_ctx* ctx, const double* states, uint32_t count, uint32_t* first_id) {

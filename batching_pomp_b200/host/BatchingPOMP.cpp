@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 
 #include <map>
@@ -379,6 +380,24 @@ void BatchingPOMP::setup() {
       throw Exception("Invalid graph type specified! Graph type needed for hybrid or edge batching!");
   }
   if (mRoadmapName == "") throw Exception("Roadmap name must be set before creating batching manager!");
+  if (mN == 0 && (mRoadmapName.rfind("halton:", 0) == 0 || mRoadmapName.rfind("uniform:", 0) == 0)) {
+    // B200 extension: "halton:<N>" / "uniform:<seed>:<N>" name a roadmap of this project's two
+    // sample sequences; its states are generated on the device (bpomp_roadmap_generate), bit-equal to the GraphML
+    // file of the same sequence, instead of being parsed from 200 MB of text.
+    const bool halton = mRoadmapName[0] == 'h';
+    unsigned long long first = 1, n = 0;
+    char tail = 0;
+    const int got = halton ? std::sscanf(mRoadmapName.c_str(), "halton:%llu%c", &n, &tail)
+                           : std::sscanf(mRoadmapName.c_str(), "uniform:%llu:%llu%c", &first, &n, &tail);
+    if (got != (halton ? 1 : 2) || n == 0 || n >= 0xFFFFFFF0ull)
+      throw Exception("Roadmap name " + mRoadmapName + " is not halton:<N> or uniform:<seed>:<N>");
+    mRoadmapOwned.assign((size_t)n * mDim, 0.0);
+    BP_DEV(bpomp_roadmap_generate(dev(), halton ? BPOMP_ROADMAP_HALTON : BPOMP_ROADMAP_UNIFORM, first, (uint32_t)n,
+                                  mRoadmapOwned.data()));
+    mRoadmap = mRoadmapOwned.data();
+    mRoadmapEdges.clear();
+    mN = (uint32_t)n;
+  }
   if (mN == 0 && mRoadmapName != "<memory>") {
     // RoadmapFromFile::generateVertices (util/RoadmapFromFile.hpp:136-147)
     std::vector<double> states;

@@ -127,6 +127,18 @@ BPOMP_API int bpomp_states_prune(bpomp_ctx* ctx, const double* states, int64_t c
 BPOMP_API int bpomp_vertices_prune(bpomp_ctx* ctx, uint32_t start_id, uint32_t goal_id, double best_cost,
                                    int check_validity, uint8_t* out);
 
+/* ---- roadmap generation ------------------------------------------------------
+ * The roadmap states a GraphML file would hold (util/RoadmapFromFile.hpp:136-147 reads them as text), generated on
+ * the device and copied to host_out ([count][dim] doubles), for roadmaps that follow this project's two sample
+ * sequences bit for bit:
+ *   BPOMP_ROADMAP_HALTON  point i = first + k (1-based index `first`), coordinate j = radical inverse of i in
+ *                         the j-th prime, evaluated as  f = f / base;  r = r + f * digit  in FP64;
+ *   BPOMP_ROADMAP_UNIFORM coordinate j of point k = (splitmix64(seed = `first`, k*dim + j + 1) >> 11) * 2^-53.
+ * Nothing is added to the vertex table (the planner admits roadmap vertices batch by batch). */
+#define BPOMP_ROADMAP_HALTON 0
+#define BPOMP_ROADMAP_UNIFORM 1
+BPOMP_API int bpomp_roadmap_generate(bpomp_ctx* ctx, int kind, uint64_t first, uint32_t count, double* host_out);
+
 /* ---- vertex table = the elements of mVertexNN ------------------------------------------- */
 
 /* mVertexNN->add — src/BatchingPOMP.cpp:782,789; VertexBatching.hpp:133; EdgeBatching.hpp:146;

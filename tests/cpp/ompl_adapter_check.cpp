@@ -216,6 +216,42 @@ int main(int argc, char** argv) {
     }
     REQUIRE(bad);
   }
+  // ---- generated roadmap (B200 extension): "halton:<N>" names the same roadmap as the GraphML file written above ----
+  {
+    batching_pomp::BatchingPOMP pg(si);
+    REQUIRE(pg.params().setParam("roadmap_filename", "halton:" + std::to_string(N)));
+    REQUIRE(pg.params().setParam("batching_type", "hybrid"));
+    REQUIRE(pg.params().setParam("graph_type", "halton"));
+    REQUIRE(pg.params().setParam("increment", "0.25"));
+    REQUIRE(pg.params().setParam("prune_threshold", "1.05"));
+    auto pdefg = std::make_shared<ob::ProblemDefinition>(si);
+    pdefg->setStartAndGoalStates(start, goal);
+    pg.setProblemDefinition(pdefg);
+    pg.setup();
+    REQUIRE(num_vertices(pg.full_g) == N);
+    for (uint32_t i = 0; i < N; i += 97)
+      REQUIRE(pg.full_g[i].v_state[0] == pts[2 * i] && pg.full_g[i].v_state[1] == pts[2 * i + 1]);
+    long bg = 300;
+    ob::PlannerTerminationCondition ptcg([&bg]() { return --bg < 0; });
+    double cost_g = 1e300;
+    for (int call = 0; call < 30; ++call) {
+      ob::PlannerStatus st = pg.solve(ptcg);
+      if (pdefg->getSolutionCount() > 0) cost_g = pg.getCurrentBestCost();
+      if (st == ob::PlannerStatus::EXACT_SOLUTION || st == ob::PlannerStatus::TIMEOUT) break;
+    }
+    REQUIRE(cost_g == last_cost && pg.getNumSearches() == planner.getNumSearches() &&
+            pg.getNumEdgeChecks() == planner.getNumEdgeChecks());  // the same run as from the file
+    bool badname = false;
+    try {
+      batching_pomp::BatchingPOMP pb(si);
+      pb.params().setParam("roadmap_filename", "halton:abc");
+      pb.params().setParam("batching_type", "vertex");
+      pb.setup();
+    } catch (const ompl::Exception&) {
+      badname = true;
+    }
+    REQUIRE(badname);
+  }
   printf("ompl adapter ok: %d improving solutions, cost %.6f, %u searches\n", improved, last_cost,
          planner.getNumSearches());
   return 0;

@@ -270,6 +270,22 @@ BPOMP_API int bpomp_belief_clear(bpomp_ctx* c) {
   c->bel_vals.clear();
   return BPOMP_OK;
 }
+extern "C" void orc_halton(int64_t first_index, int64_t count, int d, double* out);
+BPOMP_API int bpomp_roadmap_generate(bpomp_ctx* c, int kind, uint64_t first, uint32_t count, double* host_out) {
+  if (!c || (kind != 0 && kind != 1) || (count > 0 && !host_out)) return BPOMP_ERR_INVALID;
+  if (kind == 0) {
+    orc_halton((int64_t)first, (int64_t)count, c->dim, host_out);
+  } else {
+    for (uint64_t t = 0; t < (uint64_t)count * c->dim; ++t) {  // workloads.uniform: splitmix64(seed, t + 1)
+      uint64_t z = first + (t + 1) * 0x9E3779B97F4A7C15ull;
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+      z = z ^ (z >> 31);
+      host_out[t] = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+    }
+  }
+  return BPOMP_OK;
+}
 BPOMP_API int bpomp_belief_append(bpomp_ctx* c, const double* states, const double* values, int64_t count) {
   if (!c || count < 0 || (count > 0 && (!states || !values))) return BPOMP_ERR_INVALID;
   c->bel_pts.insert(c->bel_pts.end(), states, states + (size_t)count * c->dim);

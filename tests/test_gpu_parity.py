@@ -471,6 +471,18 @@ def test_fp32_prefilter_paths_equal_fp64_and_oracle(capi, orc, wl, d, K, M, nq):
         ctx.close()
 
 
+@pytest.mark.parametrize("d,n,first", [(7, 100000, 1), (2, 1000, 1), (3, 5000, 123457), (8, 300, 1)])
+def test_roadmap_generated_on_device_equals_the_file_sequences(capi, orc, wl, d, n, first):
+    """f3: bpomp_roadmap_generate against the two sample sequences as the roadmap files hold them (oracle Halton,
+    splitmix64 uniform): bit for bit."""
+    ctx = capi.Context(d, wl.segment_length(d))
+    np.testing.assert_array_equal(ctx.roadmap_generate("halton", first, n), orc.halton(first, n, d))
+    np.testing.assert_array_equal(ctx.roadmap_generate("halton", first, n), wl.halton(n, d, first_index=first))
+    np.testing.assert_array_equal(ctx.roadmap_generate("uniform", 42 + first, n), wl.uniform(42 + first, (n, d)))
+    assert ctx.roadmap_generate("uniform", 1, 0).shape == (0, d)
+    ctx.close()
+
+
 def _clustered_points(wl, d, M, seed):
     """Belief-like point sets: states strung along segments (checked edges), plus duplicates and a far outlier."""
     rng = np.random.default_rng(seed)
