@@ -37,9 +37,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's banner (printed when NCCL_DEBUG=VERSION is exported) must not join it
-if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# (On this pool NCCL_DEBUG=VERSION is exported, so under torchrun NCCL prints its one-line version banner to stdout
+# before the JSON line; neither NCCL_DEBUG=WARN nor NCCL_DEBUG_FILE moved it, so it is left alone: the JSON line
+# is the last line of stdout.)
 
 from batching_pomp_b200 import workloads  # noqa: E402
 
